@@ -1,0 +1,191 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+What is executed is the reference's own code, imported from where it lies:
+
+  * ``/root/reference/src/env/hedging_env_v2.py`` and ``hedging_env.py`` (class ``HedgingEnv``),
+    through the ~60-line gymnasium stand-in in ``oracle/_gym_stub`` (gymnasium is not installed),
+  * ``/root/reference/src/sim/option_price_assignment.py`` (``black_scholes_vectorized``,
+    ``calculate_annualized_vol_matrix``),
+  * ``/root/reference/src/tools/bs_delta.py`` (``bs_delta_hedge``),
+
+on inputs derived from the reference's shipped ``data/paths.npy`` /
+``data/paths_options.npz``.  Outputs (all small, committed):
+
+  env_<case>.npz         per-step observation / reward / terminated / info of N reference envs
+                         plus the env-schema arrays, the actions and the episode indices they used
+  schema_b_golden.npz    48 shipped paths + the shipped calls/puts for them (reference known-answer pair)
+  bs_delta_golden.npz    bs_delta_hedge P&L of 6 shipped paths
+"""
+import importlib.util
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_gym_stub"))
+sys.path.insert(0, ROOT)
+
+from oracle import bs_oracle  # noqa: E402  (inputs only: ATM book columns fed to the reference env)
+from oracle.hedge_oracle import INFO_FLOAT_KEYS, INFO_INT_KEYS  # noqa: E402
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def env_schema_from_paths(paths, variance_mode="realised", scale=1.0):
+    """Builder's choice of the env-schema columns the reference does not ship."""
+    paths = np.asarray(paths, np.float64) * scale
+    if variance_mode == "realised":
+        sig = bs_oracle.realised_vol_matrix(paths)
+        sig[:, 0] = sig[:, 2]
+        sig[:, 1] = sig[:, 2]
+        var = sig ** 2
+    else:
+        var = np.full_like(paths, 0.02903)          # xi from estimate_base_params on the shipped CSV
+    calls, puts = bs_oracle.atm_book(paths, var)
+    return dict(paths=paths, volatilities=var, call_prices_atm=calls, put_prices_atm=puts)
+
+
+def run_reference_envs(env_cls, data, kwargs, actions, seeds):
+    """Step ``len(seeds)`` unmodified reference envs through ``actions`` (steps, n, 2), resetting on termination."""
+    n = len(seeds)
+    steps = actions.shape[0]
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "schema_a.npz")
+        np.savez(f, **data)
+        envs = [env_cls(f, **kwargs) for _ in range(n)]
+    obs = np.zeros((steps, n, 13), np.float32)
+    reward = np.zeros((steps, n), np.float64)
+    term = np.zeros((steps, n), bool)
+    info_f = np.zeros((steps, n, len(INFO_FLOAT_KEYS)), np.float64)
+    info_i = np.zeros((steps, n, len(INFO_INT_KEYS)), np.int64)
+    reset_obs, episode_idx = [[] for _ in range(n)], [[] for _ in range(n)]
+    for i, e in enumerate(envs):
+        o, _ = e.reset(seed=int(seeds[i]))
+        reset_obs[i].append(o)
+        episode_idx[i].append(int(e.current_episode_idx))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for t in range(steps):
+            for i, e in enumerate(envs):
+                o, r, te, tr, inf = e.step(actions[t, i])
+                assert tr is False
+                obs[t, i], reward[t, i], term[t, i] = o, r, te
+                info_f[t, i] = [float(inf.get(k, np.nan)) for k in INFO_FLOAT_KEYS]   # v1 lacks 3 keys -> NaN
+                info_i[t, i] = [int(inf[k]) for k in INFO_INT_KEYS]
+                if te:
+                    o, _ = e.reset()
+                    reset_obs[i].append(o)
+                    episode_idx[i].append(int(e.current_episode_idx))
+    n_eps = min(len(x) for x in episode_idx)
+    return dict(obs=obs, reward=reward, terminated=term, info_f=info_f, info_i=info_i,
+                reset_obs=np.array([[reset_obs[i][k] for i in range(n)] for k in range(n_eps)], np.float32),
+                episode_idx=np.array([[episode_idx[i][k] for i in range(n)] for k in range(n_eps)], np.int64))
+
+
+def main():
+    env_v2 = _load("ref_env_v2", f"{REF}/src/env/hedging_env_v2.py").HedgingEnv
+    env_v1 = _load("ref_env_v1", f"{REF}/src/env/hedging_env.py").HedgingEnv
+    opa = _load("ref_opa", f"{REF}/src/sim/option_price_assignment.py")
+    bsd = _load("ref_bsd", f"{REF}/src/tools/bs_delta.py")
+
+    shipped = np.load(f"{REF}/data/paths.npy")
+    book = np.load(f"{REF}/data/paths_options.npz")
+    rng = np.random.default_rng(20261018)
+
+    # ---------------------------------------------------------------- env cases
+    n_env = 4
+    seeds = 12345 + np.arange(n_env)                 # train_ppo_v2.py:78 seed base
+
+    def uniform_actions(steps):
+        return rng.uniform(-1, 1, (steps, n_env, 2)).astype(np.float32)
+
+    def saturating_actions(steps):
+        a = rng.choice(np.array([-1.0, 1.0, 1.0, 1.0, 0.3, -0.1, 0.5, 0.7, 3.0, -2.5, 0.0], np.float32),
+                       size=(steps, n_env, 2)).astype(np.float32)
+        a[5, 0, 0] = np.nan
+        a[6, 1, 1] = np.inf
+        a[7, 2, 0] = -np.inf
+        a[8, 3, 1] = 1e30
+        return a
+
+    full = env_schema_from_paths(shipped[:24])
+    short = {k: v[:, : (41 if v.shape[1] == 253 else 40)] for k, v in env_schema_from_paths(shipped[24:40]).items()}
+    const_var = {k: v[:, : (41 if v.shape[1] == 253 else 40)]
+                 for k, v in env_schema_from_paths(shipped[40:56], "const").items()}
+    low = {k: v[:, : (41 if v.shape[1] == 253 else 40)]
+           for k, v in env_schema_from_paths(shipped[56:72], "realised", scale=0.04).items()}
+    tiny = {k: v.copy() for k, v in low.items()}
+    tiny["paths"][0, :] = 0.0                         # S <= 1e-6 branch of _calculate_greeks, S0 -> 1.0
+    tiny["paths"][1, 3:9] = 1e-7
+    tiny["volatilities"][2, :] = 0.0                  # sigma floor sqrt(1e-8)
+    tiny["paths"][3, :] = 0.4                         # K = round(S) = 0 -> K_checked = 1e-6
+
+    cases = {
+        # the training configuration of train_ppo_v2.py:74-80 on full-length episodes
+        "v2_train": (env_v2, full, dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3,
+                                        lambda_cost=1e-4, loss_type="abs"), uniform_actions(2 * 252 + 9)),
+        # v1 defaults (hedging_env.py:10-20)
+        "v1_default": (env_v1, short, dict(), uniform_actions(3 * 40 + 7)),
+        # mse loss, non-zero initial cash, clamps at +-200 / NaN / inf / out-of-range actions
+        "v2_mse_saturating": (env_v2, short, dict(loss_type="mse", pnl_penalty_weight=0.5, initial_cash=1000.0,
+                                                  slippage_bps=2.5, theta_weight=1e-3), saturating_actions(3 * 40 + 7)),
+        # cvar string falls back to abs; no greeks
+        "v2_cvar_nometrics": (env_v2, const_var, dict(loss_type="cvar", record_metrics=False,
+                                                      shares_to_hedge=5000, max_contracts_held_per_type=40,
+                                                      max_trade_per_step=7), uniform_actions(2 * 40 + 5)),
+        # S0 below the 25 floor
+        "v2_lowprice": (env_v2, low, dict(slippage_bps=1.0, transaction_cost_per_contract=0.05),
+                        uniform_actions(2 * 40 + 5)),
+        # degenerate prices / variances
+        "v2_degenerate": (env_v2, {k: v[:4] for k, v in tiny.items()}, dict(slippage_bps=1.0),
+                          uniform_actions(2 * 40 + 5)),
+    }
+    for name, (cls, data, kwargs, actions) in cases.items():
+        out = run_reference_envs(cls, data, kwargs, actions, seeds)
+        kw_items = {f"kw_{k}": np.array(v) for k, v in kwargs.items()}
+        np.savez_compressed(os.path.join(HERE, f"env_{name}.npz"), version=np.array(1 if cls is env_v1 else 2),
+                            actions=actions, seeds=seeds, **data, **out, **kw_items)
+        print(f"env_{name}: steps={actions.shape[0]} episodes={out['episode_idx'].shape[0]} "
+              f"terminations={int(out['terminated'].sum())}")
+
+    # ------------------------------------------------- schema B known-answer pair
+    sl = slice(0, 48)
+    vols = opa.calculate_annualized_vol_matrix(shipped[sl])
+    strikes = np.round(shipped[sl, 0])
+    Tgrid = np.clip(1 - np.arange(shipped.shape[1]) / 252, 0, None)
+    calls = np.zeros_like(shipped[sl])
+    puts = np.zeros_like(shipped[sl])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for t in range(shipped.shape[1]):
+            calls[:, t], puts[:, t] = opa.black_scholes_vectorized(shipped[sl, t], strikes, Tgrid[t], 0.04, vols[:, t])
+    err = np.nanmax(np.abs(calls - book["calls"][sl]))
+    assert err < 1e-11 and np.array_equal(np.isnan(calls), np.isnan(book["calls"][sl])), err
+    np.savez_compressed(os.path.join(HERE, "schema_b_golden.npz"), paths=shipped[sl],
+                        calls_shipped=book["calls"][sl], puts_shipped=book["puts"][sl],
+                        calls_recomputed=calls, puts_recomputed=puts, vols=vols)
+    print(f"schema_b_golden: reference functions reproduce the shipped npz to {err:.2e} abs")
+
+    # ------------------------------------------------------------ bs_delta golden
+    pnl = bsd.bs_delta_hedge(shipped[:6])
+    np.savez_compressed(os.path.join(HERE, "bs_delta_golden.npz"), paths=shipped[:6], pnl=pnl)
+    print("bs_delta_golden: 6 paths")
+
+
+if __name__ == "__main__":
+    main()
