@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Benchmark of the fused hedge step (BASELINE.json metric: env-steps/sec, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): 2^20 synthetic GBM paths x 252 steps per GPU, one European ATM call
+(put leg forced to 0), proportional transaction cost (slippage_bps = 1) + commission, the v2 training
+reward weights (src/agents/train_ppo_v2.py:74-80).  One bench "step" = one full episode sweep = 252
+launches of the fused hedge-step kernel over all envs (ends with the auto-reset of every env).
+
+  value     env-steps/s with everything resident in HBM, replay mode, fp32 state (137 algorithmic B/env-step);
+            actions are read from, and obs/reward/done written to, [T, n_envs, ...] rollout slabs, so every
+            launch touches fresh lines (inputs >> L2).
+  e2e       the same 252-step sweep through the gym-style API with HOST buffers: every step copies that
+            step's actions from pinned host memory and brings obs/reward/done back to pinned host memory.
+  roofline  137 B x n_envs per launch / mean launch duration (CUDA events over the timed region), against the
+            measured HBM copy peak in MEASURED_PEAKS.json.
+  cpu_baseline  the scalar reference-shaped port (oracle/hedge_scalar.py) on the host cores of this box.
+
+Multi-GPU (torchrun, one rank per GPU): envs are sharded by global path index, no data-path collective
+(weak scaling: 2^20 envs per GPU); time is the max over ranks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = {"fp32": 137, "fp64": 157}          # algorithmic bytes per env-step, replay mode
+ENV_KW = dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3, lambda_cost=1e-4,
+              transaction_cost_per_contract=0.65, loss_type="abs")            # train_ppo_v2.py:74-80
+R, DT, S0, XI = 0.04, 1 / 252, 100.0, 0.04                                      # rbergomi_sim.py:13,14,27,23
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cantor", choices=["cantor", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--episode-length", type=int, default=252)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--e2e-steps", type=int, default=2, help="episode sweeps timed through the host-buffer API")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- CPU legs
+def _cpu_book(n_paths=4096, T=252, seed=42):
+    """Env-schema arrays with the GPU config's dynamics, NumPy."""
+    from oracle import bs_oracle
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((n_paths, T))
+    logS = np.cumsum((R - 0.5 * XI) * DT + np.sqrt(XI * DT) * z, axis=1)
+    S = S0 * np.exp(np.concatenate([np.zeros((n_paths, 1)), logS], axis=1))
+    V = np.full_like(S, XI)
+    Cc, Pp = bs_oracle.atm_book(S, V)
+    return S, V, Cc, Pp
+
+
+def _cpu_worker(args):
+    seconds, seed = args
+    from oracle.hedge_oracle import EnvParams
+    from oracle.hedge_scalar import time_scalar_env
+    S, V, Cc, Pp = _cpu_book(256, 252, 42)
+    return time_scalar_env(S, V, Cc, Pp, EnvParams(**ENV_KW), seconds, seed)
+
+
+def cpu_baseline(seconds, procs):
+    """P forked processes, one scalar env each: the reference's SubprocVecEnv model without the pipes."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(seconds, i) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    rate = sum(r[0] / r[1] for r in res)
+    return dict(value=rate, unit="env-steps/s", cores=procs, kind="port",
+                sample=f"{procs} processes x 1 scalar reference-shaped env (oracle/hedge_scalar.py), greeks on, "
+                       f"uniform float32 actions, {steps} env-steps in {wall:.1f} s wall on 256 GBM paths x 252 steps",
+                cpu=_cpu_model())
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference-shaped CPU port on all host cores; one 'step' = one 252-step episode per process."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle.hedge_oracle import EnvParams
+    from oracle.hedge_scalar import ScalarEnv
+    procs = os.cpu_count() or 1
+    T = args.episode_length
+    ctx = mp.get_context("fork")
+    S, V, Cc, Pp = _cpu_book(256, T, 42)
+
+    def episode_batch(seed):
+        env = ScalarEnv(S, V, Cc, Pp, EnvParams(**ENV_KW), seed=seed)
+        acts = np.random.default_rng(seed).uniform(-1, 1, (T, 2)).astype(np.float32)
+        acts[:, 1] = 0.0
+        env.reset()
+        n = 0
+        for a in acts:
+            _, _, term, _, _ = env.step(a)
+            n += 1
+            if term:
+                env.reset()
+        return n
+
+    global _episode_batch
+    _episode_batch = episode_batch
+    with ctx.Pool(procs) as pool:
+        for w in range(args.warmup):
+            pool.map(_call_episode_batch, range(procs))
+        t0 = time.perf_counter()
+        total = 0
+        for k in range(args.steps):
+            total += sum(pool.map(_call_episode_batch, range(k * procs, (k + 1) * procs)))
+        el = time.perf_counter() - t0
+    value = total / el
+    sample = f"{procs} processes x 1 scalar env x {T} steps per bench step; {total} env-steps in {el:.1f} s"
+    line = dict(impl="reference", metric="env-steps/sec (fused hedge step)", value=value, unit="env-steps/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / max(args.steps, 1),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=_config(args, world), gpu_launches=0,
+                cpu_baseline=dict(value=value, unit="env-steps/s", cores=procs, kind="port", sample=sample, cpu=_cpu_model()),
+                e2e=dict(value=value, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+_episode_batch = None
+
+
+def _call_episode_batch(seed):
+    return _episode_batch(seed)
+
+
+# --------------------------------------------------------------------------------------------- GPU side
+def _config(args, world):
+    return dict(workload=f"configs[1]: {args.envs} synthetic GBM paths x {args.episode_length} steps per GPU, one European "
+                         "ATM call (put action 0), commission 0.65 + slippage 1 bp, v2 reward (w=1e-3, lam=1e-4, theta=2e-4)",
+                mode="replay", envs_per_gpu=args.envs, episode_length=args.episode_length, precision=args.precision,
+                policy="uniform random float32 actions, pre-generated on device", parallelism=f"path-sharded x{world}",
+                l2="inputs larger than L2: each launch reads/writes fresh [t] slabs of 4.2 GB replay + 17 GB rollout buffers")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) == 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) == 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[j] for r in self.rows if len(r) == 7 for j in range(4) if r[3 + j].lower() == "active"})
+        pw = [float(r[2]) for r in self.rows if len(r) == 7 and r[2].replace(".", "").isdigit()]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=reasons)
+
+
+def synth_replay_data(n, T, seed, device):
+    """Synthetic env-schema arrays of configs[1], generated on the device (setup, untimed)."""
+    import torch
+    from cantorrl_b200 import ReplayData
+    g = torch.Generator(device=device).manual_seed(seed)
+    S = torch.empty((T + 1, n), dtype=torch.float32, device=device)
+    logS = torch.zeros(n, dtype=torch.float64, device=device)
+    S[0] = S0
+    for t in range(1, T + 1):
+        z = torch.randn(n, dtype=torch.float32, device=device, generator=g).double()
+        logS += (R - 0.5 * XI) * DT + (XI * DT) ** 0.5 * z
+        S[t] = (S0 * torch.exp(logS)).float()
+    v = torch.full((T + 1, n), XI, dtype=torch.float32, device=device)
+    Sd = S[:T].double()
+    K = torch.round(Sd)
+    tenor, sig = 30 / 252, XI ** 0.5
+    d1 = (torch.log(Sd / K) + (R + 0.5 * sig * sig) * tenor) / (sig * tenor ** 0.5)
+    d2 = d1 - sig * tenor ** 0.5
+    Phi = lambda x: 0.5 * torch.erfc(-x / 2 ** 0.5)   # noqa: E731
+    disc = float(np.exp(-R * tenor))
+    Cc = (Sd * Phi(d1) - K * disc * Phi(d2)).float()
+    Pp = (K * disc * Phi(-d2) - Sd * Phi(-d1)).float()
+    return ReplayData(S, v, Cc.contiguous(), Pp.contiguous(), n_paths=n)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cantorrl_b200 import HedgingVecEnv, _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, T, K, W = args.envs, args.episode_length, args.steps, args.warmup
+    L = _lib.lib()
+
+    data = synth_replay_data(n, T, 42 + rank, dev)
+    env = HedgingVecEnv(data=data, num_envs=n, device=dev, precision=args.precision, episode_sampler="same_path",
+                        env_offset=rank * n, **ENV_KW)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    actions = torch.rand((T, n, 2), device=dev, generator=g) * 2 - 1
+    actions[:, :, 1] = 0.0                                        # one European call: the put leg is never traded
+    rdt = torch.float64 if args.precision == "fp64" else torch.float32
+    obs = torch.empty((T, n, 13), dtype=torch.float32, device=dev)
+    reward = torch.empty((T, n), dtype=rdt, device=dev)
+    done = torch.empty((T, n), dtype=torch.uint8, device=dev)
+    env.reset()
+    stream = torch.cuda.current_stream(dev)
+
+    def sweep():
+        _lib.check(L.cantor_env_step_many(C.byref(env._params), C.byref(env._book), C.byref(env._state), n, env._prec, T,
+                                          actions.data_ptr(), obs.data_ptr(), reward.data_ptr(), done.data_ptr(), None,
+                                          C.byref(env._rule), stream.cuda_stream), "cantor_env_step_many")
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(W, 3)):
+        sweep()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        sweep()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    assert bool(done[T - 1].all()) and not bool(done[T - 2].any()), "episode boundary not where expected"
+    assert bool(torch.isfinite(reward).all()) and bool(torch.isfinite(obs[T - 1]).all())
+
+    # ---- e2e: gym-style step with host buffers (pinned), copies inside the timed region --------------------
+    a_host = actions.cpu().pin_memory()
+    obs_h = torch.empty((n, 13), dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(n, dtype=rdt).pin_memory()
+    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    a_dev = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    env.reset()
+
+    def e2e_sweep():
+        for t in range(T):
+            a_dev.copy_(a_host[t], non_blocking=True)
+            o, r, d, _ = env.step(a_dev)
+            obs_h.copy_(o, non_blocking=True)
+            rew_h.copy_(r, non_blocking=True)
+            done_h.copy_(d.view(torch.uint8), non_blocking=True)
+            stream.synchronize()                       # the caller needs this step's obs before it can act again
+
+    e2e_sweep()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_sweep()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks ------------------------------------------------------------------------------------
+    tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(tt[0]), float(tt[1])
+    if rank == 0:
+        env_steps = float(n) * world * T * K
+        value = env_steps / (ms * 1e-3)
+        launch_ms = ms / (K * T)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        achieved = B_ALG[args.precision] * n / (launch_ms * 1e-3) / 1e9
+        line = dict(
+            metric="env-steps/sec (fused hedge step)", value=value, unit="env-steps/s", n_gpus=world, steps=K, warmup=max(W, 3),
+            ms_per_step=ms / K, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f32" if args.precision == "fp32" else "f64", data="synthetic", config=_config(args, world),
+            gpu_launches=K * T,
+            roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                          kernel="hedge_step_kernel<F64=%s,INFO=false>" % ("true" if args.precision == "fp64" else "false"),
+                          algorithmic_bytes_per_env_step=B_ALG[args.precision], launch_us=launch_ms * 1e3, peak_source=peak_src),
+            e2e=dict(value=float(n) * world * T * args.e2e_steps / e2e_s, unit="env-steps/s",
+                     h2d_bytes_per_step=n * 8 * T, d2h_bytes_per_step=n * (52 + reward.element_size() + 1) * T,
+                     api="HedgingVecEnv.step with pinned host action/obs/reward/done buffers, synchronised every env step"),
+            clocks=clocks)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,122 @@
+"""ctypes binding of ``libcantor_hedge.so`` (the C ABI declared in ``include/cantor_hedge.h``).
+
+The library is built in-tree by ``cantorrl_b200/csrc/Makefile`` (see ``__graft_entry__.build``).
+There is NO fallback: if the shared object is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libcantor_hedge.so")
+
+OBS_DIM = 13
+F32, F64 = 32, 64
+LOSS_ABS, LOSS_MSE = 0, 1
+RESET_SAME_PATH, RESET_FROM_ARRAY, RESET_PHILOX = 0, 1, 2
+INFO_F64_KEYS = (
+    "step_pnl_total", "per_share_step_pnl", "raw_pnl_deviation_abs", "transaction_costs_total",
+    "commission_cost", "slippage_cost", "reward_pnl_component", "transaction_cost_penalty", "theta_penalty",
+    "reward_step", "portfolio_value", "cash", "raw_action_call", "raw_action_put", "scaled_float_call",
+    "scaled_float_put", "initial_S0_for_episode",
+)
+INFO_I32_KEYS = (
+    "call_contracts", "put_contracts", "requested_calls_rounded_clipped", "requested_puts_rounded_clipped",
+    "actual_calls_traded", "actual_puts_traded",
+)
+
+
+class CantorError(RuntimeError):
+    """A libcantor_hedge call returned a non-zero status."""
+
+
+class EnvParams(C.Structure):
+    _fields_ = [
+        ("transaction_cost_per_contract", C.c_double), ("lambda_cost", C.c_double),
+        ("pnl_penalty_weight", C.c_double), ("theta_weight", C.c_double), ("slippage_bps", C.c_double),
+        ("initial_cash", C.c_double), ("risk_free_rate", C.c_double), ("option_tenor_years", C.c_double),
+        ("loss_type", C.c_int32), ("shares_to_hedge", C.c_int32), ("max_contracts_held", C.c_int32),
+        ("max_trade_per_step", C.c_int32), ("option_contract_multiplier", C.c_int32), ("record_metrics", C.c_int32),
+    ]
+
+
+class ReplayBook(C.Structure):
+    _fields_ = [("S", C.c_void_p), ("v", C.c_void_p), ("C", C.c_void_p), ("P", C.c_void_p),
+                ("ld", C.c_int64), ("n_paths", C.c_int32), ("episode_length", C.c_int32)]
+
+
+class EnvState(C.Structure):
+    _fields_ = [("core", C.c_void_p), ("cash", C.c_void_p), ("pv_prev", C.c_void_p)]
+
+
+class ResetRule(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("next_path", C.c_void_p),
+                ("seed", C.c_uint64), ("env_offset", C.c_int64), ("episode_counter", C.c_int64)]
+
+
+class InfoOut(C.Structure):
+    _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/cantor_hedge.h declares must appear here
+SIGNATURES = {
+    "cantor_abi_version": (C.c_int, []),
+    "cantor_last_error": (C.c_char_p, []),
+    "cantor_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_size_t)]),
+    "cantor_env_reset": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_env_step": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
+                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.POINTER(ResetRule), C.POINTER(InfoOut), C.c_void_p]),
+    "cantor_env_step_many": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.POINTER(ResetRule), C.c_void_p]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a with nvcc (cross-compiles without a GPU)."""
+    proc = subprocess.run(["make", "-C", CSRC, f"-j{min(8, os.cpu_count() or 1)}"], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise CantorError(f"building libcantor_hedge.so failed:\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(proc.stdout)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """The loaded shared library.  Raises if it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CantorError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(nvcc, sm_100a). cantorrl_b200 has no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)            # AttributeError if the symbol is not exported
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().cantor_last_error().decode(errors="replace")
+        raise CantorError(f"{what or 'libcantor_hedge'} failed with status {status}: {msg}")
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, or None."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,55 @@
+// Shared host/device helpers for libcantor_hedge.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cantor_hedge.h"
+
+namespace cantor {
+
+// ---- per-thread last error ---------------------------------------------------------------------
+inline char* error_buffer() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(error_buffer(), 512, fmt, a, b);
+    return code;
+}
+inline int cuda_fail(cudaError_t e, const char* where) {
+    return fail(CANTOR_ERR_CUDA, "%s: %s", where, cudaGetErrorString(e));
+}
+#define CANTOR_REQUIRE(cond, msg) \
+    do { if (!(cond)) return ::cantor::fail(CANTOR_ERR_INVALID, "%s: %s", __func__, msg); } while (0)
+#define CANTOR_CUDA(call) \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ::cantor::cuda_fail(e_, #call); } while (0)
+
+inline int check_launch(const char* kernel) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, kernel);
+    return CANTOR_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- streaming loads/stores: every byte of the hot path is touched once per step ------------------
+__device__ __forceinline__ float ldg_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ int4 ldg_stream(const int4* p) { return __ldcs(p); }
+__device__ __forceinline__ float2 ldg_stream(const float2* p) { return __ldcs(p); }
+
+// ---- 1-D TMA bulk store shared::cta -> global (SASS: UBLKCP) ---------------------------------------
+// Caller guarantees 16-byte aligned src/dst and bytes % 16 == 0.
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the bulk copies have finished READING shared memory (the CTA may then exit / reuse it)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace cantor

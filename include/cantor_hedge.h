@@ -1,0 +1,159 @@
+/*
+ * cantor_hedge.h  --  C ABI of libcantor_hedge.so (hand-written sm_100a CUDA kernels)
+ *
+ * Drop-in boundary for the ONE data-parallel hot path of bcosm/CantorRL:
+ *
+ *   src/env/hedging_env_v2.py   HedgingEnv.reset / step / _get_observation / _calculate_greeks
+ *   src/env/hedging_env.py      (v1 = v2 with slippage_bps = 0, theta_weight = 0, commission 0.05)
+ *   src/sim/rbergomi_sim.py     outer log-Euler path step + output schema (:454-464, :528)
+ *   src/sim/option_price_assignment.py   Black-Scholes repricing along paths (:10-52)
+ *   src/tools/bs_delta.py       single-call Black-Scholes delta hedge (:11-55)
+ *
+ * The reference has no FFI of its own (it is pure Python); the entry points below are what a
+ * ctypes/cffi binding of that path binds instead of the Python methods cited at each function.
+ *
+ * Conventions
+ *   - Every function returns 0 (CANTOR_OK) or a CANTOR_ERR_* code; cantor_last_error() returns the
+ *     message of the last failure on the calling thread.  Kernels never trap.
+ *   - Unless a function name ends in _host, every pointer is a DEVICE pointer owned by the caller
+ *     (e.g. torch.Tensor.data_ptr()); nothing is allocated, freed or synchronised inside a call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous.
+ *   - Path/option arrays are TIME-MAJOR: element (t, path) lives at [t * ld + path].  One warp reads
+ *     32 consecutive paths of one time slab = one 128-byte line.
+ *   - precision = CANTOR_F32 : float cash / reward, float Black-Scholes; 137 algorithmic bytes per env-step.
+ *     precision = CANTOR_F64 : double cash / portfolio value / reward with the reference's exact
+ *     float32/float64 operation ledger (bit-exact integers, <= 1e-6 relative on every float); 157 B.
+ */
+#ifndef CANTOR_HEDGE_H
+#define CANTOR_HEDGE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CANTOR_ABI_VERSION 1
+#define CANTOR_OBS_DIM 13            /* hedging_env_v2.py:138-142 */
+
+enum {
+    CANTOR_OK = 0,
+    CANTOR_ERR_INVALID = 1,          /* bad argument (NULL pointer, size, alignment, enum) */
+    CANTOR_ERR_CUDA = 2,             /* a CUDA runtime call failed; message has the CUDA error string */
+    CANTOR_ERR_NO_DEVICE = 3,        /* no usable sm_100 device */
+    CANTOR_ERR_SHAPE = 4             /* "Data shapes are inconsistent." (hedging_env_v2.py:45-48) */
+};
+
+enum { CANTOR_F32 = 32, CANTOR_F64 = 64 };
+enum { CANTOR_LOSS_ABS = 0, CANTOR_LOSS_MSE = 1 };   /* "cvar"/unknown strings use ABS (hedging_env_v2.py:250-253) */
+
+/* How a finished env picks its next episode (hedging_env_v2.py:150 draws np_random.integers(num_episodes)). */
+enum {
+    CANTOR_RESET_SAME_PATH = 0,      /* keep the current path index (env i replays path i: sharded-by-path runs) */
+    CANTOR_RESET_FROM_ARRAY = 1,     /* next_path[i], supplied by the host (e.g. the reference's PCG64 draws) */
+    CANTOR_RESET_PHILOX = 2          /* Philox4x32-10(seed; env_offset + i, episode counter) mod n_paths */
+};
+
+/* HedgingEnv.__init__ keyword arguments (hedging_env_v2.py:10-22) and constants (:56-58). */
+typedef struct cantor_env_params {
+    double transaction_cost_per_contract;   /* 0.65 (v2) / 0.05 (v1) */
+    double lambda_cost;                     /* 1.0 */
+    double pnl_penalty_weight;              /* 0.01 */
+    double theta_weight;                    /* 0.0 */
+    double slippage_bps;                    /* 0.0 */
+    double initial_cash;                    /* 0.0 */
+    double risk_free_rate;                  /* 0.04      (:57) */
+    double option_tenor_years;              /* 30 / 252  (:58) */
+    int32_t loss_type;                      /* CANTOR_LOSS_* */
+    int32_t shares_to_hedge;                /* 10000 */
+    int32_t max_contracts_held;             /* 200, must be <= 32767 */
+    int32_t max_trade_per_step;             /* 15 */
+    int32_t option_contract_multiplier;     /* 100 (:56) */
+    int32_t record_metrics;                 /* 1; 0 zeroes obs[7:11] (:80-81) */
+} cantor_env_params;
+
+/* Env-schema arrays of the reference npz (hedging_env_v2.py:36-48), float32, time-major in HBM. */
+typedef struct cantor_replay_book {
+    const float* S;        /* 'paths'            [(T+1) * ld] */
+    const float* v;        /* 'volatilities'     [(T+1) * ld]  (instantaneous VARIANCE, :84) */
+    const float* C;        /* 'call_prices_atm'  [T * ld] */
+    const float* P;        /* 'put_prices_atm'   [T * ld] */
+    int64_t ld;            /* leading dimension in elements, >= n_paths */
+    int32_t n_paths;       /* num_episodes   (:50) */
+    int32_t episode_length;/* T = paths.shape[1] - 1 (:51) */
+} cantor_replay_book;
+
+/* Per-env state, struct of arrays, caller-owned.  Packed so one env-step moves 20 B (F32) of state each way. */
+typedef struct cantor_env_state {
+    int32_t* core;         /* [n_envs * 4] 16-byte records {pos, step, path, s0}:
+                              pos  = call contracts (low int16) | put contracts (high int16)
+                              step = current_step, path = current_episode_idx,
+                              s0   = float bits of initial_S0_for_episode (after the < 1e-6 -> 1.0 rule, :157) */
+    void* cash;            /* [n_envs] float (F32) or double (F64): cash_balance */
+    double* pv_prev;       /* [n_envs] F64 only: portfolio_value_t_minus_1; NULL in F32 mode */
+} cantor_env_state;
+
+typedef struct cantor_reset_rule {
+    int32_t mode;              /* CANTOR_RESET_* */
+    int32_t reserved;
+    const int32_t* next_path;  /* [n_envs] for FROM_ARRAY, else NULL */
+    uint64_t seed;             /* PHILOX key */
+    int64_t env_offset;        /* global index of local env 0 (rank * n_envs): results independent of GPU count */
+    int64_t episode_counter;   /* PHILOX: a number that changes between steps (e.g. the global step count) */
+} cantor_reset_rule;
+
+/* Optional per-step diagnostics = the numeric keys of the info dict (hedging_env_v2.py:268-293).
+ * Key-major: value of key k for env i at [k * n_envs + i].  Pass NULL to skip (the fast path). */
+#define CANTOR_INFO_F64_KEYS 17
+#define CANTOR_INFO_I32_KEYS 6
+typedef struct cantor_info_out {
+    double* f64;   /* [17 * n_envs]: step_pnl_total, per_share_step_pnl, raw_pnl_deviation_abs, transaction_costs_total,
+                      commission_cost, slippage_cost, reward_pnl_component, transaction_cost_penalty, theta_penalty,
+                      reward_step, portfolio_value, cash, raw_action_call, raw_action_put, scaled_float_call,
+                      scaled_float_put, initial_S0_for_episode */
+    int32_t* i32;  /* [6 * n_envs]: call_contracts, put_contracts, requested_calls_rounded_clipped,
+                      requested_puts_rounded_clipped, actual_calls_traded, actual_puts_traded */
+} cantor_info_out;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int cantor_abi_version(void);
+const char* cantor_last_error(void);
+/* Writes "sm_XY" style facts about device `device`; returns CANTOR_ERR_NO_DEVICE without a GPU. */
+int cantor_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---- K3: fused hedge step (replay mode) ------------------------------------------------------------
+ * Replaces HedgingEnv.reset (hedging_env_v2.py:145-173) for the envs with mask[i] != 0 (mask NULL = all).
+ * The episode index of env i is path_idx[i] (the value the reference draws at :150).
+ * Writes the reset observation to obs[i*13 .. i*13+12] for those envs; other rows are left untouched. */
+int cantor_env_reset(const cantor_env_params* params, const cantor_replay_book* book,
+                     const cantor_env_state* state, int64_t n_envs, int32_t precision,
+                     const uint8_t* mask, const int32_t* path_idx, float* obs, void* stream);
+
+/* Replaces HedgingEnv.step (hedging_env_v2.py:175-294) + _get_observation (:109-143) + _calculate_greeks
+ * (:79-107) for n_envs envs in ONE kernel: action -> trade -> commission/slippage -> cash -> advance ->
+ * mark-to-market -> P&L reward -> done -> (auto_reset) reset of finished envs -> observation.
+ *   actions      [n_envs, 2] float32 (call, put) in [-1, 1] (unclipped values behave as in the reference)
+ *   obs          [n_envs, 13] float32; with auto_reset the row of a finished env is its RESET observation
+ *   reward       [n_envs] float (F32) / double (F64)
+ *   done         [n_envs] uint8: terminated (truncated is always False, :221)
+ *   terminal_obs [n_envs, 13] or NULL: pre-reset observation, written only for finished envs
+ * With auto_reset = 0 a finished env stays at current_step = T and reports done again if stepped. */
+int cantor_env_step(const cantor_env_params* params, const cantor_replay_book* book,
+                    const cantor_env_state* state, int64_t n_envs, int32_t precision,
+                    const float* actions, float* obs, void* reward, uint8_t* done, float* terminal_obs,
+                    int32_t auto_reset, const cantor_reset_rule* reset_rule, const cantor_info_out* info,
+                    void* stream);
+
+/* n_steps consecutive cantor_env_step calls (auto_reset on, no info) launched back to back from C, for open-loop
+ * action sequences / rollout storage: step t reads actions[t] and writes obs[t], reward[t], done[t] of
+ * [n_steps, n_envs, ...] buffers.  Same kernel, no Python between launches.  terminal_obs is [n_envs, 13] or NULL. */
+int cantor_env_step_many(const cantor_env_params* params, const cantor_replay_book* book,
+                         const cantor_env_state* state, int64_t n_envs, int32_t precision, int32_t n_steps,
+                         const float* actions, float* obs, void* reward, uint8_t* done, float* terminal_obs,
+                         const cantor_reset_rule* reset_rule, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CANTOR_HEDGE_H */

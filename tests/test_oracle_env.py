@@ -124,3 +124,24 @@ def test_oracle_matches_live_reference(version):
                 o_ref, _ = ref.reset()
                 o = orc.reset([ref.current_episode_idx])
                 np.testing.assert_array_equal(o[0], o_ref)
+
+
+def test_scalar_port_matches_golden():
+    """The scalar, reference-shaped port that bench.py times as the CPU baseline computes the golden numbers too."""
+    from conftest import load_env_case
+    from oracle.hedge_scalar import ScalarEnv
+    z, kwargs, _ = load_env_case("v2_mse_saturating")
+    env = ScalarEnv(z["paths"], z["volatilities"], z["call_prices_atm"], z["put_prices_atm"], EnvParams(**kwargs),
+                    seed=int(z["seeds"][1]))
+    obs, _ = env.reset()
+    assert env.idx == z["episode_idx"][0, 1]
+    np.testing.assert_array_equal(obs, z["reset_obs"][0, 1])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for t in range(z["actions"].shape[0]):
+            obs, r, term, trunc, info = env.step(z["actions"][t, 1])
+            assert r == z["reward"][t, 1] and term == z["terminated"][t, 1] and trunc is False
+            np.testing.assert_array_equal(obs, z["obs"][t, 1])
+            assert info["call_contracts"] == z["info_i"][t, 1, 0]
+            if term:
+                env.reset()
