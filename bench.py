@@ -220,7 +220,7 @@ def synth_replay_data(n, T, seed, device):
     disc = float(np.exp(-R * tenor))
     Cc = (Sd * Phi(d1) - K * disc * Phi(d2)).float()
     Pp = (K * disc * Phi(-d2) - Sd * Phi(-d1)).float()
-    return ReplayData(S, v, Cc.contiguous(), Pp.contiguous(), n_paths=n)
+    return ReplayData.from_time_major(S, v, Cc, Pp)
 
 
 def main():
@@ -302,13 +302,15 @@ def main():
             done_h.copy_(d.view(torch.uint8), non_blocking=True)
             stream.synchronize()                       # the caller needs this step's obs before it can act again
 
-    e2e_sweep()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    e2e_s = float("inf")
+    if args.e2e_steps > 0:
         e2e_sweep()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_sweep()
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------
     tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)

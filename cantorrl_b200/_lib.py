@@ -11,7 +11,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libcantor_hedge.so")
+# CANTOR_HEDGE_LIB selects another build of the same library (kernel-variant sweeps, profiling builds)
+LIB_PATH = os.environ.get("CANTOR_HEDGE_LIB") or os.path.join(CSRC, "libcantor_hedge.so")
 
 OBS_DIM = 13
 F32, F64 = 32, 64
@@ -44,8 +45,7 @@ class EnvParams(C.Structure):
 
 
 class ReplayBook(C.Structure):
-    _fields_ = [("S", C.c_void_p), ("v", C.c_void_p), ("C", C.c_void_p), ("P", C.c_void_p),
-                ("ld", C.c_int64), ("n_paths", C.c_int32), ("episode_length", C.c_int32)]
+    _fields_ = [("svcp", C.c_void_p), ("ld", C.c_int64), ("n_paths", C.c_int32), ("episode_length", C.c_int32)]
 
 
 class EnvState(C.Structure):
@@ -67,6 +67,10 @@ SIGNATURES = {
     "cantor_last_error": (C.c_char_p, []),
     "cantor_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(C.c_size_t)]),
+    "cantor_pack_book": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p, C.c_int64, C.c_void_p]),
+    "cantor_unpack_book": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_env_reset": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_env_step": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,

@@ -10,6 +10,33 @@ namespace cantor {
 
 constexpr double kInvSqrt2Pi = 0.3989422804014326779;   // 1/sqrt(2*pi)
 constexpr double kSqrtHalf = 0.7071067811865475244;
+constexpr float kLn2f = 0.6931471805599453f;
+constexpr float kLog2ef = 1.4426950408889634f;
+
+// ---- SFU (MUFU) primitives: one instruction each, ~1-2 ulp ------------------------------------------
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Standard normal pdf and cdf in float32 on the SFU + FP32 pipes.
+// cdf: Abramowitz & Stegun 26.2.17 (|error| < 7.5e-8), sharing the exponential with the pdf:
+//   Q(|x|) = phi(x) * t (b1 + t (b2 + t (b3 + t (b4 + t b5)))),  t = 1 / (1 + p |x|).
+// Returns phi(x); *cdf = Phi(x); *cdf_m1 = Phi(x) - 1 without cancellation for x >= 0.
+__device__ __forceinline__ float normal_pdf_cdf(float x, float* cdf, float* cdf_m1) {
+    const float ax = fabsf(x);
+    const float t = mufu_rcp(fmaf(0.2316419f, ax, 1.0f));
+    const float pdf = mufu_ex2(-0.5f * kLog2ef * x * x) * (float)kInvSqrt2Pi;
+    float poly = fmaf(t, 1.330274429f, -1.821255978f);
+    poly = fmaf(t, poly, 1.781477937f);
+    poly = fmaf(t, poly, -0.356563782f);
+    poly = fmaf(t, poly, 0.319381530f);
+    const float q = pdf * (poly * t);                 // upper tail of |x|
+    const bool pos = x >= 0.f;
+    *cdf = pos ? 1.0f - q : q;
+    *cdf_m1 = pos ? -q : q - 1.0f;
+    return pdf;
+}
 
 struct Greeks {
     float call_delta, gamma, put_delta;
@@ -19,17 +46,14 @@ struct Greeks {
 struct GreekConsts {
     float r_f;          // (float) risk_free_rate           -- python float is weak next to float32
     float T_f;          // (float) option_tenor_years
-    float sqrtT_f;      // (float) sqrt(T)
+    float inv_sqrtT_f;  // 1 / sqrt(T)
     double sqrtT_d;     // sqrt(T) in float64 (np.sqrt of a python float)
     double T_d;
     int record_metrics;
 };
 
-// hedging_env_v2.py:79-107.  S, K = rint(S), v_spot float32.
-// F64 = true follows the reference's ledger: float32 numerator, float64 denominator, float64 Phi / phi.
-// F64 = false is the throughput path: float32 everywhere, erfcf + one MUFU.EX2 for phi.
-template <bool F64>
-__device__ __forceinline__ Greeks atm_greeks(float S, float K, float v_spot, const GreekConsts& g) {
+// hedging_env_v2.py:79-107, float64 ledger: float32 numerator, float64 denominator, float64 Phi / phi.
+__device__ __forceinline__ Greeks atm_greeks_f64(float S, float K, float v_spot, const GreekConsts& g) {
     Greeks out{0.f, 0.f, 0.f};
     if (!g.record_metrics) return out;                                         // :80-81
     const float sigma = __fsqrt_rn(fmaxf(v_spot, 1e-8f));                      // :84 (>= 1e-4, so :90's sigma test never fires)
@@ -44,30 +68,47 @@ __device__ __forceinline__ Greeks atm_greeks(float S, float K, float v_spot, con
         return out;
     }
     const float Kc = fmaxf(K, 1e-6f);                                          // :94
-    if (F64) {
-        // float32 numerator exactly as NumPy evaluates it (no FMA contraction)
-        const float drift = __fmul_rn(__fadd_rn(g.r_f, __fmul_rn(0.5f, __fmul_rn(sigma, sigma))), g.T_f);
-        const float num = __fadd_rn(logf(__fdiv_rn(S, Kc)), drift);
-        const double sst = __dmul_rn((double)sigma, g.sqrtT_d);               // :95 float32 * float64
-        double d1;
-        if (sst < 1e-9) d1 = (num > 0.f ? 10.0 : (num < 0.f ? -10.0 : 0.0));   // :96-97
-        else d1 = (double)num / sst;                                           // :99
-        const double cdf = 0.5 * erfc(-d1 * kSqrtHalf);                        // norm.cdf
-        out.call_delta = (float)cdf;
-        out.put_delta = (float)(cdf - 1.0);                                    // :101
-        const double den = __dmul_rn((double)S, sst);                          // :102
-        out.gamma = (fabs(den) < 1e-9) ? 0.f : (float)(exp(-0.5 * d1 * d1) * kInvSqrt2Pi / den);   // :103-106
-    } else {
-        const float num = logf(S / Kc) + (g.r_f + 0.5f * sigma * sigma) * g.T_f;
-        const float sst = sigma * g.sqrtT_f;
-        const float inv_sst = __frcp_rn(sst);
-        const float d1 = num * inv_sst;
-        const float cdf = 0.5f * erfcf(-d1 * (float)kSqrtHalf);
-        out.call_delta = cdf;
-        out.put_delta = cdf - 1.f;
-        const float pdf = __expf(-0.5f * d1 * d1) * (float)kInvSqrt2Pi;
-        out.gamma = pdf * inv_sst / S;
+    // float32 numerator exactly as NumPy evaluates it (no FMA contraction)
+    const float drift = __fmul_rn(__fadd_rn(g.r_f, __fmul_rn(0.5f, __fmul_rn(sigma, sigma))), g.T_f);
+    const float num = __fadd_rn(logf(__fdiv_rn(S, Kc)), drift);
+    const double sst = __dmul_rn((double)sigma, g.sqrtT_d);                    // :95 float32 * float64
+    double d1;
+    if (sst < 1e-9) d1 = (num > 0.f ? 10.0 : (num < 0.f ? -10.0 : 0.0));        // :96-97
+    else d1 = (double)num / sst;                                               // :99
+    const double cdf = 0.5 * erfc(-d1 * kSqrtHalf);                            // norm.cdf
+    out.call_delta = (float)cdf;
+    out.put_delta = (float)(cdf - 1.0);                                        // :101
+    const double den = __dmul_rn((double)S, sst);                              // :102
+    out.gamma = (fabs(den) < 1e-9) ? 0.f : (float)(exp(-0.5 * d1 * d1) * kInvSqrt2Pi / den);   // :103-106
+    return out;
+}
+
+// The same function for the float32 throughput path: 6 MUFU + ~30 FP32 instructions, no divisions.
+__device__ __forceinline__ Greeks atm_greeks_f32(float S, float K, float v_spot, const GreekConsts& g) {
+    Greeks out{0.f, 0.f, 0.f};
+    if (!g.record_metrics) return out;
+    const float vv = fmaxf(v_spot, 1e-8f);
+    if (S <= 1e-6f) {
+        out.call_delta = (K == 0.f) ? 0.5f : (K > 0.f ? 0.f : 1.f);
+        out.put_delta = (K == 0.f) ? -0.5f : (K < 0.f ? 0.f : -1.f);
+        return out;
     }
+    if (g.T_d <= 1e-6) {
+        out.call_delta = (S > K) ? 1.f : (S == K ? 0.5f : 0.f);
+        out.put_delta = (S < K) ? -1.f : (S == K ? -0.5f : 0.f);
+        return out;
+    }
+    const float Kc = fmaxf(K, 1e-6f);
+    const float rs = mufu_rsqrt(vv);                                           // 1 / sigma
+    const float num = fmaf(mufu_lg2(S * mufu_rcp(Kc)), kLn2f, fmaf(0.5f, vv, g.r_f) * g.T_f);
+    const float inv_sst = rs * g.inv_sqrtT_f;                                  // 1 / (sigma sqrt(T))
+    const float d1 = num * inv_sst;
+    float cdf, cdf_m1;
+    const float pdf = normal_pdf_cdf(d1, &cdf, &cdf_m1);
+    out.call_delta = cdf;
+    out.put_delta = cdf_m1;
+    // :102-106  gamma = phi / (S sigma sqrt(T)), 0 when that denominator is < 1e-9  (S < 1e-9 / (sigma sqrt(T)))
+    out.gamma = (S < 1e-9f * inv_sst) ? 0.f : pdf * inv_sst * mufu_rcp(S);
     return out;
 }
 

@@ -52,4 +52,27 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // generic-proxy writes to shared memory -> visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// A kernel launched with launch_pdl() may start while the previous kernel in the stream is still
+// draining; it must call pdl_wait_prior_grid() before touching anything that kernel wrote.
+// pdl_launch_dependents() tells the scheduler that the NEXT kernel's CTAs may be made resident.
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline int launch_pdl(const void* kernel, dim3 grid, dim3 block, cudaStream_t stream, void** args, size_t smem = 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, args);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelExC");
+    return CANTOR_OK;
+}
+
 }  // namespace cantor

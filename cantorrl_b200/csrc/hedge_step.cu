@@ -1,10 +1,11 @@
 // K3 -- the fused hedge step in replay mode, and the env reset.
 //
 // One thread owns one env.  A step reads, once, the env's 16-byte state record, its cash, its action and
-// the two time slabs (t, t+1) of its path, and writes, once, the 13-float observation, the reward, the
-// done flag and the new state: 137 algorithmic bytes (F32) / 157 (F64) per env-step, no re-reads.  The
-// observation tile of a CTA (256 envs x 52 B = 13 KB, contiguous in the caller's [n_envs, 13] array) is
-// staged in shared memory and leaves the SM as one 1-D TMA bulk store.
+// the two 16-byte path records {S, v, C, P} at (t, path) and (t+1, path), and writes, once, the 13-float
+// observation, the reward, the done flag and the new state: 137 algorithmic bytes (F32) / 157 (F64) per
+// env-step, no re-reads.  The observation tile of a CTA (contiguous in the caller's [n_envs, 13] array) is
+// staged in shared memory and leaves the SM as one 1-D TMA bulk store (UBLKCP).  Launches are chained with
+// programmatic dependent launch so the next step's CTAs are resident before the previous grid drains.
 //
 // Reference semantics: HedgingEnv.step / _get_observation / _calculate_greeks / reset,
 // src/env/hedging_env_v2.py:175-294 / :109-143 / :79-107 / :145-173 (v1: src/env/hedging_env.py).
@@ -12,26 +13,30 @@
 #include "common.cuh"
 #include "philox.cuh"
 
+#ifndef CANTOR_STEP_THREADS
+#define CANTOR_STEP_THREADS 256
+#endif
+#ifndef CANTOR_STEP_MIN_BLOCKS
+#define CANTOR_STEP_MIN_BLOCKS 1
+#endif
+
 namespace cantor {
 
-constexpr int kStepThreads = 256;
+constexpr int kStepThreads = CANTOR_STEP_THREADS;
 
-// Everything derived from cantor_env_params once per launch, passed by value (lives in constant bank).
+// Everything derived from cantor_env_params once per launch, passed by value (lives in the constant bank).
 struct StepConsts {
-    // float64 ledger
+    // float64 ledger (F64 kernels)
     double cost_per_contract, lambda_cost, neg_w, theta_weight, bps_frac, initial_cash, mult_d, shares_d;
-    double inv_mc_d;        // unused in F64 (true division there), 1/max_contracts for F32
-    // float32 ledger
+    // float32 ledger (F32 kernels): the same quantities, reciprocals instead of divisions
+    float cost_f, lambda_f, neg_w_f, theta_per_step_f, slip_f, inv_shares_f, mult_f, inv_mc_f, inv_T_f;
     float shares_f, max_trade_f, initial_cash_f;
     int max_trade, max_contracts, shares, loss_mse, T;
     GreekConsts g;
 };
 
 struct Book {
-    const float* __restrict__ S;
-    const float* __restrict__ v;
-    const float* __restrict__ C;
-    const float* __restrict__ P;
+    const float4* __restrict__ rec;   // {S, v, C, P} at [t * ld + path]; row T carries the marks of row T-1
     long long ld;
     int n_paths;
 };
@@ -56,69 +61,82 @@ __device__ __forceinline__ int pack_pos(int c, int p) { return (c & 0xffff) | (p
 // hedging_env_v2.py:181-188: float32 product, rint (half to even), int cast, clip.
 // NaN / +-inf / |x| >= 2^63 take the x86 "integer indefinite" value INT64_MIN in the reference's
 // astype(int), which the clip turns into -max_trade; reproduced here explicitly.
-__device__ __forceinline__ int requested_trade(float scaled, int max_trade) {
-    if (!(fabsf(scaled) < 9.2233720368547758e18f)) return -max_trade;
-    const float r = rintf(scaled);
-    const float m = (float)max_trade;
-    return (int)fminf(fmaxf(r, -m), m);
+__device__ __forceinline__ int requested_trade(float scaled, float max_trade_f) {
+    const float r = fminf(fmaxf(rintf(scaled), -max_trade_f), max_trade_f);
+    return (int)((fabsf(scaled) < 9.2233720368547758e18f) ? r : -max_trade_f);
 }
 
-// hedging_env_v2.py:109-143.  `lag_valid` = (current_step != 0 && S_prev != 0).
-template <bool F64>
-__device__ __forceinline__ void make_observation(float* __restrict__ o, const StepConsts& k, float S, float v, float C,
-                                                 float P, float s0, int pos_c, int pos_p, int step, float S_prev,
-                                                 float v_prev) {
+__device__ __forceinline__ float clip_unit(float x) {          // np.clip(x, -1, 1); NaN stays NaN
+    const float c = fminf(fmaxf(x, -1.f), 1.f);
+    return (x != x) ? x : c;
+}
+
+// hedging_env_v2.py:109-143, float64 ledger.
+__device__ __forceinline__ void make_observation_f64(float* __restrict__ o, const StepConsts& k, float S, float v,
+                                                     float C, float P, float s0, int pos_c, int pos_p, int step,
+                                                     float S_prev, float v_prev) {
     const float s0_safe = fmaxf(s0, 25.0f);                                   // :116
-    if (F64) {
-        o[0] = __fdiv_rn(S, s0_safe);
-        o[1] = __fdiv_rn(C, s0_safe);
-        o[2] = __fdiv_rn(P, s0_safe);
-        o[3] = k.max_contracts != 0 ? (float)((double)pos_c / (double)k.max_contracts) : 0.f;   // :120 int64 / int
-        o[4] = k.max_contracts != 0 ? (float)((double)pos_p / (double)k.max_contracts) : 0.f;
-        o[6] = k.T != 0 ? (float)((double)(k.T - step) / (double)k.T) : 0.f;  // :122
-    } else {
-        const float inv = __frcp_rn(s0_safe);
-        o[0] = S * inv;
-        o[1] = C * inv;
-        o[2] = P * inv;
-        o[3] = (float)pos_c * (float)k.inv_mc_d;
-        o[4] = (float)pos_p * (float)k.inv_mc_d;
-        o[6] = k.T != 0 ? (float)(k.T - step) / (float)k.T : 0.f;
-    }
+    o[0] = __fdiv_rn(S, s0_safe);
+    o[1] = __fdiv_rn(C, s0_safe);
+    o[2] = __fdiv_rn(P, s0_safe);
+    o[3] = k.max_contracts != 0 ? (float)((double)pos_c / (double)k.max_contracts) : 0.f;   // :120 int64 / int
+    o[4] = k.max_contracts != 0 ? (float)((double)pos_p / (double)k.max_contracts) : 0.f;
     o[5] = v;
-    const Greeks g = atm_greeks<F64>(S, rintf(S), v, k.g);                    // :124-127, np.round = half to even
+    o[6] = k.T != 0 ? (float)((double)(k.T - step) / (double)k.T) : 0.f;      // :122
+    const Greeks g = atm_greeks_f64(S, rintf(S), v, k.g);                     // :124-127, np.round = half to even
     o[7] = g.call_delta;
     o[8] = g.gamma;
     o[9] = g.put_delta;
     o[10] = g.gamma;
     float ret = 0.f, dv = 0.f;
     if (step != 0 && S_prev != 0.f) {                                         // :129-134
-        ret = F64 ? __fdiv_rn(__fsub_rn(S, S_prev), S_prev) : (S - S_prev) / S_prev;
+        ret = __fdiv_rn(__fsub_rn(S, S_prev), S_prev);
         dv = __fsub_rn(v, v_prev);
     }
-    o[11] = fminf(fmaxf(ret, -1.f), 1.f);                                     // :135-136 (NaN propagates like np.clip)
-    o[12] = fminf(fmaxf(dv, -1.f), 1.f);
-    if (ret != ret) o[11] = ret;
-    if (dv != dv) o[12] = dv;
+    o[11] = clip_unit(ret);                                                   // :135-136
+    o[12] = clip_unit(dv);
+}
+
+// The same observation on the float32 throughput path (reciprocals from the SFU, no divisions).
+__device__ __forceinline__ void make_observation_f32(float* __restrict__ o, const StepConsts& k, float S, float v,
+                                                     float C, float P, float inv_s0, int pos_c, int pos_p, int step,
+                                                     float S_prev, float v_prev) {
+    o[0] = S * inv_s0;
+    o[1] = C * inv_s0;
+    o[2] = P * inv_s0;
+    o[3] = (float)pos_c * k.inv_mc_f;
+    o[4] = (float)pos_p * k.inv_mc_f;
+    o[5] = v;
+    o[6] = (float)(k.T - step) * k.inv_T_f;
+    const Greeks g = atm_greeks_f32(S, rintf(S), v, k.g);
+    o[7] = g.call_delta;
+    o[8] = g.gamma;
+    o[9] = g.put_delta;
+    o[10] = g.gamma;
+    float ret = 0.f, dv = 0.f;
+    if (step != 0 && S_prev != 0.f) {
+        ret = (S - S_prev) * mufu_rcp(S_prev);
+        dv = v - v_prev;
+    }
+    o[11] = clip_unit(ret);
+    o[12] = clip_unit(dv);
 }
 
 // hedging_env_v2.py:150-170 for one env; returns the reset state and fills the reset observation.
 template <bool F64>
 __device__ __forceinline__ void reset_one(const StepConsts& k, const Book& b, int path, float* __restrict__ o,
                                           int4& core, double& cash, double& pv_prev) {
-    const float S0raw = b.S[path];
-    const float v0 = b.v[path];
-    const float C0 = b.C[path];
-    const float P0 = b.P[path];
-    const float s0 = (S0raw < 1e-6f) ? 1.0f : S0raw;                          // :157
+    const float4 r0 = b.rec[path];                                            // row 0: S0, v0, C0, P0
+    const float s0 = (r0.x < 1e-6f) ? 1.0f : r0.x;                            // :157
     core.x = 0;                                                               // no contracts
     core.y = 0;                                                               // current_step
     core.z = path;
     core.w = __float_as_int(s0);
     cash = k.initial_cash;                                                    // :165
     // :167-168 evaluated in float32: (shares * S) + 0 + cash
-    pv_prev = (double)__fadd_rn(__fmul_rn(k.shares_f, S0raw), k.initial_cash_f);
-    make_observation<F64>(o, k, S0raw, v0, C0, P0, s0, 0, 0, 0, S0raw, v0);
+    pv_prev = (double)__fadd_rn(__fmul_rn(k.shares_f, r0.x), k.initial_cash_f);
+    if (F64) make_observation_f64(o, k, r0.x, r0.y, r0.z, r0.w, s0, 0, 0, 0, r0.x, r0.y);
+    else make_observation_f32(o, k, r0.x, r0.y, r0.z, r0.w, mufu_rcp(fmaxf(s0, 25.0f)), 0, 0, 0, r0.x, r0.y);
 }
 
 __device__ __forceinline__ int next_episode_path(const ResetRule& rr, const Book& b, long long i, int current) {
@@ -153,7 +171,7 @@ __device__ __forceinline__ void store_obs_tile(float* __restrict__ obs, const fl
 
 // ---------------------------------------------------------------------------------------------------
 template <bool F64, bool INFO>
-__global__ void __launch_bounds__(kStepThreads)
+__global__ void __launch_bounds__(kStepThreads, CANTOR_STEP_MIN_BLOCKS)
 hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                   double* __restrict__ pv_arr, long long n_envs, const float2* __restrict__ actions,
                   float* __restrict__ obs, void* __restrict__ reward_arr, unsigned char* __restrict__ done_arr,
@@ -165,108 +183,134 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
     const int rows = (int)min((long long)kStepThreads, n_envs - first_env);
     float* o = tile + threadIdx.x * CANTOR_OBS_DIM;                            // stride 13 words: conflict-free
 
+    pdl_wait_prior_grid();          // state / actions may come from the kernel launched just before this one
+
     if (i < n_envs) {
         // ---- independent loads first -----------------------------------------------------------------
-        int4 core = ldg_stream(core_arr + i);
-        const float2 a = ldg_stream(actions + i);
-        double cash = F64 ? __ldcs(reinterpret_cast<const double*>(cash_arr) + i)
-                          : (double)__ldcs(reinterpret_cast<const float*>(cash_arr) + i);
-        double pv_prev = F64 ? __ldcs(pv_arr + i) : 0.0;
-
+        int4 core = core_arr[i];
+        const float2 a = __ldcs(actions + i);
+        double cash = 0.0, pv_prev = 0.0;
+        float cash_f = 0.f;
+        if (F64) {
+            cash = reinterpret_cast<const double*>(cash_arr)[i];
+            pv_prev = pv_arr[i];
+        } else {
+            cash_f = reinterpret_cast<const float*>(cash_arr)[i];
+        }
         int pos_c = unpack_lo(core.x), pos_p = unpack_hi(core.x);
         int step = core.y;
         const int path = core.z;
         const float s0 = __int_as_float(core.w);
         const bool already_done = step >= k.T;                                // only reachable with auto_reset = 0
 
-        // ---- the two time slabs of this env's path ------------------------------------------------------
+        // ---- the two time records of this env's path ----------------------------------------------------
         const int t_prev = already_done ? k.T - 1 : step;
-        const int t_new = already_done ? k.T : step + 1;
+        const float4* rp = b.rec + ((long long)t_prev * b.ld + path);
+        const float4 prev = __ldcs(rp);                                       // last use of slab t
+        const float4 cur = __ldg(rp + b.ld);                                  // slab t+1 is read again next step
+        pdl_launch_dependents();
+        const int t_new = t_prev + 1;
         const bool terminated = t_new >= k.T;                                 // :220
-        const int t_opt = terminated ? t_new - 1 : t_new;                     // :226-231 stale option marks at the end
-        const float S_prev = ldg_stream(b.S + t_prev * b.ld + path);
-        const float v_prev = ldg_stream(b.v + t_prev * b.ld + path);
-        const float C_prev = ldg_stream(b.C + t_prev * b.ld + path);
-        const float P_prev = ldg_stream(b.P + t_prev * b.ld + path);
-        const float S_new = ldg_stream(b.S + t_new * b.ld + path);
-        const float v_new = ldg_stream(b.v + t_new * b.ld + path);
-        const float C_new = terminated ? C_prev : ldg_stream(b.C + t_opt * b.ld + path);
-        const float P_new = terminated ? P_prev : ldg_stream(b.P + t_opt * b.ld + path);
+        const float S_prev = prev.x, v_prev = prev.y, C_prev = prev.z, P_prev = prev.w;
+        // :226-231: row T of the packed book repeats the option marks of row T-1 (stale marks at the end)
+        const float S_new = cur.x, v_new = cur.y, C_new = cur.z, P_new = cur.w;
 
-        double reward = 0.0;
-        if (!already_done) {
-            // ---- (i) action -> trade  :178-200 ----------------------------------------------------------
-            const float cf_c = __fmul_rn(a.x, k.max_trade_f);
-            const float cf_p = __fmul_rn(a.y, k.max_trade_f);
-            const int req_c = requested_trade(cf_c, k.max_trade);
-            const int req_p = requested_trade(cf_p, k.max_trade);
-            const int new_c = max(-k.max_contracts, min(k.max_contracts, pos_c + req_c));
-            const int new_p = max(-k.max_contracts, min(k.max_contracts, pos_p + req_p));
-            const int tc = new_c - pos_c, tp = new_p - pos_p;
-            const int atc = abs(tc), atp = abs(tp);
+        // ---- (i) action -> trade  :178-200 --------------------------------------------------------------
+        const float cf_c = __fmul_rn(a.x, k.max_trade_f);
+        const float cf_p = __fmul_rn(a.y, k.max_trade_f);
+        const int req_c = requested_trade(cf_c, k.max_trade_f);
+        const int req_p = requested_trade(cf_p, k.max_trade_f);
+        const int new_c = already_done ? pos_c : max(-k.max_contracts, min(k.max_contracts, pos_c + req_c));
+        const int new_p = already_done ? pos_p : max(-k.max_contracts, min(k.max_contracts, pos_p + req_p));
+        const int tc = new_c - pos_c, tp = new_p - pos_p;
+        const int atc = abs(tc), atp = abs(tp);
 
-            // ---- (ii) commission, slippage on the PRE-advance option prices, cash  :203-213 ------------
+        float s0_floor = fmaxf(s0, 25.0f);
+        float inv_s0 = 0.f;
+        if (F64) {
+            // ---- (ii) commission, slippage on the PRE-advance option prices, cash  :203-213 -------------
             const double commission = __dmul_rn((double)(atc + atp), k.cost_per_contract);
             const double slip_c = __dmul_rn(__dmul_rn(__dmul_rn((double)atc, (double)C_prev), k.mult_d), k.bps_frac);
             const double slip_p = __dmul_rn(__dmul_rn(__dmul_rn((double)atp, (double)P_prev), k.mult_d), k.bps_frac);
             const double slippage = __dadd_rn(slip_c, slip_p);
             const double costs = __dadd_rn(commission, slippage);
             const double cash_new = __dsub_rn(cash, costs);
-
             // ---- (iv) mark to market  :233-238 ----------------------------------------------------------
             const float stock_new = __fmul_rn(k.shares_f, S_new);             // float32 stock leg (:235)
             const double opt_new = __dadd_rn(__dmul_rn(__dmul_rn((double)new_c, (double)C_new), k.mult_d),
                                              __dmul_rn(__dmul_rn((double)new_p, (double)P_new), k.mult_d));
             const double pv = __dadd_rn(__dadd_rn((double)stock_new, opt_new), cash_new);
-            double step_pnl;
-            if (F64) {
-                step_pnl = __dsub_rn(pv, pv_prev);                            // :237
-            } else {
-                // F32 state carries no portfolio value: rebuild last step's from the slab at t (same float32
-                // stock leg, same marks), so pv - pv_prev keeps the reference's roundings.
-                const float stock_prev = __fmul_rn(k.shares_f, S_prev);
-                double pv_old;
-                if (step == 0) {
-                    pv_old = (double)__fadd_rn(stock_prev, k.initial_cash_f);  // reset computes it in float32 (:167)
-                } else {
-                    const double opt_old = __dadd_rn(__dmul_rn(__dmul_rn((double)pos_c, (double)C_prev), k.mult_d),
-                                                     __dmul_rn(__dmul_rn((double)pos_p, (double)P_prev), k.mult_d));
-                    pv_old = __dadd_rn(__dadd_rn((double)stock_prev, opt_old), cash);
-                }
-                step_pnl = pv - pv_old;
-            }
+            const double step_pnl = __dsub_rn(pv, pv_prev);                   // :237
             const double pps = k.shares != 0 ? __ddiv_rn(step_pnl, k.shares_d) : step_pnl;   // :238
-
             // ---- (v) reward  :243-262 -------------------------------------------------------------------
-            const float s0_floor = fmaxf(s0, 25.0f);
             double term;
             if (k.loss_mse) term = __ddiv_rn(__dmul_rn(pps, pps), (double)__fadd_rn(__fmul_rn(s0_floor, s0_floor), 1e-9f));
             else term = __ddiv_rn(fabs(pps), (double)__fadd_rn(s0_floor, 1e-9f));
             const double rpc = __dmul_rn(k.neg_w, term);
             const double tcp = __dmul_rn(k.lambda_cost, costs);
             const double theta_pen = __dmul_rn(k.theta_weight, __ddiv_rn((double)(k.T - t_new), 252.0));
-            reward = __dsub_rn(__dsub_rn(rpc, tcp), theta_pen);
-
-            if (INFO) {
+            const double reward = already_done ? 0.0 : __dsub_rn(__dsub_rn(rpc, tcp), theta_pen);
+            if (INFO && !already_done) {
                 double* f = info.f64 + i;
                 const long long n = n_envs;
                 f[0 * n] = step_pnl;   f[1 * n] = pps;        f[2 * n] = fabs(pps);  f[3 * n] = costs;
                 f[4 * n] = commission; f[5 * n] = slippage;   f[6 * n] = rpc;        f[7 * n] = tcp;
                 f[8 * n] = theta_pen;  f[9 * n] = reward;     f[10 * n] = pv;        f[11 * n] = cash_new;
-                f[12 * n] = a.x;       f[13 * n] = a.y;       f[14 * n] = cf_c;      f[15 * n] = cf_p;
-                f[16 * n] = s0;
-                int* q = info.i32 + i;
-                q[0 * n] = new_c; q[1 * n] = new_p; q[2 * n] = req_c; q[3 * n] = req_p; q[4 * n] = tc; q[5 * n] = tp;
             }
-            pos_c = new_c;
-            pos_p = new_p;
-            cash = cash_new;
-            pv_prev = pv;
-            step = t_new;
+            if (!already_done) {
+                cash = cash_new;
+                pv_prev = pv;
+            }
+            __stcs(reinterpret_cast<double*>(reward_arr) + i, reward);
+        } else {
+            // float32 ledger.  The portfolio value is never formed: the step P&L is the sum of the three
+            // differences (stock leg, option legs, cost), each small, so nothing cancels catastrophically
+            // and the float32 stock leg of the reference (:235) enters exactly.
+            inv_s0 = mufu_rcp(s0_floor);
+            const float commission = (float)(atc + atp) * k.cost_f;
+            const float slippage = fmaf((float)atc, C_prev, (float)atp * P_prev) * k.slip_f;
+            const float costs = commission + slippage;
+            const float d_stock = __fmul_rn(k.shares_f, S_new) - __fmul_rn(k.shares_f, S_prev);
+            const float opt_new = fmaf((float)new_c, C_new, (float)new_p * P_new);
+            const float opt_old = fmaf((float)pos_c, C_prev, (float)pos_p * P_prev);
+            float step_pnl = fmaf(opt_new - opt_old, k.mult_f, d_stock) - costs;
+            if (step == 0 && k.initial_cash_f != 0.f) {
+                // the reference's first portfolio_value_t_minus_1 is float32(stock + cash) (:167-168)
+                const float stock0 = __fmul_rn(k.shares_f, S_prev);
+                step_pnl += (stock0 - __fadd_rn(stock0, k.initial_cash_f)) + k.initial_cash_f;
+            }
+            const float pps = k.shares != 0 ? step_pnl * k.inv_shares_f : step_pnl;
+            const float term = k.loss_mse ? (pps * inv_s0) * (pps * inv_s0) : fabsf(pps) * inv_s0;
+            const float rpc = k.neg_w_f * term;
+            const float tcp = k.lambda_f * costs;
+            const float theta_pen = k.theta_per_step_f * (float)(k.T - t_new);
+            const float reward = already_done ? 0.f : (rpc - tcp) - theta_pen;
+            const float cash_new = cash_f - costs;
+            if (INFO && !already_done) {
+                double* f = info.f64 + i;
+                const long long n = n_envs;
+                f[0 * n] = step_pnl;   f[1 * n] = pps;        f[2 * n] = fabsf(pps); f[3 * n] = costs;
+                f[4 * n] = commission; f[5 * n] = slippage;   f[6 * n] = rpc;        f[7 * n] = tcp;
+                f[8 * n] = theta_pen;  f[9 * n] = reward;     f[11 * n] = cash_new;
+                f[10 * n] = (double)__fmul_rn(k.shares_f, S_new) + (double)(opt_new * k.mult_f) + (double)cash_new;
+            }
+            if (!already_done) cash_f = cash_new;
+            __stcs(reinterpret_cast<float*>(reward_arr) + i, reward);
         }
+        if (INFO && !already_done) {
+            double* f = info.f64 + i;
+            const long long n = n_envs;
+            f[12 * n] = a.x; f[13 * n] = a.y; f[14 * n] = cf_c; f[15 * n] = cf_p; f[16 * n] = s0;
+            int* q = info.i32 + i;
+            q[0 * n] = new_c; q[1 * n] = new_p; q[2 * n] = req_c; q[3 * n] = req_p; q[4 * n] = tc; q[5 * n] = tp;
+        }
+        pos_c = new_c;
+        pos_p = new_p;
+        step = t_new;
 
         // ---- observation of the advanced state  :266 ------------------------------------------------------
-        make_observation<F64>(o, k, S_new, v_new, C_new, P_new, s0, pos_c, pos_p, step, S_prev, v_prev);
+        if (F64) make_observation_f64(o, k, S_new, v_new, C_new, P_new, s0, pos_c, pos_p, step, S_prev, v_prev);
+        else make_observation_f32(o, k, S_new, v_new, C_new, P_new, inv_s0, pos_c, pos_p, step, S_prev, v_prev);
         core.x = pack_pos(pos_c, pos_p);
         core.y = step;
 
@@ -278,21 +322,24 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
             }
             if (auto_reset) {                                                 // VecEnv convention: next episode starts now
                 const int next = next_episode_path(rr, b, i, path);
-                reset_one<F64>(k, b, next, o, core, cash, pv_prev);
+                double cash_d = 0.0;
+                reset_one<F64>(k, b, next, o, core, cash_d, pv_prev);
+                cash = cash_d;
+                cash_f = (float)cash_d;
             }
         }
 
         // ---- stores -------------------------------------------------------------------------------------
-        __stcs(core_arr + i, core);
+        core_arr[i] = core;
         if (F64) {
-            __stcs(reinterpret_cast<double*>(cash_arr) + i, cash);
-            __stcs(pv_arr + i, pv_prev);
-            __stcs(reinterpret_cast<double*>(reward_arr) + i, reward);
+            reinterpret_cast<double*>(cash_arr)[i] = cash;
+            pv_arr[i] = pv_prev;
         } else {
-            __stcs(reinterpret_cast<float*>(cash_arr) + i, (float)cash);
-            __stcs(reinterpret_cast<float*>(reward_arr) + i, (float)reward);
+            reinterpret_cast<float*>(cash_arr)[i] = cash_f;
         }
         done_arr[i] = terminated ? 1 : 0;
+    } else {
+        pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, obs_tma_ok && (rows % 4 == 0));
 }
@@ -326,7 +373,8 @@ env_reset_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, 
 // ---------------------------------------------------------------------------------------------------
 static int make_consts(const cantor_env_params* p, const cantor_replay_book* book, StepConsts* k, Book* b) {
     CANTOR_REQUIRE(p != nullptr && book != nullptr, "params/book is NULL");
-    CANTOR_REQUIRE(book->S && book->v && book->C && book->P, "book array is NULL");
+    CANTOR_REQUIRE(book->svcp != nullptr, "book array is NULL");
+    CANTOR_REQUIRE(aligned16(book->svcp), "book.svcp must be 16-byte aligned");
     CANTOR_REQUIRE(book->n_paths > 0 && book->episode_length > 0, "empty book");
     CANTOR_REQUIRE(book->ld >= book->n_paths, "ld < n_paths");
     CANTOR_REQUIRE(p->max_contracts_held >= 0 && p->max_contracts_held <= 32767, "max_contracts_held must be in [0, 32767]");
@@ -340,7 +388,15 @@ static int make_consts(const cantor_env_params* p, const cantor_replay_book* boo
     k->initial_cash = p->initial_cash;
     k->mult_d = (double)p->option_contract_multiplier;
     k->shares_d = (double)p->shares_to_hedge;
-    k->inv_mc_d = p->max_contracts_held != 0 ? 1.0 / (double)p->max_contracts_held : 0.0;
+    k->cost_f = (float)k->cost_per_contract;
+    k->lambda_f = (float)k->lambda_cost;
+    k->neg_w_f = (float)k->neg_w;
+    k->theta_per_step_f = (float)(p->theta_weight / 252.0);
+    k->slip_f = (float)(k->mult_d * k->bps_frac);
+    k->inv_shares_f = p->shares_to_hedge != 0 ? (float)(1.0 / k->shares_d) : 1.0f;
+    k->mult_f = (float)k->mult_d;
+    k->inv_mc_f = p->max_contracts_held != 0 ? (float)(1.0 / (double)p->max_contracts_held) : 0.0f;
+    k->inv_T_f = (float)(1.0 / (double)book->episode_length);
     k->shares_f = (float)p->shares_to_hedge;
     k->max_trade_f = (float)p->max_trade_per_step;
     k->initial_cash_f = (float)p->initial_cash;
@@ -353,9 +409,9 @@ static int make_consts(const cantor_env_params* p, const cantor_replay_book* boo
     k->g.T_f = (float)p->option_tenor_years;
     k->g.T_d = p->option_tenor_years;
     k->g.sqrtT_d = sqrt(p->option_tenor_years);
-    k->g.sqrtT_f = (float)k->g.sqrtT_d;
+    k->g.inv_sqrtT_f = p->option_tenor_years > 0 ? (float)(1.0 / k->g.sqrtT_d) : 0.f;
     k->g.record_metrics = p->record_metrics;
-    b->S = book->S; b->v = book->v; b->C = book->C; b->P = book->P;
+    b->rec = reinterpret_cast<const float4*>(book->svcp);
     b->ld = book->ld;
     b->n_paths = book->n_paths;
     return CANTOR_OK;
@@ -427,26 +483,27 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
     const unsigned grid = (unsigned)((n_envs + kStepThreads - 1) / kStepThreads);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t reward_bytes = precision == CANTOR_F64 ? sizeof(double) : sizeof(float);
+    int4* core = (int4*)state->core;
+    void* cash = state->cash;
+    double* pv = state->pv_prev;
+    long long n = n_envs;
     for (int32_t t = 0; t < n_steps; ++t) {
         // step t of a rollout writes slab t of the caller's [n_steps, n_envs, ...] buffers
         const float2* a_t = (const float2*)actions + (size_t)t * n_envs;
         float* obs_t = obs + (size_t)t * n_envs * CANTOR_OBS_DIM;
         void* rew_t = (char*)reward + (size_t)t * n_envs * reward_bytes;
-        uint8_t* done_t = done + (size_t)t * n_envs;
-        const int tma_ok = aligned16(obs_t) ? 1 : 0;
-#define LAUNCH(F64, INFO)                                                                                          \
-    hedge_step_kernel<F64, INFO><<<grid, kStepThreads, 0, s>>>(k, b, (int4*)state->core, state->cash, state->pv_prev, \
-                                                               n_envs, a_t, obs_t, rew_t, done_t, terminal_obs,     \
-                                                               auto_reset, rr, io, tma_ok)
-        if (precision == CANTOR_F64) {
-            if (info) LAUNCH(true, true); else LAUNCH(true, false);
-        } else {
-            if (info) LAUNCH(false, true); else LAUNCH(false, false);
-        }
-#undef LAUNCH
+        unsigned char* done_t = done + (size_t)t * n_envs;
+        int tma_ok = aligned16(obs_t) ? 1 : 0;
+        void* args[] = {&k, &b, &core, &cash, &pv, &n, &a_t, &obs_t, &rew_t, &done_t, &terminal_obs, &auto_reset,
+                        &rr, &io, &tma_ok};
+        const void* fn;
+        if (precision == CANTOR_F64) fn = info ? (const void*)hedge_step_kernel<true, true> : (const void*)hedge_step_kernel<true, false>;
+        else fn = info ? (const void*)hedge_step_kernel<false, true> : (const void*)hedge_step_kernel<false, false>;
+        rc = launch_pdl(fn, dim3(grid), dim3(kStepThreads), s, args);
+        if (rc) return rc;
         rr.episode_counter += 1;
     }
-    return check_launch("hedge_step_kernel");
+    return CANTOR_OK;
 }
 
 extern "C" int cantor_env_step(const cantor_env_params* params, const cantor_replay_book* book,

@@ -1,9 +1,10 @@
-"""Env-schema path data resident in HBM, time-major.
+"""Env-schema path data resident in HBM as one packed, time-major book.
 
 The reference env loads four path-major arrays from an ``.npz`` and casts them to float32
-(``src/env/hedging_env_v2.py:36-48``).  Here the same four arrays live on the GPU as
-``[T+1, ld]`` / ``[T, ld]`` float32 tensors so that the 32 envs of a warp read one 128-byte line per
-array and time slab.
+(``src/env/hedging_env_v2.py:36-48``).  Here the same data live on the GPU as ONE float32 tensor
+``book[t, path] = (S, v, C, P)`` of shape ``[T+1, ld, 4]`` so an env-step is two aligned 16-byte loads and
+the 32 envs of a warp read 512 contiguous bytes.  Row ``T`` repeats the option marks of row ``T-1`` -- the
+stale marks the reference uses at the terminal step (``:226-231``).
 """
 from __future__ import annotations
 
@@ -20,39 +21,90 @@ def _round_up(n: int, m: int) -> int:
 
 
 class ReplayData:
-    """Time-major float32 device copies of ``paths``, ``volatilities``, ``call_prices_atm``, ``put_prices_atm``."""
+    """Packed float32 device copy of ``paths``, ``volatilities``, ``call_prices_atm``, ``put_prices_atm``."""
 
-    def __init__(self, S: torch.Tensor, v: torch.Tensor, C: torch.Tensor, P: torch.Tensor, n_paths: int):
-        for t in (S, v, C, P):
-            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous() or t.dim() != 2:
-                raise ValueError("ReplayData tensors must be contiguous 2-D float32 CUDA tensors")
-        if not (S.shape == v.shape and C.shape == P.shape and S.shape[1] == C.shape[1]
-                and S.shape[0] == C.shape[0] + 1 and 0 < n_paths <= S.shape[1]):
-            raise ValueError("Data shapes are inconsistent.")
-        self.S, self.v, self.C, self.P = S, v, C, P
+    def __init__(self, book: torch.Tensor, n_paths: int):
+        if (book.dtype != torch.float32 or not book.is_cuda or not book.is_contiguous() or book.dim() != 3
+                or book.shape[2] != 4 or book.shape[0] < 2 or not 0 < n_paths <= book.shape[1]):
+            raise ValueError("ReplayData book must be a contiguous float32 CUDA tensor [T+1, ld, 4] with 0 < n_paths <= ld")
+        self.tensor = book
         self.n_paths = int(n_paths)
-        self.ld = int(S.shape[1])
-        self.episode_length = int(S.shape[0] - 1)
-        self.device = S.device
+        self.ld = int(book.shape[1])
+        self.episode_length = int(book.shape[0] - 1)
+        self.device = book.device
+
+    # strided views in the reference's vocabulary (time-major)
+    @property
+    def S(self):
+        return self.tensor[:, :, 0]
+
+    @property
+    def v(self):
+        return self.tensor[:, :, 1]
+
+    @property
+    def C(self):
+        return self.tensor[:, :, 2]
+
+    @property
+    def P(self):
+        return self.tensor[:, :, 3]
 
     # -- constructors ---------------------------------------------------------------------------
     @classmethod
+    def empty(cls, n_paths: int, episode_length: int, device="cuda") -> "ReplayData":
+        """Uninitialised book for a simulator kernel to fill."""
+        ld = _round_up(int(n_paths), 8)
+        return cls(torch.empty((episode_length + 1, ld, 4), dtype=torch.float32, device=device), n_paths)
+
+    @classmethod
     def from_arrays(cls, paths, volatilities, call_prices_atm, put_prices_atm, device="cuda") -> "ReplayData":
-        """Path-major ``(n, T+1)/(n, T)`` host arrays (any float dtype) -> time-major float32 on ``device``."""
-        arrs = [np.asarray(a) for a in (paths, volatilities, call_prices_atm, put_prices_atm)]
+        """Path-major ``(n, T+1)/(n, T)`` arrays (NumPy or torch; float32 or float64) -> packed book on ``device``.
+
+        The cast to float32 (hedging_env_v2.py:38-41), the transposition and the interleave run in one kernel.
+        """
+        arrs = []
+        for a in (paths, volatilities, call_prices_atm, put_prices_atm):
+            if isinstance(a, torch.Tensor):
+                arrs.append(a)
+            else:
+                a = np.asarray(a)
+                if a.dtype not in (np.float32, np.float64):
+                    a = a.astype(np.float64)
+                arrs.append(torch.from_numpy(np.ascontiguousarray(a)))
         S, V, Cc, Pp = arrs
         # hedging_env_v2.py:45-48
-        if not (S.ndim == 2 and S.shape == V.shape and Cc.ndim == 2 and Pp.ndim == 2
+        if not (S.dim() == 2 and S.shape == V.shape and Cc.dim() == 2 and Pp.dim() == 2
                 and S.shape[0] == Cc.shape[0] == Pp.shape[0] and S.shape[1] == Cc.shape[1] + 1 == Pp.shape[1] + 1):
             raise ValueError("Data shapes are inconsistent.")
-        n = S.shape[0]
-        ld = _round_up(n, 32)                 # 128-byte rows
-        out = []
-        for a in arrs:
-            t = torch.zeros((a.shape[1], ld), dtype=torch.float32, device=device)
-            t[:, :n] = torch.from_numpy(np.ascontiguousarray(a.astype(np.float32).T)).to(device)
-            out.append(t)
-        return cls(*out, n_paths=n)
+        dt = torch.float64 if any(a.dtype == torch.float64 for a in arrs) else torch.float32
+        dev = torch.device(device)
+        arrs = [a.to(device=dev, dtype=dt).contiguous() for a in arrs]
+        n, T = int(S.shape[0]), int(S.shape[1]) - 1
+        if T < 1 or n < 1:
+            raise ValueError("Data shapes are inconsistent.")
+        out = cls.empty(n, T, dev)
+        out.tensor.zero_()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cantor_pack_book(
+                arrs[0].data_ptr(), arrs[1].data_ptr(), arrs[2].data_ptr(), arrs[3].data_ptr(),
+                _lib.F64 if dt == torch.float64 else _lib.F32, n, T, out.tensor.data_ptr(), out.ld,
+                _lib.current_stream_ptr(dev)), "cantor_pack_book")
+        return out
+
+    @classmethod
+    def from_time_major(cls, S, v, C, P, n_paths=None) -> "ReplayData":
+        """Time-major float32 CUDA tensors ``S, v [T+1, n]``, ``C, P [T, n]`` -> packed book (torch copy; tests/tools)."""
+        T1, n = S.shape
+        out = cls.empty(n if n_paths is None else n_paths, T1 - 1, S.device)
+        out.tensor.zero_()
+        out.tensor[:, :n, 0] = S
+        out.tensor[:, :n, 1] = v
+        out.tensor[:T1 - 1, :n, 2] = C
+        out.tensor[:T1 - 1, :n, 3] = P
+        out.tensor[T1 - 1, :n, 2] = C[T1 - 2]
+        out.tensor[T1 - 1, :n, 3] = P[T1 - 2]
+        return out
 
     @classmethod
     def from_npz(cls, data_file_path, device="cuda") -> "ReplayData":
@@ -66,10 +118,22 @@ class ReplayData:
 
     # -- C ABI view -----------------------------------------------------------------------------
     def book(self) -> _lib.ReplayBook:
-        return _lib.ReplayBook(self.S.data_ptr(), self.v.data_ptr(), self.C.data_ptr(), self.P.data_ptr(),
-                               self.ld, self.n_paths, self.episode_length)
+        return _lib.ReplayBook(self.tensor.data_ptr(), self.ld, self.n_paths, self.episode_length)
 
-    def to_path_major(self):
-        """Back to the npz layout (host float32 arrays), e.g. to feed the CPU oracle."""
-        n = self.n_paths
-        return tuple(t[:, :n].T.contiguous().cpu().numpy() for t in (self.S, self.v, self.C, self.P))
+    def to_path_major(self, dtype=torch.float32):
+        """Back to the npz layout: dict of path-major device tensors (``dtype`` float32 or float64)."""
+        n, T, dev = self.n_paths, self.episode_length, self.device
+        out = {"paths": torch.empty((n, T + 1), dtype=dtype, device=dev),
+               "volatilities": torch.empty((n, T + 1), dtype=dtype, device=dev),
+               "call_prices_atm": torch.empty((n, T), dtype=dtype, device=dev),
+               "put_prices_atm": torch.empty((n, T), dtype=dtype, device=dev)}
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cantor_unpack_book(
+                self.tensor.data_ptr(), self.ld, n, T, _lib.F64 if dtype == torch.float64 else _lib.F32,
+                *(out[k].data_ptr() for k in SCHEMA_A_KEYS), _lib.current_stream_ptr(dev)), "cantor_unpack_book")
+        return out
+
+    def save_npz(self, path, compressed=True):
+        """Write the reference's env-schema file (float64 arrays like rbergomi_sim.py:528)."""
+        arrs = {k: v.cpu().numpy() for k, v in self.to_path_major(torch.float64).items()}
+        (np.savez_compressed if compressed else np.savez)(path, **arrs)

@@ -18,8 +18,8 @@
  *   - Unless a function name ends in _host, every pointer is a DEVICE pointer owned by the caller
  *     (e.g. torch.Tensor.data_ptr()); nothing is allocated, freed or synchronised inside a call.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous.
- *   - Path/option arrays are TIME-MAJOR: element (t, path) lives at [t * ld + path].  One warp reads
- *     32 consecutive paths of one time slab = one 128-byte line.
+ *   - Path/option arrays are TIME-MAJOR: element (t, path) lives at [t * ld + path], so the 32 envs of a
+ *     warp read consecutive memory of one time slab.
  *   - precision = CANTOR_F32 : float cash / reward, float Black-Scholes; 137 algorithmic bytes per env-step.
  *     precision = CANTOR_F64 : double cash / portfolio value / reward with the reference's exact
  *     float32/float64 operation ledger (bit-exact integers, <= 1e-6 relative on every float); 157 B.
@@ -73,13 +73,14 @@ typedef struct cantor_env_params {
     int32_t record_metrics;                 /* 1; 0 zeroes obs[7:11] (:80-81) */
 } cantor_env_params;
 
-/* Env-schema arrays of the reference npz (hedging_env_v2.py:36-48), float32, time-major in HBM. */
+/* The four env-schema arrays of the reference npz (hedging_env_v2.py:36-48) as ONE packed float32 array in HBM:
+ * record (t, path) = {S, v, C, P} = {'paths', 'volatilities' (instantaneous VARIANCE, :84), 'call_prices_atm',
+ * 'put_prices_atm'} at svcp[(t * ld + path) * 4 .. +3], t = 0..T.  An env-step is two aligned 16-byte loads.
+ * Row T has no option columns in the reference (they are (n, T)); it must repeat the C, P of row T-1, which is
+ * exactly the stale mark the reference uses at the terminal step (:226-231).  cantor_pack_book builds it. */
 typedef struct cantor_replay_book {
-    const float* S;        /* 'paths'            [(T+1) * ld] */
-    const float* v;        /* 'volatilities'     [(T+1) * ld]  (instantaneous VARIANCE, :84) */
-    const float* C;        /* 'call_prices_atm'  [T * ld] */
-    const float* P;        /* 'put_prices_atm'   [T * ld] */
-    int64_t ld;            /* leading dimension in elements, >= n_paths */
+    const float* svcp;     /* [(T+1) * ld * 4], 16-byte aligned */
+    int64_t ld;            /* leading dimension in records, >= n_paths */
     int32_t n_paths;       /* num_episodes   (:50) */
     int32_t episode_length;/* T = paths.shape[1] - 1 (:51) */
 } cantor_replay_book;
@@ -121,6 +122,17 @@ int cantor_abi_version(void);
 const char* cantor_last_error(void);
 /* Writes "sm_XY" style facts about device `device`; returns CANTOR_ERR_NO_DEVICE without a GPU. */
 int cantor_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---- on-disk formats <-> packed book ------------------------------------------------------------------
+ * Path-major device copies of the reference npz arrays (paths, volatilities: [n_paths, T+1]; call_prices_atm,
+ * put_prices_atm: [n_paths, T]; src_dtype CANTOR_F32 or CANTOR_F64 = the npz dtype, rbergomi_sim.py:528) ->
+ * packed float32 book; does the `.astype(np.float32)` of hedging_env_v2.py:38-41 and the transposition. */
+int cantor_pack_book(const void* paths, const void* vols, const void* calls, const void* puts,
+                     int32_t src_dtype, int32_t n_paths, int32_t episode_length, float* svcp, int64_t ld,
+                     void* stream);
+/* The inverse (e.g. to np.savez a simulated book in the reference schema). */
+int cantor_unpack_book(const float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length,
+                       int32_t dst_dtype, void* paths, void* vols, void* calls, void* puts, void* stream);
 
 /* ---- K3: fused hedge step (replay mode) ------------------------------------------------------------
  * Replaces HedgingEnv.reset (hedging_env_v2.py:145-173) for the envs with mask[i] != 0 (mask NULL = all).

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_the_header():
     from cantorrl_b200 import _lib
     assert C.sizeof(_lib.EnvParams) == 8 * 8 + 6 * 4
-    assert C.sizeof(_lib.ReplayBook) == 4 * 8 + 8 + 2 * 4
+    assert C.sizeof(_lib.ReplayBook) == 8 + 8 + 2 * 4
     assert C.sizeof(_lib.EnvState) == 3 * 8
     assert C.sizeof(_lib.ResetRule) == 2 * 4 + 8 + 8 + 8 + 8
     assert C.sizeof(_lib.InfoOut) == 16

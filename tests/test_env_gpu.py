@@ -183,7 +183,7 @@ def test_full_size_invariants(prec):
     v = torch.full((T + 1, n), 0.04, device="cuda")
     Cc = torch.rand((T, n), device="cuda", generator=g) * 5 + 1
     Pp = torch.rand((T, n), device="cuda", generator=g) * 5 + 1
-    data = ReplayData(S.contiguous(), v, Cc, Pp, n_paths=n)
+    data = ReplayData.from_time_major(S, v, Cc, Pp)
     env = HedgingVecEnv(data=data, num_envs=n, precision=prec, episode_sampler="same_path", slippage_bps=1.0,
                         pnl_penalty_weight=1.0, lambda_cost=0.0)
     env.reset()
@@ -205,7 +205,9 @@ def test_full_size_invariants(prec):
     for t in range(T + 2):
         env.step(a)
         c = env.call_contracts_held
-        fresh = env.current_step == 0
-        assert int((c - prev_c)[~fresh].abs().max()) <= 15 and int(c.abs().max()) <= 200
-        assert bool((env.cash_balance[~fresh] <= cash0[~fresh]).all())               # costs are non-negative
+        fresh = env.current_step == 0                                                # all envs move in lock-step here
+        if not bool(fresh.any()):
+            assert int((c - prev_c).abs().max()) <= 15
+            assert bool((env.cash_balance <= cash0).all())                           # costs are non-negative
+        assert int(c.abs().max()) <= 200
         prev_c, cash0 = c.clone(), env.cash_balance.clone()
