@@ -198,29 +198,20 @@ class ClockSampler:
                     power_w_max=max(pw) if pw else None, samples=len(sm), reasons=reasons)
 
 
-def synth_replay_data(n, T, seed, device):
-    """Synthetic env-schema arrays of configs[1], generated on the device (setup, untimed)."""
+def synth_replay_data(n, T, rank, device):
+    """Synthetic env-schema book of configs[1]: K1 (Philox GBM log-Euler) fused with K2 (ATM Black-Scholes), written
+    straight into HBM in the packed layout.  Returns (book, kernel milliseconds)."""
     import torch
-    from cantorrl_b200 import ReplayData
-    g = torch.Generator(device=device).manual_seed(seed)
-    S = torch.empty((T + 1, n), dtype=torch.float32, device=device)
-    logS = torch.zeros(n, dtype=torch.float64, device=device)
-    S[0] = S0
-    for t in range(1, T + 1):
-        z = torch.randn(n, dtype=torch.float32, device=device, generator=g).double()
-        logS += (R - 0.5 * XI) * DT + (XI * DT) ** 0.5 * z
-        S[t] = (S0 * torch.exp(logS)).float()
-    v = torch.full((T + 1, n), XI, dtype=torch.float32, device=device)
-    Sd = S[:T].double()
-    K = torch.round(Sd)
-    tenor, sig = 30 / 252, XI ** 0.5
-    d1 = (torch.log(Sd / K) + (R + 0.5 * sig * sig) * tenor) / (sig * tenor ** 0.5)
-    d2 = d1 - sig * tenor ** 0.5
-    Phi = lambda x: 0.5 * torch.erfc(-x / 2 ** 0.5)   # noqa: E731
-    disc = float(np.exp(-R * tenor))
-    Cc = (Sd * Phi(d1) - K * disc * Phi(d2)).float()
-    Pp = (K * disc * Phi(-d2) - Sd * Phi(-d1)).float()
-    return ReplayData.from_time_major(S, v, Cc, Pp)
+    from cantorrl_b200 import sim
+    book = sim.generate_paths_and_options(n, R, DT, 42, n_steps=T, model="gbm", s0=S0, v0=XI, path_offset=rank * n,
+                                          device=device)                       # warm-up / allocation
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sim.generate_paths_and_options(n, R, DT, 42, n_steps=T, model="gbm", s0=S0, v0=XI, path_offset=rank * n,
+                                   device=device, out=book)
+    e1.record()
+    torch.cuda.synchronize(device)
+    return book, e0.elapsed_time(e1)
 
 
 def main():
@@ -244,7 +235,7 @@ def main():
     n, T, K, W = args.envs, args.episode_length, args.steps, args.warmup
     L = _lib.lib()
 
-    data = synth_replay_data(n, T, 42 + rank, dev)
+    data, sim_ms = synth_replay_data(n, T, rank, dev)
     env = HedgingVecEnv(data=data, num_envs=n, device=dev, precision=args.precision, episode_sampler="same_path",
                         env_offset=rank * n, **ENV_KW)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -339,7 +330,10 @@ def main():
             e2e=dict(value=float(n) * world * T * args.e2e_steps / e2e_s, unit="env-steps/s",
                      h2d_bytes_per_step=n * 8 * T, d2h_bytes_per_step=n * (52 + reward.element_size() + 1) * T,
                      api="HedgingVecEnv.step with pinned host action/obs/reward/done buffers, synchronised every env step"),
-            clocks=clocks)
+            clocks=clocks,
+            extra=dict(path_sim_reprice=dict(kernel="sim_paths_kernel<GBM> (K1 fused with K2 ATM repricing)", ms=sim_ms,
+                                             path_steps_per_s=float(n) * T / (sim_ms * 1e-3),
+                                             hbm_write_gbs=float(n) * (T + 1) * 16 / (sim_ms * 1e-3) / 1e9)))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)

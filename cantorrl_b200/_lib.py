@@ -57,6 +57,16 @@ class ResetRule(C.Structure):
                 ("seed", C.c_uint64), ("env_offset", C.c_int64), ("episode_counter", C.c_int64)]
 
 
+MODEL_GBM, MODEL_HESTON = 0, 1
+
+
+class SimParams(C.Structure):
+    _fields_ = [("model", C.c_int32), ("reprice", C.c_int32), ("s0", C.c_double), ("v0", C.c_double),
+                ("r", C.c_double), ("dt", C.c_double), ("kappa", C.c_double), ("theta", C.c_double),
+                ("sigma_v", C.c_double), ("rho", C.c_double), ("tenor", C.c_double), ("seed", C.c_uint64),
+                ("path_offset", C.c_int64)]
+
+
 class InfoOut(C.Structure):
     _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p)]
 
@@ -71,6 +81,16 @@ SIGNATURES = {
                                    C.c_void_p, C.c_int64, C.c_void_p]),
     "cantor_unpack_book": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_sim_paths": (C.c_int, [C.POINTER(SimParams), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cantor_reprice_atm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p]),
+    "cantor_euler_from_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                            C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "cantor_bs_price": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_schema_b_book": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_bs_delta_hedge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_double,
+                                        C.c_void_p, C.c_void_p]),
     "cantor_env_reset": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_env_step": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,

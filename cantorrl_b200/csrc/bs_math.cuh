@@ -100,7 +100,22 @@ __device__ __forceinline__ Greeks atm_greeks_f32(float S, float K, float v_spot,
     }
     const float Kc = fmaxf(K, 1e-6f);
     const float rs = mufu_rsqrt(vv);                                           // 1 / sigma
-    const float num = fmaf(mufu_lg2(S * mufu_rcp(Kc)), kLn2f, fmaf(0.5f, vv, g.r_f) * g.T_f);
+    // log(S / K) with K = rint(S).  The reference rounds the quotient to float32 before the log (:99); with a
+    // floored sigma that rounding is amplified by 1 / (sigma sqrt(T)) ~ 3e4 in d1, so it is reproduced (IEEE
+    // division), and log(q) is taken through the log1p series of u = q - 1 (exact subtraction; |u| <= 1/16:
+    // error < u^7/7) because lg2.approx only bounds the ABSOLUTE error near 1.
+    const float u = __fdiv_rn(S, Kc) - 1.0f;
+    float lg;
+    if (fabsf(u) <= 0.0625f) {
+        float s = fmaf(u, -1.0f / 6.0f, 0.2f);
+        s = fmaf(u, s, -0.25f);
+        s = fmaf(u, s, 1.0f / 3.0f);
+        s = fmaf(u, s, -0.5f);
+        lg = fmaf(u * u, s, u);
+    } else {
+        lg = mufu_lg2(1.0f + u) * kLn2f;
+    }
+    const float num = fmaf(fmaf(0.5f, vv, g.r_f), g.T_f, lg);
     const float inv_sst = rs * g.inv_sqrtT_f;                                  // 1 / (sigma sqrt(T))
     const float d1 = num * inv_sst;
     float cdf, cdf_m1;

@@ -14,10 +14,10 @@
 #include "philox.cuh"
 
 #ifndef CANTOR_STEP_THREADS
-#define CANTOR_STEP_THREADS 256
+#define CANTOR_STEP_THREADS 128
 #endif
 #ifndef CANTOR_STEP_MIN_BLOCKS
-#define CANTOR_STEP_MIN_BLOCKS 1
+#define CANTOR_STEP_MIN_BLOCKS 12
 #endif
 
 namespace cantor {

@@ -134,6 +134,53 @@ int cantor_pack_book(const void* paths, const void* vols, const void* calls, con
 int cantor_unpack_book(const float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length,
                        int32_t dst_dtype, void* paths, void* vols, void* calls, void* puts, void* stream);
 
+/* ---- K1: path simulation (+ fused ATM repricing) -------------------------------------------------------
+ * Replaces the outer path loop of generate_paths_and_options (src/sim/rbergomi_sim.py:454-464) and its output
+ * schema (:528) with GBM / Heston log-Euler paths driven by counter-based Philox4x32-10 normals:
+ * counter = (global path index, call number, "PATH"), key = seed, so a path does not depend on the launch
+ * geometry or on how paths are sharded over GPUs.  With reprice != 0 the option columns are the closed-form
+ * Black-Scholes ATM call / put (K = round(S_t), :418; tenor, :19) that the north star substitutes for the
+ * nested-MC pricer (:246-306).  Writes the packed book (see cantor_replay_book), float32. */
+enum { CANTOR_MODEL_GBM = 0, CANTOR_MODEL_HESTON = 1 };
+typedef struct cantor_sim_params {
+    int32_t model;          /* CANTOR_MODEL_* */
+    int32_t reprice;        /* 1: fill C, P with Black-Scholes ATM prices; 0: leave them 0 */
+    double s0;              /* 100.0  S0_DEFAULT (rbergomi_sim.py:27) */
+    double v0;              /* 0.04   XI_DEFAULT (:23): GBM variance / Heston initial variance */
+    double r;               /* 0.04   (:13) */
+    double dt;              /* 1/252  (:14) */
+    double kappa, theta, sigma_v, rho;   /* Heston: dv = kappa (theta - v+) dt + sigma_v sqrt(v+ dt) z_v, corr(z_S, z_v) = rho */
+    double tenor;           /* 30/252 (:19) */
+    uint64_t seed;          /* 42     (:17) */
+    int64_t path_offset;    /* global index of path 0 of this shard */
+} cantor_sim_params;
+int cantor_sim_paths(const cantor_sim_params* params, int32_t n_paths, int32_t episode_length, float* svcp,
+                     int64_t ld, void* stream);
+/* Fills the C, P columns of a packed book that already holds S and v (paths loaded from disk). */
+int cantor_reprice_atm(float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length, double r, double tenor,
+                       void* stream);
+/* The reference's own float64 step (rbergomi_sim.py:454-464) on exported draws, for parity: time-major
+ * v [(T+1) * ld], dW1 / dW2 [T * ld] (unscaled N(0,1)), per-path S0 / rho [n_paths] -> paths [(T+1) * ld]. */
+int cantor_euler_from_normals(const double* S0, const double* v, const double* dW1, const double* dW2,
+                              const double* rho, int32_t n_paths, int32_t episode_length, int64_t ld,
+                              double r, double dt, double* paths, void* stream);
+
+/* ---- K2: Black-Scholes repricing in float64 (src/sim/option_price_assignment.py, src/tools/bs_delta.py) ---
+ * black_scholes_vectorized (:10-21), elementwise over n outputs; stride 0 broadcasts a scalar input. */
+int cantor_bs_price(const double* S, const double* K, const double* T, const double* sigma, int64_t n,
+                    int32_t stride_S, int32_t stride_K, int32_t stride_T, int32_t stride_sigma, double r,
+                    double epsilon, double* call, double* put, void* stream);
+/* process_price_paths (:33-52) on time-major float64 paths [(T+1) * ld]: realised volatility of the path prefix
+ * (:23-31; column 0 = 0, column 1 = NaN), maturity to the episode end T_t = clip(1 - t/252, 0), strikes
+ * K_m = round(S_0) * strike_mult[m] (reference: one strike, multiplier 1).  vols [(T+1) * ld] may be NULL;
+ * calls / puts are [n_strikes * (T+1) * ld] ("schema B", generalised to a strike ladder). */
+int cantor_schema_b_book(const double* paths, int32_t n_paths, int32_t episode_length, int64_t ld, double r,
+                         const double* strike_mult, int32_t n_strikes, double* vols, double* calls, double* puts,
+                         void* stream);
+/* bs_delta_hedge (src/tools/bs_delta.py:36-55): per-path delta-hedge P&L, time-major paths -> pnl [(T+1) * ld]. */
+int cantor_bs_delta_hedge(const double* paths, int32_t n_paths, int32_t episode_length, int64_t ld, double r,
+                          double dt, double* pnl, void* stream);
+
 /* ---- K3: fused hedge step (replay mode) ------------------------------------------------------------
  * Replaces HedgingEnv.reset (hedging_env_v2.py:145-173) for the envs with mask[i] != 0 (mask NULL = all).
  * The episode index of env i is path_idx[i] (the value the reference draws at :150).

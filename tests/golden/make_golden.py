@@ -187,5 +187,46 @@ def main():
     print("bs_delta_golden: 6 paths")
 
 
+def make_outer_euler_golden():
+    """Run the unmodified generate_paths_and_options (rbergomi_sim.py:309-499) on CPU under the cupy stand-in, with the
+    module constants shrunk, and export its per-path parameters, variances, unscaled draws and resulting paths."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_cupy_stub"))
+    rb = _load("ref_rbergomi", f"{REF}/src/sim/rbergomi_sim.py")
+    rb.N_STEPS, rb.N_PATHS_OPTION_MC, rb.OPTION_PRICING_MINI_BATCH_SIZE = 12, 40, 16
+    rb.tqdm = lambda it, **kw: _NoBar(it)
+    hist = np.loadtxt(f"{REF}/data/historical_prices.csv", dtype=np.float64, delimiter=",")
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                paths, v, calls, puts = rb.generate_paths_and_options(hist, 24, rb.R, rb.DT, 42)
+            chk = dict(np.load(rb.CHECKPOINT_FILE, allow_pickle=True))
+        finally:
+            os.chdir(cwd)
+    np.savez_compressed(os.path.join(HERE, "outer_euler_golden.npz"), paths=np.asarray(paths), v=np.asarray(v),
+                        S0=chk["S0_arr_gpu"], rho=chk["rho_arr_gpu"], dW1=chk["dW1_unscaled_main_gpu"],
+                        dW2=chk["dW2_unscaled_main_gpu"], r=rb.R, dt=rb.DT)
+    print(f"outer_euler_golden: {paths.shape[0]} paths x {paths.shape[1] - 1} days from the unmodified simulator")
+
+
+class _NoBar:
+    def __init__(self, it):
+        self.it = it
+
+    def __enter__(self):
+        return self.it
+
+    def __exit__(self, *a):
+        return False
+
+    def __iter__(self):
+        return iter(self.it)
+
+
 if __name__ == "__main__":
-    main()
+    if "--euler-only" not in sys.argv:
+        main()
+    make_outer_euler_golden()
