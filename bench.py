@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--episode-length", type=int, default=252)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--e2e-steps", type=int, default=2, help="episode sweeps timed through the host-buffer API")
+    ap.add_argument("--rollout-steps", type=int, default=3, help="episode sweeps of the on-the-fly rollout kernel (extra)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -305,11 +306,37 @@ def main():
         assert np.isfinite(e2e_checksum)
         henv.close()
 
+    # ---- configs[3] shape: episode-fused rollout, paths generated in-kernel, statistics all-reduced over NCCL -------
+    # One launch = one whole episode of every env (GBM on the fly + ATM repricing + delta-hedge policy + env step +
+    # episode statistics); the only inter-GPU traffic of the whole path is the all-reduce of the statistics buffers.
+    roll = None
+    if args.rollout_steps > 0:
+        from cantorrl_b200.rollout import HedgingRollout
+        ro = HedgingRollout(simulate=dict(model="gbm", seed=42, s0=S0, v0=XI, n_steps=T), num_envs=n, device=dev,
+                            env_offset=rank * n, total_envs=world * n, one_call_only=True, **ENV_KW)
+        rstats = ro.new_stats()
+
+        def roll_sweep():
+            rstats.zero_()
+            ro.run(T, "delta_every_step", stats=rstats)
+            rstats.all_reduce()
+
+        for _ in range(2):
+            roll_sweep()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for _ in range(args.rollout_steps):
+            roll_sweep()
+        r1.record(stream)
+        barrier()
+        roll = (r0.elapsed_time(r1), rstats.result())
+
     # ---- reduce over ranks ------------------------------------------------------------------------------------
-    tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    tt = torch.tensor([ms, e2e_s, roll[0] if roll else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, e2e_s = float(tt[0]), float(tt[1])
+    ms, e2e_s, roll_ms = float(tt[0]), float(tt[1]), float(tt[2])
     if rank == 0:
         env_steps = float(n) * world * T * K
         value = env_steps / (ms * 1e-3)
@@ -337,6 +364,13 @@ def main():
             extra=dict(path_sim_reprice=dict(kernel="sim_paths_kernel<GBM> (K1 fused with K2 ATM repricing)", ms=sim_ms,
                                              path_steps_per_s=float(n) * T / (sim_ms * 1e-3),
                                              hbm_write_gbs=float(n) * (T + 1) * 16 / (sim_ms * 1e-3) / 1e9)))
+        if roll is not None:
+            rs = roll[1]
+            line["extra"]["rollout_on_the_fly"] = dict(
+                kernel="rollout_kernel<GBM on the fly, delta_every_step policy, episode statistics> + all-reduce of the "
+                       "statistics buffers (NCCL) once per sweep", sweeps=args.rollout_steps, ms_per_sweep=roll_ms / args.rollout_steps,
+                env_steps_per_s=float(n) * world * T * args.rollout_steps / (roll_ms * 1e-3),
+                stats={k: rs[k] for k in ("n_episodes", "mean_abs_pnl", "std_abs_pnl", "mean_cost", "mean_reward", "cvar95_abs_pnl")})
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)

@@ -67,6 +67,26 @@ class SimParams(C.Structure):
                 ("path_offset", C.c_int64)]
 
 
+POLICY_NO_HEDGE, POLICY_RANDOM, POLICY_DELTA_BASELINES, POLICY_DELTA_BENCHMARK, POLICY_MLP, POLICY_ACTIONS = range(6)
+MLP_FLOATS = 5212
+STATS_LEN = 16
+
+
+class Policy(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("put_leg_disabled", C.c_int32), ("mlp", C.c_void_p), ("actions", C.c_void_p),
+                ("seed", C.c_uint64)]
+
+
+class StatsOut(C.Structure):
+    _fields_ = [("sums", C.c_void_p), ("hist", C.c_void_p), ("hist_sum", C.c_void_p), ("episode_b", C.c_void_p),
+                ("hist_max", C.c_double),
+                ("hist_bins", C.c_int32), ("reserved", C.c_int32), ("episode_slots", C.c_int64)]
+
+
+class RolloutOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("actions", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p)]
+
+
 class InfoOut(C.Structure):
     _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p)]
 
@@ -91,6 +111,9 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_bs_delta_hedge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_double,
                                         C.c_void_p, C.c_void_p]),
+    "cantor_rollout": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(SimParams), C.c_int32,
+                                 C.POINTER(Policy), C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(StatsOut),
+                                 C.POINTER(RolloutOut), C.c_void_p]),
     "cantor_vecenv_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(EnvParams), C.c_int32, C.c_int64, C.c_int32, C.c_int32]),
     "cantor_vecenv_destroy": (C.c_int, [C.c_void_p]),
     "cantor_vecenv_load_book_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -1,0 +1,192 @@
+// Device-side core of the hedging environment, shared by the per-step kernel (hedge_step.cu) and the
+// episode-fused rollout kernel (rollout.cu): constants, packed state helpers, the float32 ledger of one
+// env-step and the observation builders.
+//
+// Reference semantics: HedgingEnv.step / _get_observation / reset,
+// src/env/hedging_env_v2.py:175-294 / :109-143 / :145-173 (v1: src/env/hedging_env.py).
+#pragma once
+#include "bs_math.cuh"
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace cantor {
+
+// Everything derived from cantor_env_params once per launch, passed by value (lives in the constant bank).
+struct StepConsts {
+    // float64 ledger (F64 kernels)
+    double cost_per_contract, lambda_cost, neg_w, theta_weight, bps_frac, initial_cash, mult_d, shares_d;
+    // float32 ledger (F32 kernels): the same quantities, reciprocals instead of divisions
+    float cost_f, lambda_f, neg_w_f, theta_per_step_f, slip_f, inv_shares_f, mult_f, inv_mc_f, inv_T_f;
+    float shares_f, max_trade_f, initial_cash_f;
+    int max_trade, max_contracts, shares, loss_mse, T;
+    GreekConsts g;
+};
+
+struct Book {
+    const float4* __restrict__ rec;   // {S, v, C, P} at [t * ld + path]; row T carries the marks of row T-1
+    long long ld;
+    int n_paths;
+};
+
+__device__ __forceinline__ int unpack_lo(int packed) { return (int)(short)(packed & 0xffff); }
+__device__ __forceinline__ int unpack_hi(int packed) { return packed >> 16; }
+__device__ __forceinline__ int pack_pos(int c, int p) { return (c & 0xffff) | (p << 16); }
+
+// hedging_env_v2.py:181-188: float32 product, rint (half to even), int cast, clip.
+// NaN / +-inf / |x| >= 2^63 take the x86 "integer indefinite" value INT64_MIN in the reference's
+// astype(int), which the clip turns into -max_trade; reproduced here explicitly.
+__device__ __forceinline__ int requested_trade(float scaled, float max_trade_f) {
+    const float r = fminf(fmaxf(rintf(scaled), -max_trade_f), max_trade_f);
+    return (int)((fabsf(scaled) < 9.2233720368547758e18f) ? r : -max_trade_f);
+}
+
+__device__ __forceinline__ float clip_unit(float x) {          // np.clip(x, -1, 1); NaN stays NaN
+    const float c = fminf(fmaxf(x, -1.f), 1.f);
+    return (x != x) ? x : c;
+}
+
+// ---- float32 ledger of one env-step (hedging_env_v2.py:178-262) --------------------------------------
+// The portfolio value is never formed: the step P&L is the sum of three differences (stock leg, option
+// legs, cost), each small, so nothing cancels catastrophically and the float32 stock leg of the reference
+// (:235) enters exactly.  `prev` / `cur` are the path records at the env's step t and t+1.
+struct LedgerF32 {
+    int new_c, new_p, req_c, req_p;
+    float cf_c, cf_p, commission, slippage, costs, step_pnl, pps, rpc, tcp, theta_pen, reward, opt_new;
+};
+
+__device__ __forceinline__ LedgerF32 ledger_f32(const StepConsts& k, float ax, float ay, int pos_c, int pos_p, int step,
+                                                float inv_s0, const float4& prev, const float4& cur, bool frozen) {
+    LedgerF32 L;
+    L.cf_c = __fmul_rn(ax, k.max_trade_f);                                    // :181-182
+    L.cf_p = __fmul_rn(ay, k.max_trade_f);
+    L.req_c = requested_trade(L.cf_c, k.max_trade_f);
+    L.req_p = requested_trade(L.cf_p, k.max_trade_f);
+    L.new_c = frozen ? pos_c : max(-k.max_contracts, min(k.max_contracts, pos_c + L.req_c));   // :193-197
+    L.new_p = frozen ? pos_p : max(-k.max_contracts, min(k.max_contracts, pos_p + L.req_p));
+    const int atc = abs(L.new_c - pos_c), atp = abs(L.new_p - pos_p);
+    L.commission = (float)(atc + atp) * k.cost_f;                             // :203-204
+    L.slippage = fmaf((float)atc, prev.z, (float)atp * prev.w) * k.slip_f;    // :206-210 PRE-advance option prices
+    L.costs = L.commission + L.slippage;
+    const float d_stock = __fmul_rn(k.shares_f, cur.x) - __fmul_rn(k.shares_f, prev.x);
+    L.opt_new = fmaf((float)L.new_c, cur.z, (float)L.new_p * cur.w);
+    const float opt_old = fmaf((float)pos_c, prev.z, (float)pos_p * prev.w);
+    L.step_pnl = fmaf(L.opt_new - opt_old, k.mult_f, d_stock) - L.costs;      // :233-237
+    if (step == 0 && k.initial_cash_f != 0.f) {
+        // the reference's first portfolio_value_t_minus_1 is float32(stock + cash) (:167-168)
+        const float stock0 = __fmul_rn(k.shares_f, prev.x);
+        L.step_pnl += (stock0 - __fadd_rn(stock0, k.initial_cash_f)) + k.initial_cash_f;
+    }
+    L.pps = k.shares != 0 ? L.step_pnl * k.inv_shares_f : L.step_pnl;         // :238
+    const float term = k.loss_mse ? (L.pps * inv_s0) * (L.pps * inv_s0) : fabsf(L.pps) * inv_s0;   // :246-253
+    L.rpc = k.neg_w_f * term;
+    L.tcp = k.lambda_f * L.costs;
+    L.theta_pen = k.theta_per_step_f * (float)(k.T - (step + 1));             // :259-260
+    L.reward = frozen ? 0.f : (L.rpc - L.tcp) - L.theta_pen;                  // :262
+    return L;
+}
+
+// hedging_env_v2.py:109-143, float64 ledger.
+__device__ __forceinline__ void make_observation_f64(float* __restrict__ o, const StepConsts& k, float S, float v,
+                                                     float C, float P, float s0, int pos_c, int pos_p, int step,
+                                                     float S_prev, float v_prev) {
+    const float s0_safe = fmaxf(s0, 25.0f);                                   // :116
+    o[0] = __fdiv_rn(S, s0_safe);
+    o[1] = __fdiv_rn(C, s0_safe);
+    o[2] = __fdiv_rn(P, s0_safe);
+    o[3] = k.max_contracts != 0 ? (float)((double)pos_c / (double)k.max_contracts) : 0.f;   // :120 int64 / int
+    o[4] = k.max_contracts != 0 ? (float)((double)pos_p / (double)k.max_contracts) : 0.f;
+    o[5] = v;
+    o[6] = k.T != 0 ? (float)((double)(k.T - step) / (double)k.T) : 0.f;      // :122
+    const Greeks g = atm_greeks_f64(S, rintf(S), v, k.g);                     // :124-127, np.round = half to even
+    o[7] = g.call_delta;
+    o[8] = g.gamma;
+    o[9] = g.put_delta;
+    o[10] = g.gamma;
+    float ret = 0.f, dv = 0.f;
+    if (step != 0 && S_prev != 0.f) {                                         // :129-134
+        ret = __fdiv_rn(__fsub_rn(S, S_prev), S_prev);
+        dv = __fsub_rn(v, v_prev);
+    }
+    o[11] = clip_unit(ret);                                                   // :135-136
+    o[12] = clip_unit(dv);
+}
+
+// The same observation on the float32 throughput path (reciprocals from the SFU, no divisions).
+// `o` may point to shared memory (stride-13 rows) or to registers.
+__device__ __forceinline__ void make_observation_f32(float* __restrict__ o, const StepConsts& k, float S, float v,
+                                                     float C, float P, float inv_s0, int pos_c, int pos_p, int step,
+                                                     float S_prev, float v_prev) {
+    o[0] = S * inv_s0;
+    o[1] = C * inv_s0;
+    o[2] = P * inv_s0;
+    o[3] = (float)pos_c * k.inv_mc_f;
+    o[4] = (float)pos_p * k.inv_mc_f;
+    o[5] = v;
+    o[6] = (float)(k.T - step) * k.inv_T_f;
+    const Greeks g = atm_greeks_f32(S, rintf(S), v, k.g);
+    o[7] = g.call_delta;
+    o[8] = g.gamma;
+    o[9] = g.put_delta;
+    o[10] = g.gamma;
+    float ret = 0.f, dv = 0.f;
+    if (step != 0 && S_prev != 0.f) {
+        ret = (S - S_prev) * mufu_rcp(S_prev);
+        dv = v - v_prev;
+    }
+    o[11] = clip_unit(ret);
+    o[12] = clip_unit(dv);
+}
+
+// Host side: cantor_env_params -> StepConsts.  T = episode length.
+inline int make_step_consts(const cantor_env_params* p, int T, StepConsts* k) {
+    CANTOR_REQUIRE(p != nullptr, "params is NULL");
+    CANTOR_REQUIRE(T > 0, "episode_length must be positive");
+    CANTOR_REQUIRE(p->max_contracts_held >= 0 && p->max_contracts_held <= 32767, "max_contracts_held must be in [0, 32767]");
+    CANTOR_REQUIRE(p->max_trade_per_step >= 0 && p->max_trade_per_step <= 32767, "max_trade_per_step must be in [0, 32767]");
+    CANTOR_REQUIRE(p->loss_type == CANTOR_LOSS_ABS || p->loss_type == CANTOR_LOSS_MSE, "loss_type");
+    k->cost_per_contract = p->transaction_cost_per_contract;
+    k->lambda_cost = p->lambda_cost;
+    k->neg_w = -p->pnl_penalty_weight;
+    k->theta_weight = p->theta_weight;
+    k->bps_frac = p->slippage_bps / 10000.0;                                  // hedging_env_v2.py:207
+    k->initial_cash = p->initial_cash;
+    k->mult_d = (double)p->option_contract_multiplier;
+    k->shares_d = (double)p->shares_to_hedge;
+    k->cost_f = (float)k->cost_per_contract;
+    k->lambda_f = (float)k->lambda_cost;
+    k->neg_w_f = (float)k->neg_w;
+    k->theta_per_step_f = (float)(p->theta_weight / 252.0);
+    k->slip_f = (float)(k->mult_d * k->bps_frac);
+    k->inv_shares_f = p->shares_to_hedge != 0 ? (float)(1.0 / k->shares_d) : 1.0f;
+    k->mult_f = (float)k->mult_d;
+    k->inv_mc_f = p->max_contracts_held != 0 ? (float)(1.0 / (double)p->max_contracts_held) : 0.0f;
+    k->inv_T_f = (float)(1.0 / (double)T);
+    k->shares_f = (float)p->shares_to_hedge;
+    k->max_trade_f = (float)p->max_trade_per_step;
+    k->initial_cash_f = (float)p->initial_cash;
+    k->max_trade = p->max_trade_per_step;
+    k->max_contracts = p->max_contracts_held;
+    k->shares = p->shares_to_hedge;
+    k->loss_mse = p->loss_type == CANTOR_LOSS_MSE;
+    k->T = T;
+    k->g.r_f = (float)p->risk_free_rate;
+    k->g.T_f = (float)p->option_tenor_years;
+    k->g.T_d = p->option_tenor_years;
+    k->g.sqrtT_d = sqrt(p->option_tenor_years);
+    k->g.inv_sqrtT_f = p->option_tenor_years > 0 ? (float)(1.0 / k->g.sqrtT_d) : 0.f;
+    k->g.record_metrics = p->record_metrics;
+    return CANTOR_OK;
+}
+
+inline int make_book(const cantor_replay_book* book, Book* b) {
+    CANTOR_REQUIRE(book != nullptr && book->svcp != nullptr, "book is NULL");
+    CANTOR_REQUIRE(aligned16(book->svcp), "book.svcp must be 16-byte aligned");
+    CANTOR_REQUIRE(book->n_paths > 0 && book->episode_length > 0, "empty book");
+    CANTOR_REQUIRE(book->ld >= book->n_paths, "ld < n_paths");
+    b->rec = reinterpret_cast<const float4*>(book->svcp);
+    b->ld = book->ld;
+    b->n_paths = book->n_paths;
+    return CANTOR_OK;
+}
+
+}  // namespace cantor

@@ -10,48 +10,9 @@
 // columns, and the output schema (:528).  The reference's nested-MC pricer (:246-306) is replaced by the
 // closed form, as BASELINE.json's north_star prescribes.  cantor_euler_from_normals replays the reference's
 // own float64 step on exported normals for parity.
-#include "bs_math.cuh"
-#include "common.cuh"
-#include "philox.cuh"
+#include "sim_core.cuh"
 
 namespace cantor {
-
-constexpr unsigned kStreamPaths = 0x50415448u;   // "PATH": 4th counter word of the path-simulation stream
-
-struct SimConsts {
-    float s0, v0, r, dt, sqrt_dt, kappa, theta, sigma_v, rho, rho_c;
-    float drift_gbm, vol_gbm;            // (r - v0/2) dt, sqrt(v0 dt)
-    float tenor, sqrt_tenor, disc;       // option tenor, its sqrt, exp(-r tenor)
-    unsigned seed_lo, seed_hi;
-    long long path_offset;
-    int model, reprice, T;
-};
-
-// Box-Muller on two Philox words (oracle/sim_oracle.py: philox_normals).
-__device__ __forceinline__ void box_muller(unsigned x0, unsigned x1, float& n0, float& n1) {
-    const float u1 = ((float)x0 + 1.0f) * 2.3283064365386963e-10f;       // (0, 1]
-    const float u2 = (float)x1 * 2.3283064365386963e-10f;                 // [0, 1]
-    const float rad = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincosf(6.283185307179586f * u2, &s, &c);
-    n0 = rad * c;
-    n1 = rad * s;
-}
-
-// ATM call / put, float32: K = rint(S), sigma = sqrt(max(v, 0)) floored at 1e-8 (option_price_assignment.py:10-21).
-__device__ __forceinline__ void atm_call_put_f32(float S, float v, const SimConsts& k, float& call, float& put) {
-    const float K = rintf(S);
-    const float sigma = fmaxf(sqrtf(fmaxf(v, 0.0f)), 1e-8f);
-    const float sst = sigma * k.sqrt_tenor;
-    const float d1 = (logf(S / K) + (k.r + 0.5f * sigma * sigma) * k.tenor) / sst;
-    const float d2 = d1 - sst;
-    float c1, c1m, c2, c2m;
-    normal_pdf_cdf(d1, &c1, &c1m);
-    normal_pdf_cdf(d2, &c2, &c2m);
-    const float kd = K * k.disc;
-    call = S * c1 - kd * c2;
-    put = S * c1m - kd * c2m;            // K disc Phi(-d2) - S Phi(-d1), with Phi(-x) = -(Phi(x) - 1)
-}
 
 template <int MODEL>   // 0 GBM, 1 Heston
 __global__ void __launch_bounds__(128)
@@ -67,23 +28,12 @@ sim_paths_kernel(const SimConsts k, int n_paths, float4* __restrict__ rec, long 
     constexpr int NPS = MODEL == 0 ? 1 : 2;                                  // normals per step
     int t = 0;
     for (unsigned call = 0; t < k.T; ++call) {                               // one Philox call = 4 normals
-        const uint4 x = philox4x32_10(make_uint4((unsigned)gp, (unsigned)(gp >> 32), call, kStreamPaths), key);
         float z[4];
-        box_muller(x.x, x.y, z[0], z[1]);
-        box_muller(x.z, x.w, z[2], z[3]);
+        path_normals(k, gp, call, z);
 #pragma unroll
         for (int j = 0; j < 4 / NPS; ++j) {
             if (t < k.T) {
-                if (MODEL == 0) {
-                    S = fmaxf(S * expf(k.drift_gbm + k.vol_gbm * z[j]), 1e-8f);
-                } else {
-                    const float z1 = z[2 * j], z2 = z[2 * j + 1];
-                    const float vp = fmaxf(v, 0.0f);
-                    const float sq = sqrtf(vp * k.dt);
-                    const float zv = k.rho * z1 + k.rho_c * z2;                      // rbergomi_sim.py:457
-                    S = fmaxf(S * expf((k.r - 0.5f * vp) * k.dt + sq * z1), 1e-8f);  // :460-464
-                    v = v + k.kappa * (k.theta - vp) * k.dt + k.sigma_v * sq * zv;   // full-truncation Euler
-                }
+                sim_advance<MODEL>(k, S, v, z[NPS * j], z[NPS * j + NPS - 1]);
                 ++t;
                 out.x = S;
                 out.y = fmaxf(v, 0.0f);
@@ -137,19 +87,6 @@ reprice_atm_kernel(const SimConsts k, int n_paths, float4* __restrict__ rec, lon
     rec[(long long)t * ld + p] = me;
 }
 
-static void fill_consts(const cantor_sim_params* p, int T, SimConsts* k) {
-    k->s0 = (float)p->s0; k->v0 = (float)p->v0; k->r = (float)p->r; k->dt = (float)p->dt;
-    k->sqrt_dt = (float)sqrt(p->dt);
-    k->kappa = (float)p->kappa; k->theta = (float)p->theta; k->sigma_v = (float)p->sigma_v; k->rho = (float)p->rho;
-    k->rho_c = (float)sqrt(fmax(0.0, 1.0 - p->rho * p->rho));
-    k->drift_gbm = (float)((p->r - 0.5 * p->v0) * p->dt);
-    k->vol_gbm = (float)sqrt(p->v0 * p->dt);
-    k->tenor = (float)p->tenor; k->sqrt_tenor = (float)sqrt(p->tenor); k->disc = (float)exp(-p->r * p->tenor);
-    k->seed_lo = (unsigned)(p->seed & 0xffffffffull); k->seed_hi = (unsigned)(p->seed >> 32);
-    k->path_offset = p->path_offset;
-    k->model = p->model; k->reprice = p->reprice; k->T = T;
-}
-
 }  // namespace cantor
 
 using namespace cantor;
@@ -162,7 +99,7 @@ extern "C" int cantor_sim_paths(const cantor_sim_params* params, int32_t n_paths
     CANTOR_REQUIRE(aligned16(svcp), "svcp must be 16-byte aligned");
     CANTOR_REQUIRE(params->dt > 0 && params->tenor > 0, "dt and tenor must be positive");
     SimConsts k;
-    fill_consts(params, episode_length, &k);
+    fill_sim_consts(params, episode_length, &k);
     const unsigned grid = (unsigned)((n_paths + 127) / 128);
     cudaStream_t s = (cudaStream_t)stream;
     if (params->model == CANTOR_MODEL_GBM) sim_paths_kernel<0><<<grid, 128, 0, s>>>(k, n_paths, (float4*)svcp, ld);
@@ -177,7 +114,7 @@ extern "C" int cantor_reprice_atm(float* svcp, int64_t ld, int32_t n_paths, int3
     cantor_sim_params p = {};
     p.r = r; p.tenor = tenor; p.dt = 1.0 / 252;
     SimConsts k;
-    fill_consts(&p, episode_length, &k);
+    fill_sim_consts(&p, episode_length, &k);
     const dim3 grid((n_paths + 255) / 256, episode_length + 1);
     reprice_atm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(k, n_paths, (float4*)svcp, ld);
     return check_launch("reprice_atm_kernel");

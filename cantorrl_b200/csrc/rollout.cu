@@ -1,0 +1,389 @@
+// Episode-fused rollout: path step (replayed or simulated on the fly) -> ATM repricing -> observation ->
+// policy -> fused hedge step -> episode statistics, for many consecutive steps in ONE kernel with the whole
+// env state in registers.  Nothing is written per step unless rollout storage is requested, so this mode is
+// bound by the FP32 / SFU pipes, not by HBM.  Episode statistics are reduced warp -> block -> one atomic per
+// block, giving the small vector (and histogram) that the multi-GPU all-reduce sums.
+//
+// Reference semantics: the evaluation loops around HedgingEnv --
+//   evaluate_baseline_policy      src/agents/baselines.py:32-72       (per-episode mean |dPnL|, mean cost)
+//   run_evaluation statistics     src/agents/train_ppo_v2.py:482-530  (|sum dPnL| / T, cost / T, CVaR95)
+//   policy_delta_every_step       src/agents/baselines.py:77-103
+//   delta_hedging_action_selector src/benchmark/delta_and_nothing.py:122-163
+//   random policy                 src/agents/test_inf.py:29 (action_space.sample())
+//   MLP actor 13-64-64-2          quantconnect/model_wrapper.py:131,177-185 (normalise, ReLU MLP, clip)
+// and the env step itself (hedge_core.cuh).
+#include "hedge_core.cuh"
+#include "sim_core.cuh"
+
+namespace cantor {
+
+constexpr int kRollThreads = 128;
+constexpr unsigned kStreamActions = 0x4143544Eu;   // "ACTN": 4th counter word of the random-policy stream
+constexpr int kMlpIn = 13, kMlpHidden = 64, kMlpOut = 2;
+constexpr int kMlpFloats = kMlpIn * kMlpHidden + kMlpHidden + kMlpHidden * kMlpHidden + kMlpHidden +
+                           kMlpHidden * kMlpOut + kMlpOut + 2 * kMlpIn;          // 5212
+
+struct PolicyConsts {
+    int kind, put_disabled;
+    const float* mlp;
+    const float2* actions;      // CANTOR_POLICY_ACTIONS: [n_steps, n_envs] open-loop actions
+    unsigned seed_lo, seed_hi;
+};
+
+struct RolloutOut {
+    float* obs;                 // [n_steps, n_envs, 13] observation the policy saw
+    float2* actions;            // [n_steps, n_envs]
+    float* reward;              // [n_steps, n_envs]
+    unsigned char* done;        // [n_steps, n_envs]
+};
+
+struct StatsOut {
+    double* sums;               // [CANTOR_STATS_LEN]
+    unsigned long long* hist;   // [hist_bins] of b = |sum pps| / T, or NULL
+    double* hist_sum;           // [hist_bins] sum of b per bin, or NULL
+    float* episode_b;           // [n_episodes_per_env, n_envs] or NULL: per-episode b for an exact CVaR
+    float hist_scale;           // bins / hist_max
+    int hist_bins;
+    long long episode_slots;    // capacity of episode_b in episodes per env
+};
+
+// ---- policies ------------------------------------------------------------------------------------------
+// baselines.py:77-103 evaluated in float32 like NumPy does on a float32 observation (python ints are weak).
+// Returns CONTRACT COUNTS clipped to +-max_trade, which the env then multiplies by max_trade again and clips
+// (the reference's behaviour).
+__device__ __forceinline__ float2 policy_delta_baselines(const float* o, const StepConsts& k) {
+    const float cd = o[7], pd = o[9];
+    const float mc = (float)k.max_contracts;
+    const float cpos = __fmul_rn(o[3], mc), ppos = __fmul_rn(o[4], mc);
+    const float opt_delta = __fmul_rn(__fadd_rn(__fmul_rn(cpos, cd), __fmul_rn(ppos, pd)), k.mult_f);
+    const float target = -__fadd_rn(k.shares_f, opt_delta);
+    float tc = 0.f, tp = 0.f;
+    const float cdm = __fmul_rn(cd, k.mult_f), pdm = __fmul_rn(pd, k.mult_f);
+    if (fabsf(cdm) > 0.1f) tc = __fdiv_rn(target, cdm);
+    else if (fabsf(pdm) > 0.1f) tp = __fdiv_rn(target, pdm);
+    return make_float2(fminf(fmaxf(tc, -k.max_trade_f), k.max_trade_f), fminf(fmaxf(tp, -k.max_trade_f), k.max_trade_f));
+}
+
+// delta_and_nothing.py:122-163 (float32 here; the reference mixes float32 / float64).
+__device__ __forceinline__ float2 policy_delta_benchmark(const float* o, const StepConsts& k, int pos_c, int pos_p) {
+    const float cd = o[7], pd = o[9];
+    const float cur = ((float)pos_c * cd + (float)pos_p * pd) * k.mult_f;
+    const float change = -k.shares_f - cur;
+    if (fabsf(change) < 0.5f * fabsf(cd) * k.mult_f) return make_float2(0.f, 0.f);
+    float rc = 0.f, rp = 0.f;
+    if (change > 0.f) {
+        if (fabsf(cd) > 1e-6f) rc = fminf(fmaxf(change / (cd * k.mult_f), -k.max_trade_f), k.max_trade_f);
+    } else if (change < 0.f) {
+        if (fabsf(pd) > 1e-6f) rp = fminf(fmaxf(change / (pd * k.mult_f), -k.max_trade_f), k.max_trade_f);
+    }
+    return make_float2(rc, rp);
+}
+
+// uniform(-1, 1) pair from Philox(seed; global env, global step, "ACTN")
+__device__ __forceinline__ float2 policy_random(const PolicyConsts& pc, unsigned long long genv, unsigned step) {
+    const uint4 x = philox4x32_10(make_uint4((unsigned)genv, (unsigned)(genv >> 32), step, kStreamActions),
+                                  make_uint2(pc.seed_lo, pc.seed_hi));
+    return make_float2(fmaf((float)(x.x >> 8), 1.1920928955078125e-07f, -1.0f),      // [-1, 1)
+                       fmaf((float)(x.y >> 8), 1.1920928955078125e-07f, -1.0f));
+}
+
+// ReLU MLP 13 -> 64 -> 64 -> 2 on the normalised observation; weights broadcast from shared memory.
+__device__ __forceinline__ float2 policy_mlp(const float* o, const float* __restrict__ w) {
+    const float* W1 = w;
+    const float* b1 = W1 + kMlpIn * kMlpHidden;
+    const float* W2 = b1 + kMlpHidden;
+    const float* b2 = W2 + kMlpHidden * kMlpHidden;
+    const float* W3 = b2 + kMlpHidden;
+    const float* b3 = W3 + kMlpHidden * kMlpOut;
+    const float* mean = b3 + kMlpOut;
+    const float* inv_std = mean + kMlpIn;
+    float x[kMlpIn];
+#pragma unroll
+    for (int i = 0; i < kMlpIn; ++i) x[i] = fminf(fmaxf((o[i] - mean[i]) * inv_std[i], -10.f), 10.f);   // VecNormalize clip
+    float h1[kMlpHidden];
+#pragma unroll
+    for (int j = 0; j < kMlpHidden; ++j) h1[j] = b1[j];
+#pragma unroll
+    for (int i = 0; i < kMlpIn; ++i) {
+#pragma unroll
+        for (int j = 0; j < kMlpHidden; j += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(W1 + i * kMlpHidden + j);
+            h1[j] = fmaf(x[i], wv.x, h1[j]); h1[j + 1] = fmaf(x[i], wv.y, h1[j + 1]);
+            h1[j + 2] = fmaf(x[i], wv.z, h1[j + 2]); h1[j + 3] = fmaf(x[i], wv.w, h1[j + 3]);
+        }
+    }
+    float out0 = b3[0], out1 = b3[1];
+    // layer 2 is produced 4 outputs at a time and consumed immediately by layer 3 (h2 never materialised)
+#pragma unroll 1
+    for (int j = 0; j < kMlpHidden; j += 4) {
+        float a0 = b2[j], a1 = b2[j + 1], a2 = b2[j + 2], a3 = b2[j + 3];
+#pragma unroll
+        for (int i = 0; i < kMlpHidden; ++i) {
+            const float hi = fmaxf(h1[i], 0.f);
+            const float4 wv = *reinterpret_cast<const float4*>(W2 + i * kMlpHidden + j);
+            a0 = fmaf(hi, wv.x, a0); a1 = fmaf(hi, wv.y, a1); a2 = fmaf(hi, wv.z, a2); a3 = fmaf(hi, wv.w, a3);
+        }
+        a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f);
+        out0 = fmaf(a0, W3[(j + 0) * 2], out0); out1 = fmaf(a0, W3[(j + 0) * 2 + 1], out1);
+        out0 = fmaf(a1, W3[(j + 1) * 2], out0); out1 = fmaf(a1, W3[(j + 1) * 2 + 1], out1);
+        out0 = fmaf(a2, W3[(j + 2) * 2], out0); out1 = fmaf(a2, W3[(j + 2) * 2 + 1], out1);
+        out0 = fmaf(a3, W3[(j + 3) * 2], out0); out1 = fmaf(a3, W3[(j + 3) * 2 + 1], out1);
+    }
+    return make_float2(fminf(fmaxf(out0, -1.f), 1.f), fminf(fmaxf(out1, -1.f), 1.f));
+}
+
+// ---- statistics --------------------------------------------------------------------------------------------
+// Block reduction of NS doubles per thread, then one atomicAdd per value per block.
+template <int NS>
+__device__ __forceinline__ void block_accumulate(double (&v)[NS], double* __restrict__ global, double* smem /* [NS * 4] */) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[s] += __shfl_down_sync(0xffffffffu, v[s], off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) smem[s * (kRollThreads / 32) + warp] = v[s];
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kRollThreads / 32; ++w) t += smem[threadIdx.x * (kRollThreads / 32) + w];
+        atomicAdd(global + threadIdx.x, t);
+    }
+    __syncthreads();
+}
+
+// SRC: 0 replay (packed book), 1 GBM on the fly, 2 Heston on the fly.
+// MLP: the policy is the MLP (compile-time, so the other policies do not pay for its registers).
+template <int SRC, bool MLP, bool WRITE>
+__global__ void __launch_bounds__(kRollThreads)
+rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const PolicyConsts pc, long long n_envs,
+               long long env_offset, long long total_envs, int n_steps, const StatsOut st, const RolloutOut out,
+               int obs_tma_ok) {
+    extern __shared__ __align__(128) float smem_f[];
+    float* w_mlp = smem_f;                                                     // [kMlpFloats] when the policy is the MLP
+    constexpr int mlp_floats = MLP ? (kMlpFloats + 3) / 4 * 4 : 0;
+    float* tile = smem_f + mlp_floats;                                         // [kRollThreads * 13] when WRITE
+    double* red = reinterpret_cast<double*>(tile + (WRITE ? kRollThreads * CANTOR_OBS_DIM : 0));
+    if (MLP) {
+        for (int j = threadIdx.x; j < kMlpFloats; j += kRollThreads) w_mlp[j] = pc.mlp[j];
+    }
+    __syncthreads();
+
+    const long long first_env = (long long)blockIdx.x * kRollThreads;
+    const long long i = first_env + threadIdx.x;
+    const bool live = i < n_envs;
+    const int rows = (int)min((long long)kRollThreads, n_envs - first_env);
+    const unsigned long long genv = (unsigned long long)(env_offset + (live ? i : 0));
+    constexpr int MODEL = SRC == 2 ? 1 : 0;
+    constexpr int NPS = SRC == 2 ? 2 : 1;
+    constexpr int STEPS_PER_CALL = SRC == 0 ? 1 : 4 / NPS;
+
+    // env state, all in registers
+    int pos_c = 0, pos_p = 0, t = 0;
+    long long episode = 0;
+    unsigned long long gp = genv;                                              // global path of the current episode
+    float4 cur = make_float4(0.f, 0.f, 0.f, 0.f), prev;
+    float S = 0.f, v = 0.f, s0 = 1.f, inv_s0 = 1.f;
+    float acc_pps = 0.f, acc_abs = 0.f, acc_cost = 0.f, acc_reward = 0.f;
+    double stat[11];
+#pragma unroll
+    for (int s = 0; s < 11; ++s) stat[s] = 0.0;
+
+    auto begin_episode = [&]() {
+        gp = (unsigned long long)episode * (unsigned long long)total_envs + genv;
+        if (SRC == 0) {
+            cur = b.rec[(long long)(gp % (unsigned long long)b.n_paths)];
+        } else {
+            S = sk.s0;
+            v = sk.v0;
+            cur.x = S;
+            cur.y = fmaxf(v, 0.f);
+            atm_call_put_f32(cur.x, cur.y, sk, cur.z, cur.w);
+        }
+        prev = cur;
+        s0 = (cur.x < 1e-6f) ? 1.0f : cur.x;                                   // hedging_env_v2.py:157
+        inv_s0 = mufu_rcp(fmaxf(s0, 25.0f));
+        pos_c = pos_p = 0;
+        t = 0;
+        acc_pps = acc_abs = acc_cost = acc_reward = 0.f;
+    };
+    begin_episode();
+
+    int g = 0;                                                                 // global step of the rollout
+    while (g < n_steps) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (SRC != 0) path_normals(sk, gp, (unsigned)((t * NPS) >> 2), z);
+#pragma unroll
+        for (int j = 0; j < STEPS_PER_CALL; ++j) {
+            if (g >= n_steps) break;
+            // ---- observation of the current state and the policy's action --------------------------------
+            float o[CANTOR_OBS_DIM];
+            make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y);
+            float2 a;
+            if (MLP) {
+                a = policy_mlp(o, w_mlp);
+            } else {
+                switch (pc.kind) {
+                    case CANTOR_POLICY_RANDOM: a = policy_random(pc, genv, (unsigned)g); break;
+                    case CANTOR_POLICY_DELTA_BASELINES: a = policy_delta_baselines(o, k); break;
+                    case CANTOR_POLICY_DELTA_BENCHMARK: a = policy_delta_benchmark(o, k, pos_c, pos_p); break;
+                    case CANTOR_POLICY_ACTIONS: a = live ? __ldcs(pc.actions + (long long)g * n_envs + i) : make_float2(0.f, 0.f); break;
+                    default: a = make_float2(0.f, 0.f);
+                }
+            }
+            if (pc.put_disabled) a.y = 0.f;
+            // ---- next path record -------------------------------------------------------------------------
+            float4 nxt;
+            if (SRC == 0) {
+                nxt = live ? __ldcs(b.rec + ((long long)(t + 1) * b.ld + (long long)(gp % (unsigned long long)b.n_paths))) : cur;
+            } else {
+                sim_advance<MODEL>(sk, S, v, z[NPS * j], z[NPS * j + NPS - 1]);
+                nxt.x = S;
+                nxt.y = fmaxf(v, 0.f);
+                nxt.z = cur.z;
+                nxt.w = cur.w;                                                 // stale marks at the terminal step (:226-231)
+                if (t + 1 < k.T) atm_call_put_f32(nxt.x, nxt.y, sk, nxt.z, nxt.w);
+            }
+            // ---- fused hedge step ---------------------------------------------------------------------------
+            const LedgerF32 L = ledger_f32(k, a.x, a.y, pos_c, pos_p, t, inv_s0, cur, nxt, false);
+            const bool terminated = t + 1 >= k.T;
+            if (WRITE) {
+                float* orow = tile + threadIdx.x * CANTOR_OBS_DIM;
+#pragma unroll
+                for (int q = 0; q < CANTOR_OBS_DIM; ++q) orow[q] = o[q];
+                float* dst = out.obs + ((long long)g * n_envs + first_env) * CANTOR_OBS_DIM;
+                const bool tma = obs_tma_ok && (rows % 4 == 0) && ((((long long)g * n_envs) & 3) == 0);
+                if (tma) {
+                    fence_proxy_async_smem();
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        tma_store_1d(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
+                        tma_store_commit();
+                        tma_store_wait_read();
+                    }
+                    __syncthreads();
+                } else {
+                    __syncthreads();
+                    for (int q = threadIdx.x; q < rows * CANTOR_OBS_DIM; q += kRollThreads) dst[q] = tile[q];
+                    __syncthreads();
+                }
+                if (live) {
+                    const long long at = (long long)g * n_envs + i;
+                    __stcs(out.actions + at, a);
+                    __stcs(out.reward + at, L.reward);
+                    out.done[at] = terminated ? 1 : 0;
+                }
+            }
+            acc_pps += L.pps;
+            acc_abs += fabsf(L.pps);
+            acc_cost += L.costs;
+            acc_reward += L.reward;
+            pos_c = L.new_c;
+            pos_p = L.new_p;
+            prev = cur;
+            cur = nxt;
+            ++t;
+            ++g;
+            if (terminated) {
+                if (live) {
+                    const float invT = k.inv_T_f;
+                    const double ea = (double)(acc_abs * invT);                // baselines.py:54
+                    const double eb = (double)(fabsf(acc_pps) * invT);         // train_ppo_v2.py:520
+                    const double ec = (double)(acc_cost * invT);               // :521 / baselines.py:55
+                    const double er = (double)acc_reward, es = (double)acc_pps;
+                    stat[0] += 1.0;
+                    stat[1] += ea; stat[2] += ea * ea;
+                    stat[3] += eb; stat[4] += eb * eb;
+                    stat[5] += ec; stat[6] += ec * ec;
+                    stat[7] += er; stat[8] += er * er;
+                    stat[9] += es; stat[10] += es * es;
+                    if (st.hist != nullptr) {
+                        const int bin = min(st.hist_bins - 1, max(0, (int)((float)eb * st.hist_scale)));
+                        atomicAdd(st.hist + bin, 1ull);
+                        if (st.hist_sum != nullptr) atomicAdd(st.hist_sum + bin, eb);
+                    }
+                    if (st.episode_b != nullptr && episode < st.episode_slots)
+                        st.episode_b[episode * n_envs + i] = (float)eb;
+                }
+                ++episode;
+                begin_episode();
+                break;                                                         // the new path starts a new Philox call
+            }
+        }
+    }
+    // ---- one reduction at the end: warp shuffle -> shared -> one atomic per statistic per block ---------------
+    if (st.sums != nullptr) block_accumulate<11>(stat, st.sums, red);
+    if (st.sums != nullptr && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(st.sums + 11, (double)n_envs * (double)n_steps);
+}
+
+}  // namespace cantor
+
+using namespace cantor;
+
+extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_replay_book* book,
+                              const cantor_sim_params* sim, int32_t episode_length, const cantor_policy* policy,
+                              int64_t n_envs, int64_t env_offset, int64_t total_envs, int32_t n_steps,
+                              const cantor_stats_out* stats, const cantor_rollout_out* out, void* stream) {
+    CANTOR_REQUIRE(params != nullptr && policy != nullptr, "params/policy is NULL");
+    CANTOR_REQUIRE((book != nullptr) != (sim != nullptr), "exactly one of book / sim must be given");
+    CANTOR_REQUIRE(n_envs > 0 && n_steps >= 0 && total_envs >= n_envs && env_offset >= 0, "bad sizes");
+    CANTOR_REQUIRE(policy->kind >= CANTOR_POLICY_NO_HEDGE && policy->kind <= CANTOR_POLICY_ACTIONS, "policy kind");
+    CANTOR_REQUIRE(policy->kind != CANTOR_POLICY_MLP || policy->mlp != nullptr, "policy.mlp is NULL");
+    CANTOR_REQUIRE(policy->kind != CANTOR_POLICY_ACTIONS || policy->actions != nullptr, "policy.actions is NULL");
+    StepConsts k;
+    Book b{nullptr, 0, 1};
+    SimConsts sk = {};
+    int T = episode_length;
+    int src = 0;
+    if (book != nullptr) {
+        int rc = make_book(book, &b);
+        if (rc) return rc;
+        T = book->episode_length;
+    } else {
+        CANTOR_REQUIRE(sim->model == CANTOR_MODEL_GBM || sim->model == CANTOR_MODEL_HESTON, "sim.model");
+        CANTOR_REQUIRE(sim->dt > 0 && sim->tenor > 0, "dt and tenor must be positive");
+        fill_sim_consts(sim, T, &sk);
+        src = sim->model == CANTOR_MODEL_GBM ? 1 : 2;
+    }
+    int rc = make_step_consts(params, T, &k);
+    if (rc) return rc;
+    PolicyConsts pc{policy->kind, policy->put_leg_disabled, policy->mlp, (const float2*)policy->actions,
+                    (unsigned)(policy->seed & 0xffffffffull), (unsigned)(policy->seed >> 32)};
+    StatsOut so{nullptr, nullptr, nullptr, nullptr, 0.f, 0, 0};
+    if (stats != nullptr) {
+        CANTOR_REQUIRE(stats->sums != nullptr, "stats.sums is NULL");
+        CANTOR_REQUIRE(stats->hist == nullptr || (stats->hist_bins > 0 && stats->hist_max > 0), "histogram needs bins and a range");
+        so = StatsOut{stats->sums, (unsigned long long*)stats->hist, stats->hist ? stats->hist_sum : nullptr, stats->episode_b,
+                      stats->hist ? (float)(stats->hist_bins / stats->hist_max) : 0.f, stats->hist_bins, stats->episode_slots};
+    }
+    RolloutOut ro{nullptr, nullptr, nullptr, nullptr};
+    const bool write = out != nullptr;
+    if (write) {
+        CANTOR_REQUIRE(out->obs && out->actions && out->reward && out->done, "rollout output array is NULL");
+        ro = RolloutOut{out->obs, (float2*)out->actions, out->reward, out->done};
+    }
+    if (n_steps == 0) return CANTOR_OK;
+    const unsigned grid = (unsigned)((n_envs + kRollThreads - 1) / kRollThreads);
+    const size_t smem = (policy->kind == CANTOR_POLICY_MLP ? (kMlpFloats + 3) / 4 * 4 * sizeof(float) : 0) +
+                        (write ? kRollThreads * CANTOR_OBS_DIM * sizeof(float) : 0) + 11 * (kRollThreads / 32) * sizeof(double) + 16;
+    const int tma_ok = write && aligned16(out->obs) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool mlp = policy->kind == CANTOR_POLICY_MLP;
+#define LAUNCH(SRC, MLP, WRITE) \
+    rollout_kernel<SRC, MLP, WRITE><<<grid, kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok)
+#define LAUNCH_SRC(SRC)                                                      \
+    do {                                                                     \
+        if (mlp) { if (write) LAUNCH(SRC, true, true); else LAUNCH(SRC, true, false); } \
+        else { if (write) LAUNCH(SRC, false, true); else LAUNCH(SRC, false, false); }   \
+    } while (0)
+    if (src == 0) LAUNCH_SRC(0);
+    else if (src == 1) LAUNCH_SRC(1);
+    else LAUNCH_SRC(2);
+#undef LAUNCH_SRC
+#undef LAUNCH
+    return check_launch("rollout_kernel");
+}

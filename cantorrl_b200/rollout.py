@@ -1,0 +1,169 @@
+"""Episode-fused rollouts: policy + env step + (optionally) path simulation in one kernel, with episode statistics.
+
+Host-side mirror of the loops the reference runs around its env:
+
+  ``evaluate_baseline_policy``   src/agents/baselines.py:32-72          (no-hedge / delta-every-step policies)
+  ``run_benchmark_strategy``     src/benchmark/delta_and_nothing.py:34-114
+  ``run_evaluation``             src/agents/train_ppo_v2.py:465-530     (policy -> env.step -> per-episode statistics)
+  random policy                  src/agents/test_inf.py:27-39
+
+``HedgingRollout`` takes the reference env's constructor keywords; ``run`` forwards to ``cantor_rollout``
+(``include/cantor_hedge.h``), which keeps the whole env state in registers for ``n_steps`` consecutive env-steps,
+so nothing is written per step unless rollout storage is asked for.  Envs are identified by a GLOBAL index
+(``env_offset + i`` of ``total_envs``) that drives every Philox counter: the statistics of a population do not
+depend on how it is sharded over GPUs, and shards combine with ``EpisodeStats.all_reduce``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .data import ReplayData
+from .stats import EpisodeStats
+
+POLICIES = {"no_hedge": _lib.POLICY_NO_HEDGE, "random": _lib.POLICY_RANDOM,
+            "delta_every_step": _lib.POLICY_DELTA_BASELINES, "delta_benchmark": _lib.POLICY_DELTA_BENCHMARK}
+
+
+def pack_mlp(W1, b1, W2, b2, W3, b3, obs_mean=None, obs_var=None, epsilon=1e-8, device="cuda") -> torch.Tensor:
+    """Actor weights in ``torch.nn.Linear`` layout (``[out, in]``) -> the flat float32 block ``cantor_policy.mlp`` wants.
+
+    Layout: ``W1[13][64] b1[64] W2[64][64] b2[64] W3[64][2] b3[2] obs_mean[13] obs_inv_std[13]`` (input-major weights).
+    ``obs_mean`` / ``obs_var`` are VecNormalize's running statistics; the kernel applies
+    ``clip((obs - mean) / sqrt(var + 1e-8), -10, 10)`` (quantconnect/model_wrapper.py:131) before the first layer.
+    """
+    def t(x, shape):
+        x = torch.as_tensor(np.asarray(x.detach().cpu() if isinstance(x, torch.Tensor) else x, np.float32))
+        if tuple(x.shape) != shape:
+            raise ValueError(f"expected shape {shape}, got {tuple(x.shape)}")
+        return x
+    W1, b1, W2, b2, W3, b3 = t(W1, (64, 13)), t(b1, (64,)), t(W2, (64, 64)), t(b2, (64,)), t(W3, (2, 64)), t(b3, (2,))
+    mean = t(obs_mean, (13,)) if obs_mean is not None else torch.zeros(13)
+    var = t(obs_var, (13,)) if obs_var is not None else torch.ones(13) - epsilon
+    inv_std = (1.0 / torch.sqrt(var.double() + epsilon)).float()
+    flat = torch.cat([W1.T.contiguous().flatten(), b1, W2.T.contiguous().flatten(), b2, W3.T.contiguous().flatten(), b3,
+                      mean, inv_std])
+    assert flat.numel() == _lib.MLP_FLOATS
+    return flat.to(device)
+
+
+@dataclass
+class RolloutResult:
+    stats: EpisodeStats
+    n_steps: int
+    obs: Optional[torch.Tensor] = None        # [n_steps, n_envs, 13] observation the policy acted on
+    actions: Optional[torch.Tensor] = None    # [n_steps, n_envs, 2]
+    reward: Optional[torch.Tensor] = None     # [n_steps, n_envs]
+    done: Optional[torch.Tensor] = None       # [n_steps, n_envs] bool
+
+
+class HedgingRollout:
+    """``num_envs`` hedging environments advanced for many steps by one kernel launch.
+
+    Reference keywords as in ``HedgingVecEnv`` (hedging_env_v2.py:10-22).  Data source: ``data`` (a ``ReplayData``
+    book or a dict of the npz arrays, replayed) or ``simulate=dict(model="gbm"|"heston", seed=..., s0=..., v0=...,
+    kappa=..., theta=..., sigma_v=..., rho=..., n_steps=252)`` (paths and ATM marks generated on the fly from the
+    same Philox counters ``sim.generate_paths_and_options`` uses).  Episode ``e`` of global env ``g`` runs on
+    global path ``e * total_envs + g`` (modulo the book size when replaying).
+    """
+
+    def __init__(self, data_file_path=None, transaction_cost_per_contract=0.65, lambda_cost=1.0, pnl_penalty_weight=0.01,
+                 theta_weight=0.0, slippage_bps=0.0, loss_type="abs", initial_cash=0.0, shares_to_hedge=10000,
+                 max_contracts_held_per_type=200, max_trade_per_step=15, profile_print_interval=0, record_metrics=True,
+                 *, num_envs, data=None, simulate: Optional[dict] = None, device="cuda", env_offset=0, total_envs=None,
+                 one_call_only=False):
+        _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CantorError("HedgingRollout runs on CUDA devices only (no CPU fallback)")
+        self.num_envs = int(num_envs)
+        self.env_offset = int(env_offset)
+        self.total_envs = int(total_envs) if total_envs is not None else self.env_offset + self.num_envs
+        self.one_call_only = bool(one_call_only)
+        self.loss_type = loss_type
+        self._params = _lib.EnvParams(
+            float(transaction_cost_per_contract), float(lambda_cost), float(pnl_penalty_weight), float(theta_weight),
+            float(slippage_bps), float(initial_cash), 0.04, 30 / 252, _lib.LOSS_MSE if loss_type == "mse" else _lib.LOSS_ABS,
+            int(shares_to_hedge), int(max_contracts_held_per_type), int(max_trade_per_step), 100, int(bool(record_metrics)))
+        self.data = None
+        self._sim = None
+        if simulate is not None:
+            if data is not None or data_file_path is not None:
+                raise ValueError("give either data or simulate, not both")
+            kw = dict(model="gbm", seed=42, s0=100.0, v0=0.04, r=0.04, dt=1 / 252, kappa=2.0, theta=0.04, sigma_v=0.5,
+                      rho=-0.7, tenor=30 / 252, n_steps=252)
+            unknown = set(simulate) - set(kw)
+            if unknown:
+                raise TypeError(f"unknown simulate keys: {sorted(unknown)}")
+            kw.update(simulate)
+            if kw["model"] not in ("gbm", "heston"):
+                raise ValueError("model must be 'gbm' or 'heston'")
+            self.episode_length = int(kw["n_steps"])
+            self._sim = _lib.SimParams(_lib.MODEL_GBM if kw["model"] == "gbm" else _lib.MODEL_HESTON, 1, kw["s0"], kw["v0"],
+                                       kw["r"], kw["dt"], kw["kappa"], kw["theta"], kw["sigma_v"], kw["rho"], kw["tenor"],
+                                       int(kw["seed"]) & (2 ** 64 - 1), 0)
+        else:
+            if isinstance(data, ReplayData):
+                self.data = data
+            elif isinstance(data, dict):
+                self.data = ReplayData.from_arrays(*(data[k] for k in ("paths", "volatilities", "call_prices_atm",
+                                                                        "put_prices_atm")), device=self.device)
+            elif data_file_path is not None:
+                self.data = ReplayData.from_npz(data_file_path, device=self.device)
+            else:
+                raise FileNotFoundError("Could not load or parse data from None. Error: no data_file_path / data / simulate given")
+            self.episode_length = self.data.episode_length
+            self._book = self.data.book()
+
+    def new_stats(self, hist_bins=4096, hist_max=4.0, keep_episodes=0) -> EpisodeStats:
+        return EpisodeStats(self.device, hist_bins, hist_max, keep_episodes, self.num_envs)
+
+    def run(self, n_steps: int, policy: Union[str, torch.Tensor] = "delta_every_step", *, mlp: Optional[torch.Tensor] = None,
+            actions: Optional[torch.Tensor] = None, seed: int = 0, stats: Optional[EpisodeStats] = None,
+            store: bool = False) -> RolloutResult:
+        """``n_steps`` env-steps of every env (auto-reset at episode ends), statistics accumulated into ``stats``.
+
+        policy   "no_hedge" | "random" | "delta_every_step" | "delta_benchmark" | "mlp" (with ``mlp=pack_mlp(...)``)
+                 | "actions" (open loop, ``actions`` float32 ``[n_steps, num_envs, 2]`` on the device)
+        store    also write the rollout (obs the policy saw, actions, reward, done), time-major
+        """
+        n, dev = self.num_envs, self.device
+        pol = _lib.Policy()
+        pol.put_leg_disabled = int(self.one_call_only)
+        pol.seed = int(seed) & (2 ** 64 - 1)
+        if policy == "mlp":
+            if mlp is None or mlp.dtype != torch.float32 or mlp.numel() != _lib.MLP_FLOATS or mlp.device != dev:
+                raise ValueError("policy='mlp' needs mlp=pack_mlp(...) on the rollout's device")
+            pol.kind, pol.mlp = _lib.POLICY_MLP, mlp.data_ptr()
+        elif policy == "actions":
+            if actions is None or actions.dtype != torch.float32 or tuple(actions.shape) != (n_steps, n, 2) \
+                    or not actions.is_contiguous() or actions.device != dev:
+                raise ValueError("policy='actions' needs a contiguous float32 [n_steps, num_envs, 2] device tensor")
+            pol.kind, pol.actions = _lib.POLICY_ACTIONS, actions.data_ptr()
+        elif policy in POLICIES:
+            pol.kind = POLICIES[policy]
+        else:
+            raise ValueError(f"unknown policy {policy!r}")
+        stats = stats if stats is not None else self.new_stats()
+        st = stats.c_struct()
+        res = RolloutResult(stats, int(n_steps))
+        out = None
+        if store:
+            res.obs = torch.empty((n_steps, n, _lib.OBS_DIM), dtype=torch.float32, device=dev)
+            res.actions = torch.empty((n_steps, n, 2), dtype=torch.float32, device=dev)
+            res.reward = torch.empty((n_steps, n), dtype=torch.float32, device=dev)
+            done = torch.empty((n_steps, n), dtype=torch.uint8, device=dev)
+            res.done = done.view(torch.bool)
+            out = _lib.RolloutOut(res.obs.data_ptr(), res.actions.data_ptr(), res.reward.data_ptr(), done.data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().cantor_rollout(
+                C.byref(self._params), C.byref(self._book) if self._sim is None else None,
+                C.byref(self._sim) if self._sim is not None else None, self.episode_length, C.byref(pol), n,
+                self.env_offset, self.total_envs, int(n_steps), C.byref(st), C.byref(out) if out is not None else None,
+                _lib.current_stream_ptr(dev)), "cantor_rollout")
+        return res

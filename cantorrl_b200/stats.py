@@ -1,0 +1,143 @@
+"""Episode statistics of the evaluation loops, as a small vector that shards combine by addition.
+
+The reference computes, over finished episodes (one list entry per episode, Python lists on the host):
+
+  ``evaluate_baseline_policy``  src/agents/baselines.py:49-65      a = mean_t |per_share_step_pnl|, c = mean_t cost;
+                                                                    mean / std over episodes
+  ``run_evaluation``            src/agents/train_ppo_v2.py:482-530 b = |sum_t per_share_step_pnl| / T, c = sum_t cost / T,
+                                                                    R = sum_t reward; mean, std, CVaR95 = mean of the
+                                                                    top 5 % of sorted b (index int(0.95 n) onward)
+
+Here the kernels reduce ``n, sum x, sum x^2`` of each quantity (``include/cantor_hedge.h``: ``cantor_stats_out``)
+plus a fixed-bin histogram of ``b`` (counts and per-bin sums), so the statistics of an env population sharded
+over GPUs by path index are ONE all-reduce(sum) of ``16 + 2 * bins`` numbers -- the only collective on the path.
+``EpisodeStats`` holds those buffers (caller-owned torch tensors), all-reduces them over ``torch.distributed``
+(NCCL on GPUs; any backend works, the tests use gloo) and turns them into the reference's statistics.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+# sums[] layout (cantor_hedge.h)
+N_EPISODES, A_SUM, A_SQ, B_SUM, B_SQ, C_SUM, C_SQ, R_SUM, R_SQ, S_SUM, S_SQ, ENV_STEPS = range(12)
+
+
+def _mean_std(n, s, sq):
+    if n <= 0:
+        return float("nan"), float("nan")
+    mean = s / n
+    return mean, math.sqrt(max(sq / n - mean * mean, 0.0))          # np.std: population standard deviation
+
+
+class EpisodeStats:
+    """Accumulators for the per-episode hedging-error statistics (device tensors, zeroed on construction).
+
+    hist_bins / hist_max  fixed-bin histogram of ``b`` over ``[0, hist_max)`` for CVaR95 (values beyond the range
+                          land in the last bin; their exact sum is kept, so the tail mean stays exact)
+    episode_slots         optionally keep every episode's ``b`` (``[episode_slots, n_envs]`` floats) for an exact,
+                          sort-based CVaR on one GPU
+    """
+
+    def __init__(self, device="cuda", hist_bins: int = 4096, hist_max: float = 4.0, episode_slots: int = 0,
+                 n_envs: int = 0):
+        dev = torch.device(device)
+        self.device = dev
+        self.sums = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=dev)
+        self.hist_bins, self.hist_max = int(hist_bins), float(hist_max)
+        self.hist = torch.zeros(self.hist_bins, dtype=torch.int64, device=dev) if hist_bins > 0 else None   # u64 counts
+        self.hist_sum = torch.zeros(self.hist_bins, dtype=torch.float64, device=dev) if hist_bins > 0 else None
+        self.episode_slots = int(episode_slots)
+        self.episode_b = (torch.full((self.episode_slots, int(n_envs)), float("nan"), dtype=torch.float32, device=dev)
+                          if episode_slots > 0 else None)
+
+    def zero_(self):
+        self.sums.zero_()
+        if self.hist is not None:
+            self.hist.zero_()
+            self.hist_sum.zero_()
+        if self.episode_b is not None:
+            self.episode_b.fill_(float("nan"))
+        return self
+
+    def c_struct(self) -> _lib.StatsOut:
+        return _lib.StatsOut(self.sums.data_ptr(), _lib.ptr(self.hist), _lib.ptr(self.hist_sum), _lib.ptr(self.episode_b),
+                             self.hist_max, self.hist_bins, 0, self.episode_slots)
+
+    # ------------------------------------------------------------------------------------------ collective
+    def all_reduce(self, group=None, async_op: bool = False):
+        """Sum the accumulators over the ranks of ``group`` (no-op without an initialised process group).
+
+        One flat float64 buffer would need a dtype change of the counts; two small all-reduces keep the counts
+        exact (int64) and the sums in float64.  Both are latency-bound (<= 64 KB) on NVLink / NVSwitch.
+        """
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return []
+        works = [dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=group, async_op=async_op)]
+        if self.hist is not None:
+            works.append(dist.all_reduce(self.hist, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
+            works.append(dist.all_reduce(self.hist_sum, op=dist.ReduceOp.SUM, group=group, async_op=async_op))
+        return works
+
+    # --------------------------------------------------------------------------------------------- results
+    def cvar95(self, level: float = 0.95) -> Optional[float]:
+        """Mean of the top ``n - int(level * n)`` values of ``b`` (train_ppo_v2.py:527-530) from the histogram.
+
+        Whole bins above the cut contribute their exact sums; the bin that straddles the cut contributes its
+        mean value for the remaining count (error <= one bin width times that bin's share of the tail).
+        """
+        if self.hist is None:
+            return None
+        cnt = self.hist.cpu().numpy()
+        sm = self.hist_sum.cpu().numpy()
+        n = int(cnt.sum())
+        if n == 0:
+            return float("nan")
+        k = n - int(level * n)                      # len(sorted[int(0.95 n):])
+        if k <= 0:
+            return float("nan")
+        need, total = k, 0.0
+        for j in range(self.hist_bins - 1, -1, -1):
+            c = int(cnt[j])
+            if c == 0:
+                continue
+            if c <= need:
+                total += float(sm[j])
+                need -= c
+            else:
+                total += float(sm[j]) / c * need
+                need = 0
+            if need == 0:
+                break
+        return total / k
+
+    def cvar95_exact(self, level: float = 0.95) -> Optional[float]:
+        """Sort-based CVaR over the kept per-episode values (single GPU; NaN slots = episodes not finished)."""
+        if self.episode_b is None:
+            return None
+        b = self.episode_b.flatten()
+        b = b[~torch.isnan(b)]
+        if b.numel() == 0:
+            return float("nan")
+        sb = torch.sort(b.double()).values
+        return float(sb[int(level * sb.numel()):].mean())
+
+    def result(self) -> dict:
+        """The reference's statistics (names follow train_ppo_v2.py:520-530 / baselines.py:63-65)."""
+        s = self.sums.cpu().numpy()
+        n = float(s[N_EPISODES])
+        out = {"n_episodes": int(n), "env_steps": int(s[ENV_STEPS])}
+        out["mean_abs_pnl_baseline"], out["std_abs_pnl_baseline"] = _mean_std(n, s[A_SUM], s[A_SQ])
+        out["mean_abs_pnl"], out["std_abs_pnl"] = _mean_std(n, s[B_SUM], s[B_SQ])
+        out["mean_cost"], out["std_cost"] = _mean_std(n, s[C_SUM], s[C_SQ])
+        out["mean_reward"], out["std_reward"] = _mean_std(n, s[R_SUM], s[R_SQ])
+        out["mean_signed_pnl"], out["std_signed_pnl"] = _mean_std(n, s[S_SUM], s[S_SQ])
+        out["cvar95_abs_pnl"] = self.cvar95()
+        if self.episode_b is not None:
+            out["cvar95_abs_pnl_exact"] = self.cvar95_exact()
+        return out

@@ -212,6 +212,64 @@ int cantor_env_step_many(const cantor_env_params* params, const cantor_replay_bo
                          const float* actions, float* obs, void* reward, uint8_t* done, float* terminal_obs,
                          const cantor_reset_rule* reset_rule, void* stream);
 
+/* ---- episode-fused rollout + statistics ------------------------------------------------------------------
+ * Replaces the evaluation loops around the env: evaluate_baseline_policy (src/agents/baselines.py:32-72),
+ * run_benchmark_strategy (src/benchmark/delta_and_nothing.py:34-114) and the statistics of run_evaluation
+ * (src/agents/train_ppo_v2.py:482-530).  One kernel runs n_steps consecutive env-steps per env with the state in
+ * registers: path step (replayed from `book` or simulated on the fly from `sim`, same Philox counters as
+ * cantor_sim_paths) -> ATM repricing -> observation -> policy -> fused hedge step -> auto-reset, and reduces
+ * per-episode statistics on the fly.  Episode e of global env g uses global path e * total_envs + g
+ * (mod n_paths when replaying), so results do not depend on how envs are sharded over GPUs. */
+enum {
+    CANTOR_POLICY_NO_HEDGE = 0,          /* baselines.py:74-75 */
+    CANTOR_POLICY_RANDOM = 1,            /* action_space.sample(): uniform(-1, 1), Philox stream "ACTN" */
+    CANTOR_POLICY_DELTA_BASELINES = 2,   /* policy_delta_every_step, baselines.py:77-103 */
+    CANTOR_POLICY_DELTA_BENCHMARK = 3,   /* delta_hedging_action_selector, delta_and_nothing.py:122-163 */
+    CANTOR_POLICY_MLP = 4,               /* ReLU MLP 13-64-64-2 on the normalised obs, output clipped to [-1, 1] */
+    CANTOR_POLICY_ACTIONS = 5            /* open-loop: actions[step, env, 2] */
+};
+#define CANTOR_MLP_FLOATS 5212           /* W1[13][64] b1[64] W2[64][64] b2[64] W3[64][2] b3[2] obs_mean[13] obs_inv_std[13] */
+typedef struct cantor_policy {
+    int32_t kind;                        /* CANTOR_POLICY_* */
+    int32_t put_leg_disabled;            /* 1: action[1] forced to 0 (one European call) */
+    const float* mlp;                    /* [CANTOR_MLP_FLOATS] for CANTOR_POLICY_MLP */
+    const float* actions;                /* [n_steps, n_envs, 2] for CANTOR_POLICY_ACTIONS */
+    uint64_t seed;                       /* CANTOR_POLICY_RANDOM */
+} cantor_policy;
+
+/* sums[] layout; every entry is a plain sum over finished episodes, so shards combine by addition (all-reduce):
+ *  0 n_episodes
+ *  1,2  sum, sum of squares of a = mean_t |per_share_step_pnl|        (baselines.py:49-54)
+ *  3,4  ... of b = |sum_t per_share_step_pnl| / T                       (train_ppo_v2.py:482,520)
+ *  5,6  ... of c = sum_t transaction_costs_total / T                    (train_ppo_v2.py:483,521; baselines.py:50,55)
+ *  7,8  ... of R = sum_t reward                                         (train_ppo_v2.py:484)
+ *  9,10 ... of s = sum_t per_share_step_pnl (signed)
+ *  11   env-steps executed */
+#define CANTOR_STATS_LEN 16
+typedef struct cantor_stats_out {
+    double* sums;                        /* [CANTOR_STATS_LEN], accumulated into (zero it first) */
+    uint64_t* hist;                      /* [hist_bins] histogram of b over [0, hist_max) for CVaR95 (:527-530), or NULL */
+    double* hist_sum;                    /* [hist_bins] sum of b per bin (tail means exact up to the boundary bin), or NULL */
+    float* episode_b;                    /* [episode_slots, n_envs] per-episode b for an exact CVaR, or NULL */
+    double hist_max;
+    int32_t hist_bins;
+    int32_t reserved;
+    int64_t episode_slots;
+} cantor_stats_out;
+
+typedef struct cantor_rollout_out {      /* optional rollout storage, time-major */
+    float* obs;                          /* [n_steps, n_envs, 13] observation the policy acted on */
+    float* actions;                      /* [n_steps, n_envs, 2] */
+    float* reward;                       /* [n_steps, n_envs] */
+    uint8_t* done;                       /* [n_steps, n_envs] */
+} cantor_rollout_out;
+
+/* Exactly one of book / sim is non-NULL (episode_length is taken from the book when replaying). */
+int cantor_rollout(const cantor_env_params* params, const cantor_replay_book* book, const cantor_sim_params* sim,
+                   int32_t episode_length, const cantor_policy* policy, int64_t n_envs, int64_t env_offset,
+                   int64_t total_envs, int32_t n_steps, const cantor_stats_out* stats,
+                   const cantor_rollout_out* out, void* stream);
+
 /* ---- host-buffer face (what a NumPy / SubprocVecEnv-style caller binds) ---------------------------------
  * These are the only functions that take HOST pointers, allocate, and synchronise.  The handle owns the device
  * copies; a step copies the actions in, runs the fused hedge-step kernel and copies obs / reward / done back,

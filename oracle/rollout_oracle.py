@@ -1,0 +1,131 @@
+"""CPU ORACLE for the episode-fused rollout  --  TEST INFRASTRUCTURE ONLY (never imported by the product package).
+
+Restates, in NumPy, the loop the reference runs around its env
+
+  * ``evaluate_baseline_policy``  src/agents/baselines.py:32-72      (reset; while not done: policy -> env.step)
+  * ``run_evaluation``            src/agents/train_ppo_v2.py:465-530 (per-episode sums, statistics)
+
+on top of ``hedge_oracle.OracleVecEnv`` (the env step) and ``policy_oracle`` (the hand-written policies), plus the
+two policy sources the CUDA rollout adds: counter-based uniform actions (the stand-in for
+``action_space.sample()``, src/agents/test_inf.py:29) and the ReLU MLP actor 13-64-64-2 on the normalised
+observation (quantconnect/model_wrapper.py:131,177-185; output clipped like SB3 clips a Box action).
+
+Episode ``e`` of global env ``g`` runs on path ``(e * total_envs + g) % n_paths`` -- the rule of
+``cantorrl_b200/csrc/rollout.cu`` -- so a population sharded over ranks visits the same paths.
+
+Parity status: the env step and the two delta policies are PINNED (see hedge_oracle.py / policy_oracle.py); the
+uniform-action stream is pinned by the Random123 known-answer vectors of ``sim_oracle.philox4x32_10``; the MLP
+has no reference golden vector (the reference's actor runs inside SB3/torch) -- "parity unpinned" for it, it is
+checked against this plain float32 restatement only.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import policy_oracle
+from .hedge_oracle import EnvParams, OracleVecEnv
+from .sim_oracle import philox4x32_10
+
+F32 = np.float32
+STREAM_ACTIONS = 0x4143544E      # "ACTN"
+
+
+def uniform_actions(seed, global_env, step):
+    """uniform[-1, 1) float32 pairs of Philox(seed; global env, rollout step, "ACTN") (rollout.cu: policy_random)."""
+    g = np.asarray(global_env, np.uint64).ravel()
+    ctr = np.zeros((g.size, 4), np.uint32)
+    ctr[:, 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    ctr[:, 1] = (g >> np.uint64(32)).astype(np.uint32)
+    ctr[:, 2] = np.uint32(step)
+    ctr[:, 3] = STREAM_ACTIONS
+    x = philox4x32_10(ctr, np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], np.uint32))
+    u = (x[:, :2] >> np.uint32(8)).astype(F32)                    # 24 bits: exact in float32
+    return (u * F32(2.0 ** -23) + F32(-1.0)).astype(F32)            # fmaf is exact here (24-bit integer * 2^-23 - 1)
+
+
+def mlp_actor(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8):
+    """float32 actor: clip((obs - mean) / sqrt(var + eps), +-10) -> ReLU(64) -> ReLU(64) -> 2, clipped to [-1, 1].
+
+    Weights in ``torch.nn.Linear`` layout (``[out, in]``).  Accumulation in float64 then rounded: the CUDA kernel's
+    float32 FMA chain agrees to ~1e-6 relative.
+    """
+    x = np.asarray(obs, F32)
+    if mean is not None:
+        inv = (1.0 / np.sqrt(np.asarray(var, np.float64) + epsilon)).astype(F32)
+        x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-10), F32(10))
+    h = np.maximum(x.astype(np.float64) @ np.asarray(W1, np.float64).T + b1, 0)
+    h = np.maximum(h @ np.asarray(W2, np.float64).T + b2, 0)
+    out = h @ np.asarray(W3, np.float64).T + b3
+    return np.clip(out, -1, 1).astype(F32)
+
+
+def run_rollout(paths, vols, calls, puts, params: EnvParams, policy, n_envs, n_steps, env_offset=0, total_envs=None,
+                forced_actions=None, one_call_only=False, seed=0, mlp=None):
+    """Free-running (or, with ``forced_actions`` [n_steps, n_envs, 2], teacher-forced) rollout of the oracle env.
+
+    Returns a dict: ``obs`` (what the policy saw) [n_steps, n_envs, 13], ``actions``, ``policy_actions`` (what the
+    oracle policy would have played on that observation), ``reward`` / ``pps`` / ``cost`` [n_steps, n_envs],
+    ``done``, and the finished episodes' per-step series ``ep_pps`` / ``ep_cost`` / ``ep_reward`` [(episodes), T].
+    """
+    total = n_envs + env_offset if total_envs is None else total_envs
+    env = OracleVecEnv(paths, vols, calls, puts, params, n_envs)
+    T, n_paths = env.episode_length, env.num_episodes
+    genv = env_offset + np.arange(n_envs, dtype=np.int64)
+    episode = np.zeros(n_envs, np.int64)
+    obs = env.reset((episode * total + genv) % n_paths)
+    rec = {k: [] for k in ("obs", "actions", "policy_actions", "reward", "pps", "cost", "done")}
+    cur = {k: np.zeros((n_envs, T)) for k in ("pps", "cost", "reward")}
+    fin = {k: [] for k in ("pps", "cost", "reward")}
+    for g in range(n_steps):
+        if policy == "no_hedge":
+            a = policy_oracle.no_hedge(obs)
+        elif policy == "random":
+            a = uniform_actions(seed, genv, g)
+        elif policy == "delta_every_step":
+            a = policy_oracle.delta_every_step(obs, params.max_contracts_held_per_type, 100, params.shares_to_hedge,
+                                               params.max_trade_per_step)
+        elif policy == "delta_benchmark":
+            a = policy_oracle.delta_benchmark(obs, env.pos_c, env.pos_p, 100, params.shares_to_hedge, params.max_trade_per_step)
+        elif policy == "mlp":
+            a = mlp_actor(obs, *mlp)
+        elif policy == "actions":
+            a = np.asarray(forced_actions[g], F32)
+        else:
+            raise ValueError(policy)
+        a = np.array(a, F32)
+        if one_call_only:
+            a[:, 1] = 0
+        played = a if forced_actions is None else np.asarray(forced_actions[g], F32)
+        t = env.step_count.copy()
+        episode_next = episode + 1
+        nobs, r, d, _, info = env.step_autoreset(played, (episode_next * total + genv) % n_paths)
+        rows = np.arange(n_envs)
+        cur["pps"][rows, t] = info["per_share_step_pnl"]
+        cur["cost"][rows, t] = info["transaction_costs_total"]
+        cur["reward"][rows, t] = r
+        for k, v in (("obs", obs), ("actions", played), ("policy_actions", a), ("reward", r),
+                     ("pps", info["per_share_step_pnl"]), ("cost", info["transaction_costs_total"]), ("done", d)):
+            rec[k].append(np.array(v))
+        if d.any():
+            for k in fin:
+                fin[k].append(cur[k][d].copy())
+            episode = np.where(d, episode_next, episode)
+        obs = nobs
+    out = {k: np.stack(v) for k, v in rec.items()}
+    for k in fin:
+        out["ep_" + k] = np.concatenate(fin[k]) if fin[k] else np.zeros((0, T))
+    out["episode_length"] = T
+    return out
+
+
+def stats_vector(ep_pps, ep_cost, ep_reward, T):
+    """The ``sums[0:11]`` vector of include/cantor_hedge.h from finished episodes' per-step series."""
+    a = np.abs(ep_pps).sum(1) / T
+    b = np.abs(ep_pps.sum(1)) / T
+    c = ep_cost.sum(1) / T
+    R = ep_reward.sum(1)
+    s = ep_pps.sum(1)
+    v = [float(len(a))]
+    for x in (a, b, c, R, s):
+        v += [x.sum(), (x * x).sum()]
+    return np.array(v), b

@@ -1,0 +1,78 @@
+"""Pins oracle/policy_oracle.py against the unmodified reference policy functions (build container only)."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE, ROOT
+from oracle import policy_oracle
+
+needs_reference = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+
+
+def _load(name, path):
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_gym_stub"))
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _random_obs(rng, n):
+    obs = rng.uniform(-1, 1, (n, 13)).astype(np.float32)
+    obs[:, 7] = rng.uniform(0, 1, n)                 # call delta
+    obs[:, 9] = obs[:, 7] - 1                        # put delta
+    obs[::7, 7] = 0.0                                # falls through to the put branch
+    obs[::11, 9] = 0.0
+    obs[:, 3] = rng.integers(-200, 201, n) / 200.0
+    obs[:, 4] = rng.integers(-200, 201, n) / 200.0
+    return obs
+
+
+@needs_reference
+def test_delta_every_step_matches_reference():
+    mod = _load("ref_baselines", f"{REFERENCE}/src/agents/baselines.py")
+    env = types.SimpleNamespace(max_contracts_held=200, option_contract_multiplier=100, shares_held_fixed=10000,
+                                max_trade_per_step=15, action_space=types.SimpleNamespace(dtype=np.float32))
+    rng = np.random.default_rng(0)
+    obs = _random_obs(rng, 2000)
+    got = policy_oracle.delta_every_step(obs)
+    want = np.stack([mod.policy_delta_every_step(o, env) for o in obs])
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(policy_oracle.no_hedge(obs[:3]), np.stack([mod.policy_no_hedge(o, env) for o in obs[:3]]))
+
+
+@needs_reference
+def test_delta_benchmark_matches_reference():
+    mod = _load("ref_delta_and_nothing", f"{REFERENCE}/src/benchmark/delta_and_nothing.py")
+    rng = np.random.default_rng(1)
+    obs = _random_obs(rng, 2000)
+    pos_c = rng.integers(-200, 201, 2000)
+    pos_p = rng.integers(-200, 201, 2000)
+    pos_c[:100] = 0
+    pos_p[:100] = 0
+    got = policy_oracle.delta_benchmark(obs, pos_c, pos_p)
+    want = np.stack([mod.delta_hedging_action_selector(dict(
+        S_t=100.0, v_t=0.04, call_delta_atm=o[7], put_delta_atm=o[9], current_call_contracts=np.int64(c),
+        current_put_contracts=np.int64(p), shares_to_hedge=10000, option_contract_multiplier=100, max_trade_per_step=15))
+        for o, c, p in zip(obs, pos_c, pos_p)])
+    np.testing.assert_array_equal(got, want)
+
+
+def test_episode_statistics_definitions():
+    rng = np.random.default_rng(2)
+    pps = rng.normal(0, 1, (200, 30))
+    cost = np.abs(rng.normal(5, 1, (200, 30)))
+    rew = -np.abs(pps) * 1e-3 - cost * 1e-4
+    s = policy_oracle.episode_statistics(pps, cost, rew, 30)
+    # train_ppo_v2.py:520-530 written out literally
+    ep = [np.abs(x) / 30 for x in pps.sum(1)]
+    srt = sorted(ep)
+    assert np.isclose(s["mean_abs_pnl"], np.mean(ep)) and np.isclose(s["std_abs_pnl"], np.std(ep))
+    assert np.isclose(s["cvar95_abs_pnl"], np.mean(srt[int(0.95 * len(srt)):]))
+    # baselines.py:49-65
+    assert np.isclose(s["mean_abs_pnl_baseline"], np.mean([np.abs(r).sum() / 30 for r in pps]))
+    assert np.isclose(s["mean_cost"], np.mean([r.sum() / 30 for r in cost]))

@@ -1,0 +1,146 @@
+"""GPU parity tests of the episode-fused rollout kernel (policy + env step + statistics) against the oracle.
+
+Parity is checked TEACHER-FORCED: the kernel's stored actions drive the oracle env, so a policy output that differs
+in the last float32 bit cannot fork the two trajectories; the policy itself is compared on the kernel's own
+observations.  fp32 tolerance of the north star: 1e-4 relative; done flags and episode counts exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rollout_oracle, sim_oracle, bs_oracle
+from oracle.hedge_oracle import EnvParams
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3, lambda_cost=1e-4)
+
+
+def _book(n_paths, T, seed=5, heston=False):
+    idx = np.arange(n_paths)
+    S, V = (sim_oracle.heston_paths if heston else sim_oracle.gbm_paths)(seed, idx, T)
+    C, P = bs_oracle.atm_book(S.astype(np.float64), V.astype(np.float64))
+    return S, V, C.astype(np.float32), P.astype(np.float32)
+
+
+def _mlp_weights(seed=0):
+    g = np.random.default_rng(seed)
+    W1, b1 = g.normal(0, 0.5, (64, 13)).astype(np.float32), g.normal(0, 0.1, 64).astype(np.float32)
+    W2, b2 = g.normal(0, 0.2, (64, 64)).astype(np.float32), g.normal(0, 0.1, 64).astype(np.float32)
+    W3, b3 = g.normal(0, 0.3, (2, 64)).astype(np.float32), g.normal(0, 0.1, 2).astype(np.float32)
+    mean = g.normal(0, 0.2, 13).astype(np.float32)
+    var = g.uniform(0.05, 2.0, 13).astype(np.float32)
+    return W1, b1, W2, b2, W3, b3, mean, var
+
+
+@pytest.mark.parametrize("policy", ["no_hedge", "random", "delta_every_step", "delta_benchmark", "mlp", "actions"])
+@pytest.mark.parametrize("loss", ["abs", "mse"])
+def test_rollout_matches_oracle_teacher_forced(policy, loss):
+    from cantorrl_b200.rollout import HedgingRollout, pack_mlp
+    n_paths, T, n_envs, n_steps, off, total = 61, 12, 203, 41, 1000, 5000
+    S, V, C, P = _book(n_paths, T, heston=True)
+    kw = dict(KW, loss_type=loss)
+    ro = HedgingRollout(data=dict(paths=S, volatilities=V, call_prices_atm=C, put_prices_atm=P), num_envs=n_envs,
+                        env_offset=off, total_envs=total, **kw)
+    w = _mlp_weights()
+    forced = None
+    if policy == "actions":
+        forced = np.random.default_rng(9).uniform(-1.3, 1.3, (n_steps, n_envs, 2)).astype(np.float32)
+    stats = ro.new_stats(hist_bins=512, hist_max=2.0, keep_episodes=4)
+    res = ro.run(n_steps, policy, mlp=pack_mlp(*w) if policy == "mlp" else None, seed=77, stats=stats, store=True,
+                 actions=torch.from_numpy(forced).cuda() if forced is not None else None)
+    torch.cuda.synchronize()
+    got = {k: getattr(res, k).cpu().numpy() for k in ("obs", "actions", "reward", "done")}
+    ref = rollout_oracle.run_rollout(S, V, C, P, EnvParams(**kw), policy, n_envs, n_steps, off, total,
+                                     forced_actions=got["actions"], seed=77, mlp=w)
+    assert np.array_equal(got["done"], ref["done"])
+    np.testing.assert_allclose(got["obs"], ref["obs"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(got["reward"], ref["reward"], rtol=1e-4, atol=1e-7)
+    # the policy, on the observations the kernel itself produced
+    if policy in ("random", "actions", "no_hedge"):
+        assert np.array_equal(got["actions"], ref["policy_actions"])           # same Philox words / same inputs: bit-exact
+    else:
+        np.testing.assert_allclose(got["actions"], ref["policy_actions"], rtol=1e-4, atol=2e-5)
+    # statistics of the finished episodes
+    want, b = rollout_oracle.stats_vector(ref["ep_pps"], ref["ep_cost"], ref["ep_reward"], T)
+    sums = stats.sums.cpu().numpy()
+    assert sums[0] == want[0] == n_envs * (n_steps // T)
+    scale = np.abs(ref["ep_pps"]).sum(1).mean() / T
+    np.testing.assert_allclose(sums[1:11], want[1:], rtol=2e-4, atol=2e-4 * max(scale, 1e-6) * want[0])
+    assert sums[11] == n_envs * n_steps
+    r = stats.result()
+    sb = np.sort(b)
+    np.testing.assert_allclose(r["cvar95_abs_pnl_exact"], sb[int(0.95 * len(sb)):].mean(), rtol=2e-4, atol=1e-6)
+    assert int(stats.hist.sum()) == int(want[0])
+    np.testing.assert_allclose(r["cvar95_abs_pnl"], r["cvar95_abs_pnl_exact"], rtol=0, atol=2.0 / 512)
+
+
+@pytest.mark.parametrize("model", ["gbm", "heston"])
+def test_on_the_fly_rollout_equals_replay_of_simulated_book(model):
+    """Same Philox counters, same device functions: simulating inside the rollout == replaying K1's book, bit for bit."""
+    from cantorrl_b200 import sim
+    from cantorrl_b200.rollout import HedgingRollout
+    n_envs, T, episodes = 1000, 21, 3
+    n_steps = T * episodes - 5
+    book = sim.generate_paths_and_options(n_envs * episodes, seed=11, n_steps=T, model=model)
+    a = HedgingRollout(data=book, num_envs=n_envs, **KW)
+    b = HedgingRollout(simulate=dict(model=model, seed=11, n_steps=T), num_envs=n_envs, **KW)
+    for policy in ("random", "delta_every_step"):
+        ra, rb = a.run(n_steps, policy, seed=3, store=True), b.run(n_steps, policy, seed=3, store=True)
+        for k in ("obs", "actions", "reward", "done"):
+            assert torch.equal(getattr(ra, k), getattr(rb, k)), (policy, k)
+        np.testing.assert_allclose(ra.stats.sums.cpu().numpy(), rb.stats.sums.cpu().numpy(), rtol=1e-12)
+        assert torch.equal(ra.stats.hist, rb.stats.hist)
+
+
+def test_statistics_do_not_depend_on_sharding():
+    """2 shards of the global env index == 1 shard: histogram counts exact, float64 sums to summation-order noise."""
+    from cantorrl_b200.rollout import HedgingRollout
+    total, T = 6000, 10
+    sim_kw = dict(model="heston", seed=4, n_steps=T)
+    whole = HedgingRollout(simulate=sim_kw, num_envs=total, **KW).run(35, "delta_benchmark")
+    parts = [HedgingRollout(simulate=sim_kw, num_envs=cnt, env_offset=off, total_envs=total, **KW).run(35, "delta_benchmark")
+             for off, cnt in ((0, 2500), (2500, 3500))]
+    sums = sum(p.stats.sums for p in parts)
+    hist = sum(p.stats.hist for p in parts)
+    assert torch.equal(hist, whole.stats.hist) and int(hist.sum()) == total * 3
+    np.testing.assert_allclose(sums.cpu().numpy(), whole.stats.sums.cpu().numpy(), rtol=1e-11)
+    np.testing.assert_allclose(sum(p.stats.hist_sum for p in parts).cpu().numpy(), whole.stats.hist_sum.cpu().numpy(), rtol=1e-11)
+
+
+def test_full_size_rollout_invariants():
+    """BASELINE configs[1] shape (2^20 envs x 252 steps, GBM on the fly): size-independent properties."""
+    from cantorrl_b200.rollout import HedgingRollout
+    n, T = 1 << 20, 252
+    ro = HedgingRollout(simulate=dict(model="gbm", seed=42, n_steps=T), num_envs=n, one_call_only=True, **KW)
+    r0 = ro.run(T, "no_hedge").stats.result()
+    assert r0["n_episodes"] == n and r0["env_steps"] == n * T
+    assert r0["mean_cost"] == 0.0 and r0["std_cost"] == 0.0                      # no trades, no costs
+    # unhedged P&L per share = S_T - S_0: mean of |S_T - S_0| / T for GBM(mu = .04, sigma = .2), S0 = 100
+    assert abs(r0["mean_signed_pnl"] - 100 * (np.exp(0.04) - 1)) < 0.1
+    # theta penalty alone is deterministic: sum_t 2e-4 (T - t) / 252, t = 1..T
+    theta = 2e-4 * sum(T - t for t in range(1, T + 1)) / 252
+    assert r0["mean_reward"] < -theta
+    r1 = ro.run(T, "random", seed=1).stats.result()
+    assert r1["n_episodes"] == n and r1["mean_cost"] > 0
+    # idempotence: the same launch twice gives the same statistics (counter-based randomness, no hidden state)
+    r2 = ro.run(T, "random", seed=1).stats.result()
+    assert r1["n_episodes"] == r2["n_episodes"] and abs(r1["mean_abs_pnl"] - r2["mean_abs_pnl"]) < 1e-12
+    assert r1["cvar95_abs_pnl"] >= r1["mean_abs_pnl"]
+
+
+def test_rollout_argument_errors():
+    from cantorrl_b200 import CantorError
+    from cantorrl_b200.rollout import HedgingRollout
+    ro = HedgingRollout(simulate=dict(n_steps=8), num_envs=16)
+    with pytest.raises(ValueError):
+        ro.run(4, "mlp")
+    with pytest.raises(ValueError):
+        ro.run(4, "nonsense")
+    with pytest.raises(ValueError):
+        ro.run(4, "actions", actions=torch.zeros((3, 16, 2), device="cuda"))
+    with pytest.raises(TypeError):
+        HedgingRollout(simulate=dict(nsteps=8), num_envs=16)
+    with pytest.raises(FileNotFoundError):
+        HedgingRollout(num_envs=4)
+    assert issubclass(CantorError, RuntimeError)
