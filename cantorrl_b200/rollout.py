@@ -81,6 +81,8 @@ class HedgingRollout:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.CantorError("HedgingRollout runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
         self.env_offset = int(env_offset)
         self.total_envs = int(total_envs) if total_envs is not None else self.env_offset + self.num_envs

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import rollout_oracle, sim_oracle, bs_oracle
+from oracle import bs_oracle, policy_oracle, rollout_oracle, sim_oracle
 from oracle.hedge_oracle import EnvParams
 
 pytestmark = pytest.mark.gpu
@@ -56,11 +56,19 @@ def test_rollout_matches_oracle_teacher_forced(policy, loss):
     assert np.array_equal(got["done"], ref["done"])
     np.testing.assert_allclose(got["obs"], ref["obs"], rtol=1e-4, atol=2e-6)
     np.testing.assert_allclose(got["reward"], ref["reward"], rtol=1e-4, atol=1e-7)
-    # the policy, on the observations the kernel itself produced
+    # the policy, evaluated by the oracle on the observations the kernel itself produced (same float32 inputs)
+    flat = got["obs"].reshape(-1, 13)
     if policy in ("random", "actions", "no_hedge"):
         assert np.array_equal(got["actions"], ref["policy_actions"])           # same Philox words / same inputs: bit-exact
     else:
-        np.testing.assert_allclose(got["actions"], ref["policy_actions"], rtol=1e-4, atol=2e-5)
+        if policy == "delta_every_step":
+            want_a = policy_oracle.delta_every_step(flat)
+        elif policy == "delta_benchmark":
+            pos = np.rint(flat[:, 3:5].astype(np.float64) * 200).astype(np.int64)
+            want_a = policy_oracle.delta_benchmark(flat, pos[:, 0], pos[:, 1])
+        else:
+            want_a = rollout_oracle.mlp_actor(flat, *w)
+        np.testing.assert_allclose(got["actions"].reshape(-1, 2), want_a, rtol=1e-4, atol=1e-4)
     # statistics of the finished episodes
     want, b = rollout_oracle.stats_vector(ref["ep_pps"], ref["ep_cost"], ref["ep_reward"], T)
     sums = stats.sums.cpu().numpy()
