@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Launched with torchrun (one rank per GPU): statistics of a population sharded by global env index and all-reduced
+over NCCL must equal the statistics of the whole population computed on one GPU (rank 0 checks and prints OK)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cantorrl_b200.distributed import init_process_group, rank_world, shard  # noqa: E402
+from cantorrl_b200.rollout import HedgingRollout  # noqa: E402
+
+KW = dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3, lambda_cost=1e-4)
+
+
+def main():
+    rank, local_rank, world = rank_world()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    init_process_group("nccl", dev)
+    total, T, steps = 300_001, 21, 50
+    sim = dict(model="heston", seed=9, n_steps=T)
+    off, cnt = shard(total, rank, world)
+    part = HedgingRollout(simulate=sim, num_envs=cnt, env_offset=off, total_envs=total, device=dev, **KW)
+    st = part.run(steps, "delta_benchmark").stats
+    st.all_reduce()
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        whole = HedgingRollout(simulate=sim, num_envs=total, device=dev, **KW).run(steps, "delta_benchmark").stats
+        ok = torch.equal(whole.hist, st.hist)
+        ok &= bool(np.allclose(whole.sums.cpu().numpy(), st.sums.cpu().numpy(), rtol=1e-10, atol=0))
+        ok &= int(st.sums[0]) == total * (steps // T) and int(st.sums[11]) == total * steps
+        r = st.result()
+        print(f"world={world} n_episodes={r['n_episodes']} mean_abs_pnl={r['mean_abs_pnl']:.6f} cvar95={r['cvar95_abs_pnl']:.6f}")
+        print("MULTIGPU_OK" if ok else "MULTIGPU_MISMATCH", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
