@@ -115,9 +115,11 @@ def run_reference(args, rank, world):
     ctx = mp.get_context("fork")
     S, V, Cc, Pp = _cpu_book(256, T, 42)
 
+    EP = 8                                                # episodes per process per bench step (bounded sample)
+
     def episode_batch(seed):
         env = ScalarEnv(S, V, Cc, Pp, EnvParams(**ENV_KW), seed=seed)
-        acts = np.random.default_rng(seed).uniform(-1, 1, (T, 2)).astype(np.float32)
+        acts = np.random.default_rng(seed).uniform(-1, 1, (EP * T, 2)).astype(np.float32)
         acts[:, 1] = 0.0
         env.reset()
         n = 0
@@ -139,7 +141,8 @@ def run_reference(args, rank, world):
             total += sum(pool.map(_call_episode_batch, range(k * procs, (k + 1) * procs)))
         el = time.perf_counter() - t0
     value = total / el
-    sample = f"{procs} processes x 1 scalar env x {T} steps per bench step; {total} env-steps in {el:.1f} s"
+    sample = (f"{procs} processes x 1 scalar reference-shaped env (oracle/hedge_scalar.py, greeks on) x {EP} episodes x {T} steps "
+              f"per bench step; {total} env-steps in {el:.1f} s")
     line = dict(impl="reference", metric="env-steps/sec (fused hedge step)", value=value, unit="env-steps/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / max(args.steps, 1),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",

@@ -58,6 +58,7 @@ class ResetRule(C.Structure):
 
 
 MODEL_GBM, MODEL_HESTON = 0, 1
+SIGMA_REALISED, SIGMA_BOOK_VARIANCE = 0, 1
 
 
 class SimParams(C.Structure):
@@ -109,6 +110,8 @@ SIGNATURES = {
                                   C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_schema_b_book": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_reprice_book": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32,
+                                      C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_bs_delta_hedge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_double,
                                         C.c_void_p, C.c_void_p]),
     "cantor_rollout": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(SimParams), C.c_int32,

@@ -128,6 +128,30 @@ def process_price_paths(paths, r=R, strike_multipliers=(1.0,), device="cuda", re
     return (calls, puts, vols.T) if return_vols else (calls, puts)
 
 
+def reprice_book(book: ReplayData, strike_multipliers=(1.0,), r=R, sigma="realised", tenor=None, greeks=False):
+    """Float32 multi-strike Black-Scholes book along every path of a packed book (BASELINE configs[2]).
+
+    ``process_price_paths`` (option_price_assignment.py:33-52) in throughput form: K_m = round(S_0) * mult_m, maturity to
+    the episode end (``tenor=None``) or a fixed ``tenor``; ``sigma="realised"`` is the reference's prefix volatility,
+    ``sigma="book"`` uses the book's instantaneous variance (Heston).  Returns time-major device tensors
+    ``calls, puts`` of shape ``[M, T+1, n_paths]`` (+ ``deltas, gammas`` with ``greeks=True``); ``.permute(0, 2, 1)``
+    gives the reference's path-major ``(n, T+1)`` planes.
+    """
+    if sigma not in ("realised", "book"):
+        raise ValueError("sigma must be 'realised' or 'book'")
+    dev = book.device
+    mult = torch.as_tensor(np.asarray(list(strike_multipliers), np.float32)).to(dev)
+    M, T1, ld = int(mult.numel()), book.episode_length + 1, book.ld
+    outs = [torch.empty((M, T1, ld), dtype=torch.float32, device=dev) for _ in range(4 if greeks else 2)]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cantor_reprice_book(
+            book.tensor.data_ptr(), ld, book.n_paths, book.episode_length, float(r), mult.data_ptr(), M,
+            _lib.SIGMA_REALISED if sigma == "realised" else _lib.SIGMA_BOOK_VARIANCE, float(tenor or 0.0),
+            outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr() if greeks else None,
+            outs[3].data_ptr() if greeks else None, _stream(dev)), "cantor_reprice_book")
+    return tuple(o[:, :, :book.n_paths] for o in outs)
+
+
 def calculate_annualized_vol_matrix(paths, device="cuda"):
     """option_price_assignment.py:23-31: realised annualised volatility of each path prefix (n, T+1) float64."""
     return process_price_paths(paths, device=device, return_vols=True)[2]

@@ -177,6 +177,16 @@ int cantor_bs_price(const double* S, const double* K, const double* T, const dou
 int cantor_schema_b_book(const double* paths, int32_t n_paths, int32_t episode_length, int64_t ld, double r,
                          const double* strike_mult, int32_t n_strikes, double* vols, double* calls, double* puts,
                          void* stream);
+/* The same book in float32, throughput form, straight from a packed book (S, v) in HBM: price, call delta and gamma of
+ * the strike ladder K_m = round(S_0) * strike_mult[m] along every path.  sigma_source selects the reference's realised
+ * volatility of the path prefix (:23-31) or the book's own instantaneous variance, sigma = sqrt(max(v_t, 0)) (Heston);
+ * fixed_tenor = 0 runs maturities to the episode end (:38), > 0 prices a constant tenor (the env's 30/252).
+ * calls / puts / deltas / gammas are [n_strikes * (T+1) * ld] float32, time-major per strike; deltas and gammas may
+ * be NULL.  Delta / gamma follow HedgingEnv._calculate_greeks (src/env/hedging_env_v2.py:94-106). */
+enum { CANTOR_SIGMA_REALISED = 0, CANTOR_SIGMA_BOOK_VARIANCE = 1 };
+int cantor_reprice_book(const float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length, double r,
+                        const float* strike_mult, int32_t n_strikes, int32_t sigma_source, double fixed_tenor,
+                        float* calls, float* puts, float* deltas, float* gammas, void* stream);
 /* bs_delta_hedge (src/tools/bs_delta.py:36-55): per-path delta-hedge P&L, time-major paths -> pnl [(T+1) * ld]. */
 int cantor_bs_delta_hedge(const double* paths, int32_t n_paths, int32_t episode_length, int64_t ld, double r,
                           double dt, double* pnl, void* stream);

@@ -95,6 +95,24 @@ def atm_book(paths, variances, r=RISK_FREE_RATE, tenor=30 / 252):
     return black_scholes(S, K, tenor, r, np.sqrt(np.maximum(v, 0.0)))
 
 
+def call_delta_gamma(S, K, T, r, sigma, epsilon=1e-8):
+    """Closed-form call delta Phi(d1) and gamma phi(d1) / (S sigma sqrt(T)) in float64, the formulas of
+    ``HedgingEnv._calculate_greeks`` (src/env/hedging_env_v2.py:94-106) for a general strike / maturity; at T <= 0 the
+    step delta of :90-92 and gamma 0.  sigma floored like ``black_scholes`` (option_price_assignment.py:12)."""
+    S, K, T, sigma = (np.asarray(x, np.float64) for x in (S, K, T, sigma))
+    with np.errstate(all="ignore"):
+        T_safe = np.where(T <= 0, 1e-8, T)
+        sig = np.where(sigma < epsilon, epsilon, sigma)
+        sst = sig * np.sqrt(T_safe)
+        d1 = (np.log(S / K) + (r + 0.5 * sig ** 2) * T_safe) / sst
+        delta = ndtr(d1)
+        gamma = np.exp(-0.5 * d1 * d1) / math.sqrt(2 * math.pi) / (S * sst)
+        step = np.where(S > K, 1.0, np.where(S == K, 0.5, 0.0))
+        delta = np.where(T <= 0, step, delta)
+        gamma = np.where(T <= 0, 0.0, gamma)
+    return delta, gamma
+
+
 def _scalar_call_and_delta(S, K, T, r, sigma, epsilon=1e-8):
     """bs_delta.py:11-24 (scalar, math-module arithmetic)."""
     if sigma < epsilon or T <= 0:

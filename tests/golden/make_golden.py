@@ -212,6 +212,36 @@ def make_outer_euler_golden():
     print(f"outer_euler_golden: {paths.shape[0]} paths x {paths.shape[1] - 1} days from the unmodified simulator")
 
 
+def make_policy_golden():
+    """Run the unmodified hand-written policies (baselines.py:74-103, delta_and_nothing.py:122-163) on random observations."""
+    import types
+    bl = _load("ref_baselines", f"{REF}/src/agents/baselines.py")
+    dn = _load("ref_delta_and_nothing", f"{REF}/src/benchmark/delta_and_nothing.py")
+    rng = np.random.default_rng(20240)
+    n = 600
+    obs = rng.uniform(-1, 1, (n, 13)).astype(np.float32)
+    obs[:, 7] = rng.uniform(0, 1, n)
+    obs[:, 9] = obs[:, 7] - 1
+    obs[::7, 7] = 0.0
+    obs[::11, 9] = 0.0
+    obs[::13, 7] = 5e-4                                    # |delta * 100| below the 0.1 threshold
+    pos_c, pos_p = rng.integers(-200, 201, n), rng.integers(-200, 201, n)
+    pos_c[:60] = 0
+    pos_p[:60] = 0
+    obs[:, 3], obs[:, 4] = pos_c / 200.0, pos_p / 200.0
+    env = types.SimpleNamespace(max_contracts_held=200, option_contract_multiplier=100, shares_held_fixed=10000,
+                                max_trade_per_step=15, action_space=types.SimpleNamespace(dtype=np.float32))
+    a_every = np.stack([bl.policy_delta_every_step(o, env) for o in obs])
+    a_none = np.stack([bl.policy_no_hedge(o, env) for o in obs])
+    a_bench = np.stack([dn.delta_hedging_action_selector(dict(
+        S_t=100.0, v_t=0.04, call_delta_atm=o[7], put_delta_atm=o[9], current_call_contracts=np.int64(c),
+        current_put_contracts=np.int64(q), shares_to_hedge=10000, option_contract_multiplier=100, max_trade_per_step=15))
+        for o, c, q in zip(obs, pos_c, pos_p)])
+    np.savez_compressed(os.path.join(HERE, "policy_golden.npz"), obs=obs, pos_c=pos_c, pos_p=pos_p,
+                        delta_every_step=a_every, no_hedge=a_none, delta_benchmark=a_bench)
+    print(f"policy_golden: {n} observations through the unmodified policies")
+
+
 class _NoBar:
     def __init__(self, it):
         self.it = it
@@ -227,6 +257,10 @@ class _NoBar:
 
 
 if __name__ == "__main__":
+    if "--policy-only" in sys.argv:
+        make_policy_golden()
+        sys.exit(0)
     if "--euler-only" not in sys.argv:
         main()
+        make_policy_golden()
     make_outer_euler_golden()

@@ -62,6 +62,14 @@ def test_delta_benchmark_matches_reference():
     np.testing.assert_array_equal(got, want)
 
 
+def test_policies_match_golden_vectors_from_the_unmodified_reference():
+    """tests/golden/policy_golden.npz (make_golden.py --policy-only): travels to the GPU box, unlike /root/reference."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "policy_golden.npz"))
+    np.testing.assert_array_equal(policy_oracle.delta_every_step(z["obs"]), z["delta_every_step"])
+    np.testing.assert_array_equal(policy_oracle.no_hedge(z["obs"]), z["no_hedge"])
+    np.testing.assert_array_equal(policy_oracle.delta_benchmark(z["obs"], z["pos_c"], z["pos_p"]), z["delta_benchmark"])
+
+
 def test_episode_statistics_definitions():
     rng = np.random.default_rng(2)
     pps = rng.normal(0, 1, (200, 30))
