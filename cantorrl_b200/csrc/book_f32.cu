@@ -31,18 +31,21 @@ struct BookOut {
     float* gammas;   // or NULL
 };
 
-// Welford recurrence over log-returns, float32 (option_price_assignment.py:23-31: std with ddof = 1, times sqrt(252)).
+// Welford recurrence over log-returns (option_price_assignment.py:23-31: std with ddof = 1, times sqrt(252)).  The
+// accumulators are float64 -- five FP64 operations per (path, t), nothing per strike -- so sigma keeps float32 accuracy
+// even after hundreds of steps; the log-return itself is float32.
 struct RunningVolF32 {
     int n = 0;
-    float mean = 0.f, m2 = 0.f;
-    __device__ __forceinline__ void push(float x) {
+    double mean = 0.0, m2 = 0.0;
+    __device__ __forceinline__ void push(float xf) {
+        const double x = (double)xf;
         ++n;
-        const float d = x - mean;
-        mean += __fdiv_rn(d, (float)n);
-        m2 = fmaf(d, x - mean, m2);
+        const double d = x - mean;
+        mean += d / (double)n;
+        m2 += d * (x - mean);
     }
     // n == 1 -> 0 / 0 = NaN, like np.std(ddof=1) of one sample
-    __device__ __forceinline__ float sigma_annual() const { return sqrtf(__fdiv_rn(m2, (float)(n - 1))) * 15.874507866387544f; }
+    __device__ __forceinline__ float sigma_annual() const { return (float)(sqrt(m2 / (double)(n - 1)) * 15.874507866387544); }
 };
 
 template <bool GREEKS>
@@ -133,6 +136,8 @@ book_f32_kernel(const float4* __restrict__ rec, long long ld, int n_paths, int T
                 const float c2m = pos2 ? -q2 : q2 - 1.0f;
                 call = fmaf(S, c1, -kd * c2);                                 // S Phi(d1) - K e^{-rT} Phi(d2)
                 put = fmaf(S, c1m, -kd * c2m);                                // K e^{-rT} Phi(-d2) - S Phi(-d1)
+                call = (call < 0.f) ? 0.f : call;                             // cancellation noise of a price that is >= 0
+                put = (put < 0.f) ? 0.f : put;                                // (a NaN stays a NaN)
                 if (GREEKS) {
                     delta = c1;
                     gamma = pdf1 * gamma_scale;                               // phi(d1) / (S sigma sqrt(T))

@@ -83,23 +83,15 @@ __device__ __forceinline__ Greeks atm_greeks_f64(float S, float K, float v_spot,
     return out;
 }
 
-// The same function for the float32 throughput path: 6 MUFU + ~30 FP32 instructions, no divisions.
-__device__ __forceinline__ Greeks atm_greeks_f32(float S, float K, float v_spot, const GreekConsts& g) {
-    Greeks out{0.f, 0.f, 0.f};
-    if (!g.record_metrics) return out;
-    const float vv = fmaxf(v_spot, 1e-8f);
-    if (S <= 1e-6f) {
-        out.call_delta = (K == 0.f) ? 0.5f : (K > 0.f ? 0.f : 1.f);
-        out.put_delta = (K == 0.f) ? -0.5f : (K < 0.f ? 0.f : -1.f);
-        return out;
-    }
-    if (g.T_d <= 1e-6) {
-        out.call_delta = (S > K) ? 1.f : (S == K ? 0.5f : 0.f);
-        out.put_delta = (S < K) ? -1.f : (S == K ? -0.5f : 0.f);
-        return out;
-    }
+// Shared core of the float32 ATM greeks and the float32 ATM price: d1, phi(d1), Phi(d1), Phi(d1) - 1 and
+// 1 / (sigma sqrt(T)) for S > 1e-6, K = rint(S), vv = max(v, 1e-8), T > 1e-6.  6 MUFU + ~30 FP32 instructions.
+struct AtmCore {
+    float d1, pdf, cdf, cdf_m1, inv_sst, rs;     // rs = 1 / sigma
+};
+__device__ __forceinline__ AtmCore atm_core_f32(float S, float K, float vv, float r, float T, float inv_sqrtT) {
+    AtmCore c;
     const float Kc = fmaxf(K, 1e-6f);
-    const float rs = mufu_rsqrt(vv);                                           // 1 / sigma
+    c.rs = mufu_rsqrt(vv);                                                     // 1 / sigma
     // log(S / K) with K = rint(S).  The reference rounds the quotient to float32 before the log (:99); with a
     // floored sigma that rounding is amplified by 1 / (sigma sqrt(T)) ~ 3e4 in d1, so it is reproduced (IEEE
     // division), and log(q) is taken through the log1p series of u = q - 1 (exact subtraction; |u| <= 1/16:
@@ -115,15 +107,33 @@ __device__ __forceinline__ Greeks atm_greeks_f32(float S, float K, float v_spot,
     } else {
         lg = mufu_lg2(1.0f + u) * kLn2f;
     }
-    const float num = fmaf(fmaf(0.5f, vv, g.r_f), g.T_f, lg);
-    const float inv_sst = rs * g.inv_sqrtT_f;                                  // 1 / (sigma sqrt(T))
-    const float d1 = num * inv_sst;
-    float cdf, cdf_m1;
-    const float pdf = normal_pdf_cdf(d1, &cdf, &cdf_m1);
-    out.call_delta = cdf;
-    out.put_delta = cdf_m1;
+    const float num = fmaf(fmaf(0.5f, vv, r), T, lg);
+    c.inv_sst = c.rs * inv_sqrtT;                                              // 1 / (sigma sqrt(T))
+    c.d1 = num * c.inv_sst;
+    c.pdf = normal_pdf_cdf(c.d1, &c.cdf, &c.cdf_m1);
+    return c;
+}
+
+// hedging_env_v2.py:79-107 for the float32 throughput path: no divisions beyond the one the reference rounds.
+__device__ __forceinline__ Greeks atm_greeks_f32(float S, float K, float v_spot, const GreekConsts& g) {
+    Greeks out{0.f, 0.f, 0.f};
+    if (!g.record_metrics) return out;
+    const float vv = fmaxf(v_spot, 1e-8f);
+    if (S <= 1e-6f) {
+        out.call_delta = (K == 0.f) ? 0.5f : (K > 0.f ? 0.f : 1.f);
+        out.put_delta = (K == 0.f) ? -0.5f : (K < 0.f ? 0.f : -1.f);
+        return out;
+    }
+    if (g.T_d <= 1e-6) {
+        out.call_delta = (S > K) ? 1.f : (S == K ? 0.5f : 0.f);
+        out.put_delta = (S < K) ? -1.f : (S == K ? -0.5f : 0.f);
+        return out;
+    }
+    const AtmCore c = atm_core_f32(S, K, vv, g.r_f, g.T_f, g.inv_sqrtT_f);
+    out.call_delta = c.cdf;
+    out.put_delta = c.cdf_m1;
     // :102-106  gamma = phi / (S sigma sqrt(T)), 0 when that denominator is < 1e-9  (S < 1e-9 / (sigma sqrt(T)))
-    out.gamma = (S < 1e-9f * inv_sst) ? 0.f : pdf * inv_sst * mufu_rcp(S);
+    out.gamma = (S < 1e-9f * c.inv_sst) ? 0.f : c.pdf * c.inv_sst * mufu_rcp(S);
     return out;
 }
 

@@ -113,9 +113,10 @@ __device__ __forceinline__ void make_observation_f64(float* __restrict__ o, cons
 
 // The same observation on the float32 throughput path (reciprocals from the SFU, no divisions).
 // `o` may point to shared memory (stride-13 rows) or to registers.
+// `g` = the ATM greeks of (S, v), computed by the caller (atm_greeks_f32, or shared with the price: atm_quote_f32).
 __device__ __forceinline__ void make_observation_f32(float* __restrict__ o, const StepConsts& k, float S, float v,
                                                      float C, float P, float inv_s0, int pos_c, int pos_p, int step,
-                                                     float S_prev, float v_prev) {
+                                                     float S_prev, float v_prev, const Greeks& g) {
     o[0] = S * inv_s0;
     o[1] = C * inv_s0;
     o[2] = P * inv_s0;
@@ -123,7 +124,6 @@ __device__ __forceinline__ void make_observation_f32(float* __restrict__ o, cons
     o[4] = (float)pos_p * k.inv_mc_f;
     o[5] = v;
     o[6] = (float)(k.T - step) * k.inv_T_f;
-    const Greeks g = atm_greeks_f32(S, rintf(S), v, k.g);
     o[7] = g.call_delta;
     o[8] = g.gamma;
     o[9] = g.put_delta;
@@ -135,6 +135,11 @@ __device__ __forceinline__ void make_observation_f32(float* __restrict__ o, cons
     }
     o[11] = clip_unit(ret);
     o[12] = clip_unit(dv);
+}
+__device__ __forceinline__ void make_observation_f32(float* __restrict__ o, const StepConsts& k, float S, float v,
+                                                     float C, float P, float inv_s0, int pos_c, int pos_p, int step,
+                                                     float S_prev, float v_prev) {
+    make_observation_f32(o, k, S, v, C, P, inv_s0, pos_c, pos_p, step, S_prev, v_prev, atm_greeks_f32(S, rintf(S), v, k.g));
 }
 
 // Host side: cantor_env_params -> StepConsts.  T = episode length.

