@@ -75,7 +75,7 @@ STATS_LEN = 16
 
 class Policy(C.Structure):
     _fields_ = [("kind", C.c_int32), ("put_leg_disabled", C.c_int32), ("mlp", C.c_void_p), ("actions", C.c_void_p),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("mlp_tensor_cores", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StatsOut(C.Structure):

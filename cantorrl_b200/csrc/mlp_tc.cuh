@@ -1,0 +1,241 @@
+// Tensor-core actor for the rollout kernel: the ReLU MLP 13 -> 64 -> 64 -> 2 of one CTA's 128 envs as three
+// tcgen05.mma products per env-step, bf16 operands staged in shared memory, float32 accumulators in tensor memory.
+//
+//   rows (M = 128)   = the CTA's envs: thread m owns env m, TMEM lane m holds its accumulator row
+//   layer 1  D[128 x 64] = A1[128 x 16] * W1^T     A1 = {normalised obs (13), 1.0, 0, 0}; W1 column 13 = b1 (bias folded)
+//   layer 2  D[128 x 64] = A2[128 x 80] * W2^T     A2 = {ReLU(h1) (64), 1.0, 0 x 15};     W2 column 64 = b2
+//   layer 3  D[128 x 16] = A2[128 x 80] * W3^T     A2 = {ReLU(h2) (64), 1.0, ...};        W3 rows 0, 1 = the two actions, column 64 = b3
+//
+// Operands use the canonical K-major, no-swizzle UMMA layout ("core matrices" of 8 rows x 16 bytes, cute
+// Layout_K_INTER_Atom): element (row, k) of a [rows x K] bf16 tile sits at
+//   (row / 8) * SBO + (k / 8) * LBO + (row % 8) * 16 + (k % 8) * 2      with LBO = 128, SBO = (K / 8) * 128
+// so thread m writes its row as K/8 sixteen-byte stores; eight consecutive threads fill one 128-byte core matrix
+// (bank-conflict free).  Each epilogue is: tcgen05.ld of the thread's own lane (16 columns at a time) -> ReLU fused
+// into cvt.rn.relu.bf16x2.f32 -> st.shared into the next layer's A tile.  One elected thread issues the MMAs and
+// commits them to an mbarrier that all 128 threads wait on.
+//
+// Reference: the actor head of the shipped policy, quantconnect/model_wrapper.py:177-185 (ReLU MLP), :131 (observation
+// normalisation), with SB3's clip of the action to the Box bounds.  bf16 operands make this the THROUGHPUT form of the
+// policy (~3 significant digits); the float32 FFMA form (rollout.cu: policy_mlp) is the parity form.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace cantor {
+namespace mlptc {
+
+constexpr int kRows = 128;                       // envs per CTA = UMMA M
+constexpr int kIn = 13, kHidden = 64, kOut = 2;
+constexpr int kK1 = 16;                          // layer-1 K: 13 inputs + ones column + 2 zero columns
+constexpr int kK2 = 80;                          // layer-2/3 K: 64 activations + ones column + 15 zero columns
+constexpr int kN3 = 16;                          // layer-3 N padded to the UMMA minimum for M = 128
+constexpr int kLbo = 128;                        // bytes between the core matrices of consecutive 8-element K chunks
+constexpr int kSbo1 = (kK1 / 8) * 128;           // bytes between 8-row groups, K = 16
+constexpr int kSbo2 = (kK2 / 8) * 128;           // K = 80
+constexpr int kW1Bytes = kHidden * kK1 * 2, kW2Bytes = kHidden * kK2 * 2, kW3Bytes = kN3 * kK2 * 2;
+constexpr int kA1Bytes = kRows * kK1 * 2, kA2Bytes = kRows * kK2 * 2;
+constexpr int kSmemBytes = kW1Bytes + kW2Bytes + kW3Bytes + kA1Bytes + kA2Bytes + 16;   // + mbarrier (8) + TMEM address (4)
+constexpr int kTmemCols = 64;
+constexpr unsigned kSpinLimit = 1u << 24;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = Blackwell).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M x N (cute::UMMA::InstrDescriptor).
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// {lo, hi} = {bf16(max(a, 0)), bf16(max(b, 0))}: `a` lands at the lower address
+__device__ __forceinline__ uint32_t relu_pack_bf16(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+
+struct Actor {
+    unsigned char* w1;      // shared-memory tiles (bf16, core-matrix layout)
+    unsigned char* w2;
+    unsigned char* w3;
+    unsigned char* a1;
+    unsigned char* a2;
+    uint32_t mbar, tmem, phase;
+    const float* norm;      // global: mean[13], inv_std[13]
+    bool timed_out;
+
+    // One-time CTA setup: converts the float32 weight block to bf16 tiles, allocates 64 TMEM columns, arms the mbarrier.
+    // `w` = W1[13][64] b1[64] W2[64][64] b2[64] W3[64][2] b3[2] mean[13] inv_std[13] (cantor_policy.mlp), in global memory.
+    __device__ __forceinline__ void setup(unsigned char* smem, const float* __restrict__ w) {
+        w1 = smem;
+        w2 = w1 + kW1Bytes;
+        w3 = w2 + kW2Bytes;
+        a1 = w3 + kW3Bytes;
+        a2 = a1 + kA1Bytes;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(a2 + kA2Bytes);
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+        mbar = smem_u32(bar);
+        phase = 0;
+        timed_out = false;
+        const float* W1 = w;
+        const float* b1 = W1 + kIn * kHidden;
+        const float* W2 = b1 + kHidden;
+        const float* b2 = W2 + kHidden * kHidden;
+        const float* W3 = b2 + kHidden;
+        const float* b3 = W3 + kHidden * kOut;
+        norm = b3 + kOut;
+        const int tid = threadIdx.x;
+        __nv_bfloat16* w1h = reinterpret_cast<__nv_bfloat16*>(w1);
+        for (int e = tid; e < kHidden * kK1; e += kRows) {           // B1(n, k) = W1[k][n], k = 13 -> b1[n]
+            const int n = e / kK1, k = e % kK1;
+            const float v = k < kIn ? W1[k * kHidden + n] : (k == kIn ? b1[n] : 0.f);
+            w1h[((n >> 3) * kSbo1 + (k >> 3) * kLbo + (n & 7) * 16 + (k & 7) * 2) >> 1] = __float2bfloat16_rn(v);
+        }
+        __nv_bfloat16* w2h = reinterpret_cast<__nv_bfloat16*>(w2);
+        for (int e = tid; e < kHidden * kK2; e += kRows) {           // B2(n, k) = W2[k][n], k = 64 -> b2[n]
+            const int n = e / kK2, k = e % kK2;
+            const float v = k < kHidden ? W2[k * kHidden + n] : (k == kHidden ? b2[n] : 0.f);
+            w2h[((n >> 3) * kSbo2 + (k >> 3) * kLbo + (n & 7) * 16 + (k & 7) * 2) >> 1] = __float2bfloat16_rn(v);
+        }
+        __nv_bfloat16* w3h = reinterpret_cast<__nv_bfloat16*>(w3);
+        for (int e = tid; e < kN3 * kK2; e += kRows) {               // B3(n, k) = W3[k][n] for n < 2, k = 64 -> b3[n]
+            const int n = e / kK2, k = e % kK2;
+            float v = 0.f;
+            if (n < kOut) v = k < kHidden ? W3[k * kOut + n] : (k == kHidden ? b3[n] : 0.f);
+            w3h[((n >> 3) * kSbo2 + (k >> 3) * kLbo + (n & 7) * 16 + (k & 7) * 2) >> 1] = __float2bfloat16_rn(v);
+        }
+        // constant tail of this thread's A2 row: column 64 = 1.0 (bias), 65..79 = 0
+        {
+            const int m = tid;
+            unsigned char* row = a2 + (m >> 3) * kSbo2 + (m & 7) * 16;
+            *reinterpret_cast<uint4*>(row + 8 * kLbo) = make_uint4(0x00003F80u, 0u, 0u, 0u);     // bf16(1.0) = 0x3F80
+            *reinterpret_cast<uint4*>(row + 9 * kLbo) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (tid < 32) {                                               // warp 0 owns the TMEM allocation
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        fence_proxy_async_smem();                                     // weight tiles -> visible to the tensor core (async proxy)
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        tmem = *tmem_slot;
+    }
+
+    __device__ __forceinline__ void teardown() {
+        fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
+    }
+
+    __device__ __forceinline__ void wait_mma() {
+        uint32_t done = 0;
+        unsigned spins = 0;
+        while (!done && !timed_out) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+            if (!done && ++spins > kSpinLimit) timed_out = true;      // never hang the GPU: bail out, the caller reports it
+        }
+        phase ^= 1;
+        fence_after_sync();
+    }
+
+    // publish this thread's freshly written A rows, then let one thread issue `ksteps` MMAs of K = 16 each
+    __device__ __forceinline__ void run_layer(uint32_t a_addr, uint32_t a_sbo, uint32_t b_addr, uint32_t b_sbo, int ksteps, uint32_t idesc) {
+        fence_before_sync();          // earlier tcgen05.ld of the accumulator this layer overwrites
+        fence_proxy_async_smem();     // st.shared of the A tile -> async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fence_after_sync();
+            for (int k = 0; k < ksteps; ++k)
+                umma_bf16(tmem, smem_desc(a_addr + k * 2 * kLbo, kLbo, a_sbo), smem_desc(b_addr + k * 2 * kLbo, kLbo, b_sbo),
+                          idesc, k > 0 ? 1u : 0u);
+            umma_commit(mbar);
+        }
+        wait_mma();
+    }
+
+    // accumulator row of this thread (64 columns) -> ReLU -> bf16 -> this thread's A2 row
+    __device__ __forceinline__ void hidden_epilogue() {
+        const int m = threadIdx.x;
+        const uint32_t lane_addr = tmem + ((uint32_t)(m & ~31) << 16);
+        unsigned char* row = a2 + (m >> 3) * kSbo2 + (m & 7) * 16;
+#pragma unroll
+        for (int c = 0; c < kHidden / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld16(lane_addr + c * 16, r);
+            tmem_ld_wait();
+            uint4 lo, hi;
+            lo.x = relu_pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
+            lo.y = relu_pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
+            lo.z = relu_pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));
+            lo.w = relu_pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
+            hi.x = relu_pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));
+            hi.y = relu_pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
+            hi.z = relu_pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13]));
+            hi.w = relu_pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
+            *reinterpret_cast<uint4*>(row + (2 * c) * kLbo) = lo;
+            *reinterpret_cast<uint4*>(row + (2 * c + 1) * kLbo) = hi;
+        }
+    }
+
+    // The actor on this thread's observation; CTA-collective (every thread of the CTA must call it each step).
+    __device__ __forceinline__ float2 forward(const float* o) {
+        const int m = threadIdx.x;
+        float x[kK1];
+#pragma unroll
+        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - __ldg(norm + i)) * __ldg(norm + kIn + i), -10.f), 10.f);
+        x[13] = 1.0f;
+        x[14] = 0.f;
+        x[15] = 0.f;
+        unsigned char* row = a1 + (m >> 3) * kSbo1 + (m & 7) * 16;
+        *reinterpret_cast<uint4*>(row) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+        *reinterpret_cast<uint4*>(row + kLbo) = make_uint4(pack_bf16(x[8], x[9]), pack_bf16(x[10], x[11]), pack_bf16(x[12], x[13]), pack_bf16(x[14], x[15]));
+        run_layer(smem_u32(a1), kSbo1, smem_u32(w1), kSbo1, kK1 / 16, instr_desc(kRows, kHidden));
+        hidden_epilogue();
+        run_layer(smem_u32(a2), kSbo2, smem_u32(w2), kSbo2, kK2 / 16, instr_desc(kRows, kHidden));
+        hidden_epilogue();
+        run_layer(smem_u32(a2), kSbo2, smem_u32(w3), kSbo2, kK2 / 16, instr_desc(kRows, kN3));
+        uint32_t r0, r1;
+        tmem_ld2(tmem + ((uint32_t)(m & ~31) << 16), r0, r1);
+        tmem_ld_wait();
+        return make_float2(fminf(fmaxf(__uint_as_float(r0), -1.f), 1.f), fminf(fmaxf(__uint_as_float(r1), -1.f), 1.f));
+    }
+};
+
+}  // namespace mlptc
+}  // namespace cantor

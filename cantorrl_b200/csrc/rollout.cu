@@ -13,6 +13,7 @@
 //   MLP actor 13-64-64-2          quantconnect/model_wrapper.py:131,177-185 (normalise, ReLU MLP, clip)
 // and the env step itself (hedge_core.cuh).
 #include "hedge_core.cuh"
+#include "mlp_tc.cuh"
 #include "sim_core.cuh"
 
 namespace cantor {
@@ -157,20 +158,24 @@ __device__ __forceinline__ void block_accumulate(double (&v)[NS], double* __rest
 }
 
 // SRC: 0 replay (packed book), 1 GBM on the fly, 2 Heston on the fly.
-// MLP: the policy is the MLP (compile-time, so the other policies do not pay for its registers).
-template <int SRC, bool MLP, bool WRITE>
+// MLP: 0 = one of the closed-form / tabulated policies, 1 = the MLP actor in float32 FFMAs (parity form),
+//      2 = the MLP actor on the tensor cores (bf16 tcgen05.mma, mlp_tc.cuh); compile-time, so the other policies do not
+//      pay for its registers and shared memory.
+template <int SRC, int MLP, bool WRITE>
 __global__ void __launch_bounds__(kRollThreads)
 rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const PolicyConsts pc, long long n_envs,
                long long env_offset, long long total_envs, int n_steps, const StatsOut st, const RolloutOut out,
                int obs_tma_ok, int share_quote) {
     extern __shared__ __align__(128) float smem_f[];
-    float* w_mlp = smem_f;                                                     // [kMlpFloats] when the policy is the MLP
-    constexpr int mlp_floats = MLP ? (kMlpFloats + 3) / 4 * 4 : 0;
+    float* w_mlp = smem_f;                                                     // [kMlpFloats] float32 weights (MLP == 1)
+    constexpr int mlp_floats = MLP == 1 ? (kMlpFloats + 3) / 4 * 4 : (MLP == 2 ? mlptc::kSmemBytes / 4 : 0);
     float* tile = smem_f + mlp_floats;                                         // [kRollThreads * 13] when WRITE
     double* red = reinterpret_cast<double*>(tile + (WRITE ? kRollThreads * CANTOR_OBS_DIM : 0));
-    if (MLP) {
+    mlptc::Actor actor;
+    if (MLP == 1) {
         for (int j = threadIdx.x; j < kMlpFloats; j += kRollThreads) w_mlp[j] = pc.mlp[j];
     }
+    if (MLP == 2) actor.setup(reinterpret_cast<unsigned char*>(smem_f), pc.mlp);
     __syncthreads();
 
     const long long first_env = (long long)blockIdx.x * kRollThreads;
@@ -230,7 +235,9 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             if (SRC != 0 && share_quote) make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y, gk);
             else make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y);
             float2 a;
-            if (MLP) {
+            if (MLP == 2) {
+                a = actor.forward(o);                                          // CTA-collective: all 128 threads, every step
+            } else if (MLP == 1) {
                 a = policy_mlp(o, w_mlp);
             } else {
                 switch (pc.kind) {
@@ -329,6 +336,10 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
     // ---- one reduction at the end: warp shuffle -> shared -> one atomic per statistic per block ---------------
     if (st.sums != nullptr) block_accumulate<11>(stat, st.sums, red);
     if (st.sums != nullptr && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(st.sums + 11, (double)n_envs * (double)n_steps);
+    if (MLP == 2) {
+        if (actor.timed_out && st.sums != nullptr) atomicAdd(st.sums + 15, 1.0);   // an MMA never completed: results are invalid
+        actor.teardown();
+    }
 }
 
 }  // namespace cantor
@@ -379,19 +390,20 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
     }
     if (n_steps == 0) return CANTOR_OK;
     const unsigned grid = (unsigned)((n_envs + kRollThreads - 1) / kRollThreads);
-    const size_t smem = (policy->kind == CANTOR_POLICY_MLP ? (kMlpFloats + 3) / 4 * 4 * sizeof(float) : 0) +
+    const int mlp_mode = policy->kind != CANTOR_POLICY_MLP ? 0 : (policy->mlp_tensor_cores ? 2 : 1);
+    const size_t smem = (mlp_mode == 1 ? (kMlpFloats + 3) / 4 * 4 * sizeof(float) : (mlp_mode == 2 ? (size_t)mlptc::kSmemBytes : 0)) +
                         (write ? kRollThreads * CANTOR_OBS_DIM * sizeof(float) : 0) + 11 * (kRollThreads / 32) * sizeof(double) + 16;
     const int tma_ok = write && aligned16(out->obs) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool mlp = policy->kind == CANTOR_POLICY_MLP;
     // the observation's greeks can ride on the price evaluation when the env and the simulator agree on (r, tenor)
     const int share = (src != 0 && params->record_metrics && k.g.r_f == sk.r && k.g.T_f == sk.tenor && sk.tenor > 1e-6f) ? 1 : 0;
 #define LAUNCH(SRC, MLP, WRITE) \
     rollout_kernel<SRC, MLP, WRITE><<<grid, kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok, share)
 #define LAUNCH_SRC(SRC)                                                      \
     do {                                                                     \
-        if (mlp) { if (write) LAUNCH(SRC, true, true); else LAUNCH(SRC, true, false); } \
-        else { if (write) LAUNCH(SRC, false, true); else LAUNCH(SRC, false, false); }   \
+        if (mlp_mode == 2) { if (write) LAUNCH(SRC, 2, true); else LAUNCH(SRC, 2, false); }      \
+        else if (mlp_mode == 1) { if (write) LAUNCH(SRC, 1, true); else LAUNCH(SRC, 1, false); } \
+        else { if (write) LAUNCH(SRC, 0, true); else LAUNCH(SRC, 0, false); }                    \
     } while (0)
     if (src == 0) LAUNCH_SRC(0);
     else if (src == 1) LAUNCH_SRC(1);

@@ -130,15 +130,17 @@ class HedgingRollout:
             store: bool = False) -> RolloutResult:
         """``n_steps`` env-steps of every env (auto-reset at episode ends), statistics accumulated into ``stats``.
 
-        policy   "no_hedge" | "random" | "delta_every_step" | "delta_benchmark" | "mlp" (with ``mlp=pack_mlp(...)``)
-                 | "actions" (open loop, ``actions`` float32 ``[n_steps, num_envs, 2]`` on the device)
+        policy   "no_hedge" | "random" | "delta_every_step" | "delta_benchmark" | "actions" (open loop, ``actions``
+                 float32 ``[n_steps, num_envs, 2]`` on the device) | "mlp" (``mlp=pack_mlp(...)``; float32 FFMA actor,
+                 the parity form) | "mlp_bf16" (same weights on the tensor cores: bf16 operands, float32 accumulation)
         store    also write the rollout (obs the policy saw, actions, reward, done), time-major
         """
         n, dev = self.num_envs, self.device
         pol = _lib.Policy()
         pol.put_leg_disabled = int(self.one_call_only)
         pol.seed = int(seed) & (2 ** 64 - 1)
-        if policy == "mlp":
+        if policy in ("mlp", "mlp_bf16"):
+            pol.mlp_tensor_cores = int(policy == "mlp_bf16")
             if mlp is None or mlp.dtype != torch.float32 or mlp.numel() != _lib.MLP_FLOATS or mlp.device != dev:
                 raise ValueError("policy='mlp' needs mlp=pack_mlp(...) on the rollout's device")
             pol.kind, pol.mlp = _lib.POLICY_MLP, mlp.data_ptr()

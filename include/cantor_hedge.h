@@ -245,6 +245,8 @@ typedef struct cantor_policy {
     const float* mlp;                    /* [CANTOR_MLP_FLOATS] for CANTOR_POLICY_MLP */
     const float* actions;                /* [n_steps, n_envs, 2] for CANTOR_POLICY_ACTIONS */
     uint64_t seed;                       /* CANTOR_POLICY_RANDOM */
+    int32_t mlp_tensor_cores;            /* CANTOR_POLICY_MLP: 0 = float32 FFMA (parity form), 1 = bf16 tcgen05.mma (throughput form) */
+    int32_t reserved;
 } cantor_policy;
 
 /* sums[] layout; every entry is a plain sum over finished episodes, so shards combine by addition (all-reduce):
@@ -254,7 +256,8 @@ typedef struct cantor_policy {
  *  5,6  ... of c = sum_t transaction_costs_total / T                    (train_ppo_v2.py:483,521; baselines.py:50,55)
  *  7,8  ... of R = sum_t reward                                         (train_ppo_v2.py:484)
  *  9,10 ... of s = sum_t per_share_step_pnl (signed)
- *  11   env-steps executed */
+ *  11   env-steps executed
+ *  15   error flag: > 0 if a tensor-core MLP launch timed out waiting for an MMA (results invalid) */
 #define CANTOR_STATS_LEN 16
 typedef struct cantor_stats_out {
     double* sums;                        /* [CANTOR_STATS_LEN], accumulated into (zero it first) */

@@ -59,6 +59,26 @@ def mlp_actor(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8):
     return np.clip(out, -1, 1).astype(F32)
 
 
+def _bf16(x):
+    """Round float32 to bfloat16 (round to nearest even), returned as float32."""
+    u = np.asarray(x, F32).view(np.uint32).astype(np.uint64)
+    r = ((u + np.uint64(0x7FFF) + ((u >> np.uint64(16)) & np.uint64(1))) >> np.uint64(16)) << np.uint64(16)
+    return r.astype(np.uint32).view(F32)
+
+
+def mlp_actor_bf16(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8):
+    """The tensor-core form of ``mlp_actor`` (cantorrl_b200/csrc/mlp_tc.cuh): inputs, weights, biases and hidden
+    activations rounded to bfloat16, products accumulated in float32 (float64 here: the order is the hardware's)."""
+    x = np.asarray(obs, F32)
+    if mean is not None:
+        inv = (1.0 / np.sqrt(np.asarray(var, np.float64) + epsilon)).astype(F32)
+        x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-10), F32(10))
+    h = _bf16(x).astype(np.float64) @ _bf16(W1).astype(np.float64).T + _bf16(b1)
+    h = _bf16(np.maximum(h, 0).astype(F32)).astype(np.float64) @ _bf16(W2).astype(np.float64).T + _bf16(b2)
+    out = _bf16(np.maximum(h, 0).astype(F32)).astype(np.float64) @ _bf16(W3).astype(np.float64).T + _bf16(b3)
+    return np.clip(out, -1, 1).astype(F32)
+
+
 def run_rollout(paths, vols, calls, puts, params: EnvParams, policy, n_envs, n_steps, env_offset=0, total_envs=None,
                 forced_actions=None, one_call_only=False, seed=0, mlp=None):
     """Free-running (or, with ``forced_actions`` [n_steps, n_envs, 2], teacher-forced) rollout of the oracle env.
@@ -88,6 +108,8 @@ def run_rollout(paths, vols, calls, puts, params: EnvParams, policy, n_envs, n_s
             a = policy_oracle.delta_benchmark(obs, env.pos_c, env.pos_p, 100, params.shares_to_hedge, params.max_trade_per_step)
         elif policy == "mlp":
             a = mlp_actor(obs, *mlp)
+        elif policy == "mlp_bf16":
+            a = mlp_actor_bf16(obs, *mlp)
         elif policy == "actions":
             a = np.asarray(forced_actions[g], F32)
         else:
