@@ -49,7 +49,8 @@ class ReplayBook(C.Structure):
 
 
 class EnvState(C.Structure):
-    _fields_ = [("core", C.c_void_p), ("cash", C.c_void_p), ("pv_prev", C.c_void_p)]
+    _fields_ = [("core", C.c_void_p), ("cash", C.c_void_p), ("pv_prev", C.c_void_p), ("episode_acc", C.c_void_p),
+                ("episode_return", C.c_void_p), ("episode_length", C.c_void_p), ("stats", C.c_void_p)]
 
 
 class ResetRule(C.Structure):
@@ -71,6 +72,7 @@ class SimParams(C.Structure):
 POLICY_NO_HEDGE, POLICY_RANDOM, POLICY_DELTA_BASELINES, POLICY_DELTA_BENCHMARK, POLICY_MLP, POLICY_ACTIONS = range(6)
 MLP_FLOATS = 5212
 STATS_LEN = 16
+VECNORM_DOUBLES = 96
 
 
 class Policy(C.Structure):
@@ -114,6 +116,10 @@ SIGNATURES = {
                                       C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_bs_delta_hedge": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_double,
                                         C.c_void_p, C.c_void_p]),
+    "cantor_vecnorm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cantor_vecnorm_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_void_p]),
     "cantor_rollout": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(SimParams), C.c_int32,
                                  C.POINTER(Policy), C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(StatsOut),
                                  C.POINTER(RolloutOut), C.c_void_p]),

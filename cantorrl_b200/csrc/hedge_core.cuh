@@ -142,6 +142,73 @@ __device__ __forceinline__ void make_observation_f32(float* __restrict__ o, cons
     make_observation_f32(o, k, S, v, C, P, inv_s0, pos_c, pos_p, step, S_prev, v_prev, atm_greeks_f32(S, rintf(S), v, k.g));
 }
 
+// ---- episode statistics (include/cantor_hedge.h: cantor_stats_out) ------------------------------------------------
+struct StatsOut {
+    double* sums;               // [CANTOR_STATS_LEN]
+    unsigned long long* hist;   // [hist_bins] of b = |sum pps| / T, or NULL
+    double* hist_sum;           // [hist_bins] sum of b per bin, or NULL
+    float* episode_b;           // [n_episodes_per_env, n_envs] or NULL: per-episode b for an exact CVaR
+    float hist_scale;           // bins / hist_max
+    int hist_bins;
+    long long episode_slots;    // capacity of episode_b in episodes per env
+};
+
+// Block reduction of NS doubles per thread, then one atomicAdd per value per block.  smem: [NS * THREADS / 32] doubles.
+template <int NS, int THREADS>
+__device__ __forceinline__ void block_accumulate(double (&v)[NS], double* __restrict__ global, double* smem) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[s] += __shfl_down_sync(0xffffffffu, v[s], off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) smem[s * (THREADS / 32) + warp] = v[s];
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) t += smem[threadIdx.x * (THREADS / 32) + w];
+        atomicAdd(global + threadIdx.x, t);
+    }
+    __syncthreads();
+}
+
+// The 11 per-episode statistics of one finished episode (sums[0..10]) from its running sums; also the histogram.
+// acc = {sum reward, sum pps, sum |pps|, sum cost}.  Returns b = |sum pps| / T.
+__device__ __forceinline__ float episode_statistics(double (&stat)[11], float acc_reward, float acc_pps, float acc_abs,
+                                                    float acc_cost, float inv_T, const StatsOut& st) {
+    const double ea = (double)(acc_abs * inv_T);                // baselines.py:54
+    const float ebf = fabsf(acc_pps) * inv_T;
+    const double eb = (double)ebf;                              // train_ppo_v2.py:520
+    const double ec = (double)(acc_cost * inv_T);               // :521 / baselines.py:55
+    const double er = (double)acc_reward, es = (double)acc_pps;
+    stat[0] += 1.0;
+    stat[1] += ea; stat[2] += ea * ea;
+    stat[3] += eb; stat[4] += eb * eb;
+    stat[5] += ec; stat[6] += ec * ec;
+    stat[7] += er; stat[8] += er * er;
+    stat[9] += es; stat[10] += es * es;
+    if (st.hist != nullptr) {
+        const int bin = min(st.hist_bins - 1, max(0, (int)(ebf * st.hist_scale)));
+        atomicAdd(st.hist + bin, 1ull);
+        if (st.hist_sum != nullptr) atomicAdd(st.hist_sum + bin, eb);
+    }
+    return ebf;
+}
+
+inline int make_stats_out(const cantor_stats_out* stats, StatsOut* so) {
+    *so = StatsOut{nullptr, nullptr, nullptr, nullptr, 0.f, 0, 0};
+    if (stats == nullptr) return CANTOR_OK;
+    CANTOR_REQUIRE(stats->sums != nullptr, "stats.sums is NULL");
+    CANTOR_REQUIRE(stats->hist == nullptr || (stats->hist_bins > 0 && stats->hist_max > 0), "histogram needs bins and a range");
+    *so = StatsOut{stats->sums, (unsigned long long*)stats->hist, stats->hist ? stats->hist_sum : nullptr, stats->episode_b,
+                   stats->hist ? (float)(stats->hist_bins / stats->hist_max) : 0.f, stats->hist_bins, stats->episode_slots};
+    return CANTOR_OK;
+}
+
 // Host side: cantor_env_params -> StepConsts.  T = episode length.
 inline int make_step_consts(const cantor_env_params* p, int T, StepConsts* k) {
     CANTOR_REQUIRE(p != nullptr, "params is NULL");

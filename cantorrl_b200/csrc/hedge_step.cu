@@ -83,14 +83,29 @@ __device__ __forceinline__ void store_obs_tile(float* __restrict__ obs, const fl
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <bool F64, bool INFO>
-__global__ void __launch_bounds__(kStepThreads, CANTOR_STEP_MIN_BLOCKS)
+// Optional Monitor state / outputs (cantor_env_state.episode_*): per-env running sums of the current episode.
+struct Monitor {
+    void* acc;                 // [n * 4] float / double: {reward, pps, |pps|, cost}
+    void* episode_return;      // [n] float / double, written at episode end
+    int* episode_length;       // [n]
+    StatsOut stats;            // stats.sums == NULL: no reduction
+};
+
+template <bool F64, bool INFO, bool MON>
+__global__ void __launch_bounds__(kStepThreads, (MON || INFO || F64) ? 8 : CANTOR_STEP_MIN_BLOCKS)
 hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                   double* __restrict__ pv_arr, long long n_envs, const float2* __restrict__ actions,
                   float* __restrict__ obs, void* __restrict__ reward_arr, unsigned char* __restrict__ done_arr,
                   float* __restrict__ terminal_obs, int auto_reset, const ResetRule rr, const InfoOut info,
-                  int obs_tma_ok) {
+                  int obs_tma_ok, const Monitor mon) {
     __shared__ __align__(128) float tile[kStepThreads * CANTOR_OBS_DIM];
+    __shared__ double red[MON ? 11 * (kStepThreads / 32) : 1];
+    double stat[11];
+    bool finished_episode = false;                                            // MON: this thread's env just ended an episode
+    if (MON) {
+#pragma unroll
+        for (int s = 0; s < 11; ++s) stat[s] = 0.0;
+    }
     const long long first_env = (long long)blockIdx.x * kStepThreads;
     const long long i = first_env + threadIdx.x;
     const int rows = (int)min((long long)kStepThreads, n_envs - first_env);
@@ -175,6 +190,23 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
                 pv_prev = pv;
             }
             __stcs(reinterpret_cast<double*>(reward_arr) + i, reward);
+            if (MON && !already_done) {
+                double2* ap = reinterpret_cast<double2*>(mon.acc) + 2 * i;
+                double2 a0 = ap[0], a1 = ap[1];                               // {reward, pps}, {|pps|, cost}
+                a0.x += reward; a0.y += pps; a1.x += fabs(pps); a1.y += costs;
+                if (terminated) {
+                    if (mon.episode_return != nullptr) reinterpret_cast<double*>(mon.episode_return)[i] = a0.x;
+                    if (mon.episode_length != nullptr) mon.episode_length[i] = t_new;
+                    if (mon.stats.sums != nullptr) {
+                        episode_statistics(stat, (float)a0.x, (float)a0.y, (float)a1.x, (float)a1.y, k.inv_T_f, mon.stats);
+                        finished_episode = true;
+                    }
+                    a0 = make_double2(0.0, 0.0);
+                    a1 = a0;
+                }
+                ap[0] = a0;
+                ap[1] = a1;
+            }
         } else {
             // float32 ledger (hedge_core.cuh): P&L as a sum of small differences, no portfolio value formed
             inv_s0 = mufu_rcp(s0_floor);
@@ -193,6 +225,21 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
             }
             if (!already_done) cash_f = cash_new;
             __stcs(reinterpret_cast<float*>(reward_arr) + i, reward);
+            if (MON && !already_done) {
+                float4* ap = reinterpret_cast<float4*>(mon.acc) + i;
+                float4 a = *ap;                                               // {reward, pps, |pps|, cost}
+                a.x += reward; a.y += pps; a.z += fabsf(pps); a.w += costs;
+                if (terminated) {
+                    if (mon.episode_return != nullptr) reinterpret_cast<float*>(mon.episode_return)[i] = a.x;
+                    if (mon.episode_length != nullptr) mon.episode_length[i] = t_new;
+                    if (mon.stats.sums != nullptr) {
+                        episode_statistics(stat, a.x, a.y, a.z, a.w, k.inv_T_f, mon.stats);
+                        finished_episode = true;
+                    }
+                    a = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                *ap = a;
+            }
         }
         if (INFO && !already_done) {
             double* f = info.f64 + i;
@@ -239,6 +286,14 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, obs_tma_ok && (rows % 4 == 0));
+    if (MON) {
+        // finished episodes -> statistics vector: warp shuffle -> shared -> one atomic per statistic per CTA, only on the
+        // steps where some env of this CTA finished (block-uniform vote, so the barrier inside is safe)
+        if (mon.stats.sums != nullptr && __syncthreads_or(finished_episode)) {
+            block_accumulate<11, kStepThreads>(stat, mon.stats.sums, red);
+        }
+        if (mon.stats.sums != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(mon.stats.sums + 11, (double)n_envs);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -246,10 +301,18 @@ template <bool F64>
 __global__ void __launch_bounds__(kStepThreads)
 env_reset_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                  double* __restrict__ pv_arr, long long n_envs, const unsigned char* __restrict__ mask,
-                 const int* __restrict__ path_idx, float* __restrict__ obs) {
+                 const int* __restrict__ path_idx, float* __restrict__ obs, void* __restrict__ episode_acc) {
     const long long i = (long long)blockIdx.x * kStepThreads + threadIdx.x;
     if (i >= n_envs) return;
     if (mask != nullptr && mask[i] == 0) return;
+    if (episode_acc != nullptr) {
+        if (F64) {
+            reinterpret_cast<double2*>(episode_acc)[2 * i] = make_double2(0.0, 0.0);
+            reinterpret_cast<double2*>(episode_acc)[2 * i + 1] = make_double2(0.0, 0.0);
+        } else {
+            reinterpret_cast<float4*>(episode_acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     float o[CANTOR_OBS_DIM];
     int4 core;
     double cash, pv_prev;
@@ -280,6 +343,9 @@ static int check_state(const cantor_env_state* st, int precision) {
     CANTOR_REQUIRE(aligned16(st->core), "state.core must be 16-byte aligned");
     CANTOR_REQUIRE(precision == CANTOR_F32 || precision == CANTOR_F64, "precision must be 32 or 64");
     CANTOR_REQUIRE(precision == CANTOR_F32 || st->pv_prev != nullptr, "state.pv_prev is required in F64 mode");
+    CANTOR_REQUIRE(st->episode_acc == nullptr || aligned16(st->episode_acc), "state.episode_acc must be 16-byte aligned");
+    CANTOR_REQUIRE(st->episode_acc != nullptr || (st->episode_return == nullptr && st->episode_length == nullptr && st->stats == nullptr),
+                   "episode_return / episode_length / stats need state.episode_acc");
     return CANTOR_OK;
 }
 
@@ -303,10 +369,10 @@ extern "C" int cantor_env_reset(const cantor_env_params* params, const cantor_re
     cudaStream_t s = (cudaStream_t)stream;
     if (precision == CANTOR_F64)
         env_reset_kernel<true><<<grid, kStepThreads, 0, s>>>(k, b, (int4*)state->core, state->cash, state->pv_prev,
-                                                             n_envs, mask, path_idx, obs);
+                                                             n_envs, mask, path_idx, obs, state->episode_acc);
     else
         env_reset_kernel<false><<<grid, kStepThreads, 0, s>>>(k, b, (int4*)state->core, state->cash, nullptr, n_envs,
-                                                              mask, path_idx, obs);
+                                                              mask, path_idx, obs, state->episode_acc);
     return check_launch("env_reset_kernel");
 }
 
@@ -337,6 +403,10 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
         CANTOR_REQUIRE(info->f64 != nullptr && info->i32 != nullptr, "info arrays are NULL");
         io = InfoOut{info->f64, info->i32};
     }
+    Monitor mon{state->episode_acc, state->episode_return, state->episode_length, {}};
+    rc = make_stats_out(state->episode_acc ? state->stats : nullptr, &mon.stats);
+    if (rc) return rc;
+    const bool mon_on = state->episode_acc != nullptr;
     if (n_envs == 0) return CANTOR_OK;
     const unsigned grid = (unsigned)((n_envs + kStepThreads - 1) / kStepThreads);
     cudaStream_t s = (cudaStream_t)stream;
@@ -353,10 +423,13 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
         unsigned char* done_t = done + (size_t)t * n_envs;
         int tma_ok = aligned16(obs_t) ? 1 : 0;
         void* args[] = {&k, &b, &core, &cash, &pv, &n, &a_t, &obs_t, &rew_t, &done_t, &terminal_obs, &auto_reset,
-                        &rr, &io, &tma_ok};
+                        &rr, &io, &tma_ok, &mon};
         const void* fn;
-        if (precision == CANTOR_F64) fn = info ? (const void*)hedge_step_kernel<true, true> : (const void*)hedge_step_kernel<true, false>;
-        else fn = info ? (const void*)hedge_step_kernel<false, true> : (const void*)hedge_step_kernel<false, false>;
+#define PICK(F64) (info ? (mon_on ? (const void*)hedge_step_kernel<F64, true, true> : (const void*)hedge_step_kernel<F64, true, false>) \
+                        : (mon_on ? (const void*)hedge_step_kernel<F64, false, true> : (const void*)hedge_step_kernel<F64, false, false>))
+        if (precision == CANTOR_F64) fn = PICK(true);
+        else fn = PICK(false);
+#undef PICK
         rc = launch_pdl(fn, dim3(grid), dim3(kStepThreads), s, args);
         if (rc) return rc;
         rr.episode_counter += 1;

@@ -35,7 +35,7 @@ constexpr int kSbo1 = (kK1 / 8) * 128;           // bytes between 8-row groups, 
 constexpr int kSbo2 = (kK2 / 8) * 128;           // K = 80
 constexpr int kW1Bytes = kHidden * kK1 * 2, kW2Bytes = kHidden * kK2 * 2, kW3Bytes = kN3 * kK2 * 2;
 constexpr int kA1Bytes = kRows * kK1 * 2, kA2Bytes = kRows * kK2 * 2;
-constexpr int kSmemBytes = kW1Bytes + kW2Bytes + kW3Bytes + kA1Bytes + kA2Bytes + 16;   // + mbarrier (8) + TMEM address (4)
+constexpr int kSmemBytes = kW1Bytes + kW2Bytes + kW3Bytes + kA1Bytes + kA2Bytes + 16 + 128;   // + mbarrier (8) + TMEM address (4) + mean / inv_std (2 x 16 floats)
 constexpr int kTmemCols = 64;
 constexpr unsigned kSpinLimit = 1u << 24;
 
@@ -89,7 +89,7 @@ struct Actor {
     unsigned char* a1;
     unsigned char* a2;
     uint32_t mbar, tmem, phase;
-    const float* norm;      // global: mean[13], inv_std[13]
+    const float* norm;      // shared: mean[16], inv_std[16]
     bool timed_out;
 
     // One-time CTA setup: converts the float32 weight block to bf16 tiles, allocates 64 TMEM columns, arms the mbarrier.
@@ -111,8 +111,10 @@ struct Actor {
         const float* b2 = W2 + kHidden * kHidden;
         const float* W3 = b2 + kHidden;
         const float* b3 = W3 + kHidden * kOut;
-        norm = b3 + kOut;
         const int tid = threadIdx.x;
+        float* norm_s = reinterpret_cast<float*>(a2 + kA2Bytes + 16);
+        if (tid < 32) norm_s[tid] = (tid & 15) < kIn ? (b3 + kOut)[(tid >> 4) * kIn + (tid & 15)] : 0.f;
+        norm = norm_s;
         __nv_bfloat16* w1h = reinterpret_cast<__nv_bfloat16*>(w1);
         for (int e = tid; e < kHidden * kK1; e += kRows) {           // B1(n, k) = W1[k][n], k = 13 -> b1[n]
             const int n = e / kK1, k = e % kK1;
@@ -218,7 +220,7 @@ struct Actor {
         const int m = threadIdx.x;
         float x[kK1];
 #pragma unroll
-        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - __ldg(norm + i)) * __ldg(norm + kIn + i), -10.f), 10.f);
+        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - norm[i]) * norm[16 + i], -10.f), 10.f);
         x[13] = 1.0f;
         x[14] = 0.f;
         x[15] = 0.f;

@@ -38,16 +38,6 @@ struct RolloutOut {
     unsigned char* done;        // [n_steps, n_envs]
 };
 
-struct StatsOut {
-    double* sums;               // [CANTOR_STATS_LEN]
-    unsigned long long* hist;   // [hist_bins] of b = |sum pps| / T, or NULL
-    double* hist_sum;           // [hist_bins] sum of b per bin, or NULL
-    float* episode_b;           // [n_episodes_per_env, n_envs] or NULL: per-episode b for an exact CVaR
-    float hist_scale;           // bins / hist_max
-    int hist_bins;
-    long long episode_slots;    // capacity of episode_b in episodes per env
-};
-
 // ---- policies ------------------------------------------------------------------------------------------
 // baselines.py:77-103 evaluated in float32 like NumPy does on a float32 observation (python ints are weak).
 // Returns CONTRACT COUNTS clipped to +-max_trade, which the env then multiplies by max_trade again and clips
@@ -89,7 +79,8 @@ __device__ __forceinline__ float2 policy_random(const PolicyConsts& pc, unsigned
 }
 
 // ReLU MLP 13 -> 64 -> 64 -> 2 on the normalised observation; weights broadcast from shared memory.
-__device__ __forceinline__ float2 policy_mlp(const float* o, const float* __restrict__ w) {
+// noinline: inlined into the 4x-unrolled step loop the 64-wide accumulator arrays no longer fit the register file
+__device__ __noinline__ float2 policy_mlp(const float* o, const float* __restrict__ w) {
     const float* W1 = w;
     const float* b1 = W1 + kMlpIn * kMlpHidden;
     const float* W2 = b1 + kMlpHidden;
@@ -131,30 +122,6 @@ __device__ __forceinline__ float2 policy_mlp(const float* o, const float* __rest
         out0 = fmaf(a3, W3[(j + 3) * 2], out0); out1 = fmaf(a3, W3[(j + 3) * 2 + 1], out1);
     }
     return make_float2(fminf(fmaxf(out0, -1.f), 1.f), fminf(fmaxf(out1, -1.f), 1.f));
-}
-
-// ---- statistics --------------------------------------------------------------------------------------------
-// Block reduction of NS doubles per thread, then one atomicAdd per value per block.
-template <int NS>
-__device__ __forceinline__ void block_accumulate(double (&v)[NS], double* __restrict__ global, double* smem /* [NS * 4] */) {
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v[s] += __shfl_down_sync(0xffffffffu, v[s], off);
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) smem[s * (kRollThreads / 32) + warp] = v[s];
-    }
-    __syncthreads();
-    if (threadIdx.x < NS) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < kRollThreads / 32; ++w) t += smem[threadIdx.x * (kRollThreads / 32) + w];
-        atomicAdd(global + threadIdx.x, t);
-    }
-    __syncthreads();
 }
 
 // SRC: 0 replay (packed book), 1 GBM on the fly, 2 Heston on the fly.
@@ -308,24 +275,9 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             ++g;
             if (terminated) {
                 if (live) {
-                    const float invT = k.inv_T_f;
-                    const double ea = (double)(acc_abs * invT);                // baselines.py:54
-                    const double eb = (double)(fabsf(acc_pps) * invT);         // train_ppo_v2.py:520
-                    const double ec = (double)(acc_cost * invT);               // :521 / baselines.py:55
-                    const double er = (double)acc_reward, es = (double)acc_pps;
-                    stat[0] += 1.0;
-                    stat[1] += ea; stat[2] += ea * ea;
-                    stat[3] += eb; stat[4] += eb * eb;
-                    stat[5] += ec; stat[6] += ec * ec;
-                    stat[7] += er; stat[8] += er * er;
-                    stat[9] += es; stat[10] += es * es;
-                    if (st.hist != nullptr) {
-                        const int bin = min(st.hist_bins - 1, max(0, (int)((float)eb * st.hist_scale)));
-                        atomicAdd(st.hist + bin, 1ull);
-                        if (st.hist_sum != nullptr) atomicAdd(st.hist_sum + bin, eb);
-                    }
+                    const float eb = episode_statistics(stat, acc_reward, acc_pps, acc_abs, acc_cost, k.inv_T_f, st);
                     if (st.episode_b != nullptr && episode < st.episode_slots)
-                        st.episode_b[episode * n_envs + i] = (float)eb;
+                        st.episode_b[episode * n_envs + i] = eb;
                 }
                 ++episode;
                 begin_episode();
@@ -334,7 +286,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
         }
     }
     // ---- one reduction at the end: warp shuffle -> shared -> one atomic per statistic per block ---------------
-    if (st.sums != nullptr) block_accumulate<11>(stat, st.sums, red);
+    if (st.sums != nullptr) block_accumulate<11, kRollThreads>(stat, st.sums, red);
     if (st.sums != nullptr && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(st.sums + 11, (double)n_envs * (double)n_steps);
     if (MLP == 2) {
         if (actor.timed_out && st.sums != nullptr) atomicAdd(st.sums + 15, 1.0);   // an MMA never completed: results are invalid
@@ -375,13 +327,9 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
     if (rc) return rc;
     PolicyConsts pc{policy->kind, policy->put_leg_disabled, policy->mlp, (const float2*)policy->actions,
                     (unsigned)(policy->seed & 0xffffffffull), (unsigned)(policy->seed >> 32)};
-    StatsOut so{nullptr, nullptr, nullptr, nullptr, 0.f, 0, 0};
-    if (stats != nullptr) {
-        CANTOR_REQUIRE(stats->sums != nullptr, "stats.sums is NULL");
-        CANTOR_REQUIRE(stats->hist == nullptr || (stats->hist_bins > 0 && stats->hist_max > 0), "histogram needs bins and a range");
-        so = StatsOut{stats->sums, (unsigned long long*)stats->hist, stats->hist ? stats->hist_sum : nullptr, stats->episode_b,
-                      stats->hist ? (float)(stats->hist_bins / stats->hist_max) : 0.f, stats->hist_bins, stats->episode_slots};
-    }
+    StatsOut so;
+    rc = make_stats_out(stats, &so);
+    if (rc) return rc;
     RolloutOut ro{nullptr, nullptr, nullptr, nullptr};
     const bool write = out != nullptr;
     if (write) {

@@ -56,7 +56,7 @@ class VecInfo:
         self._env, self._done, self._terminal_obs = env, done, terminal_obs
 
     def keys(self):
-        ks = ["terminal_observation"]
+        ks = ["terminal_observation"] + (["episode"] if self._env.monitor else [])
         if self._env._info_f64 is not None:
             ks += list(_lib.INFO_F64_KEYS) + list(_lib.INFO_I32_KEYS) + ["loss_type_used"]
         return ks
@@ -68,6 +68,10 @@ class VecInfo:
                 return self._terminal_obs
             if key == "loss_type_used":
                 return env.loss_type
+            if key == "episode":          # Monitor: return / length of the episode that just ended, valid where done
+                if not env.monitor:
+                    raise KeyError("'episode': construct HedgingVecEnv(monitor=True)")
+                return {"r": env._ep_return, "l": env._ep_length}
             if env._info_f64 is None:
                 raise KeyError(f"{key!r}: construct HedgingVecEnv(record_info=True) to materialise the info dict")
             if key in _lib.INFO_F64_KEYS:
@@ -87,6 +91,8 @@ class VecInfo:
             out["loss_type_used"] = env.loss_type
         if self._terminal_obs is not None and bool(self._done[i]):
             out["terminal_observation"] = self._terminal_obs[i].cpu().numpy()
+        if env.monitor and bool(self._done[i]):
+            out["episode"] = {"r": float(env._ep_return[i]), "l": int(env._ep_length[i]), "t": 0.0}
         return out
 
     def get(self, key, default=None):
@@ -116,6 +122,9 @@ class HedgingVecEnv:
     record_info      materialise the numeric ``info`` keys each step (costs 160 extra bytes per env-step)
     auto_reset       VecEnv convention (default).  False keeps finished envs at the terminal state.
     env_offset       global index of env 0 on this rank (multi-GPU sharding by path index)
+    monitor          SB3 ``Monitor`` fused into the step kernel: per-env episode return / length, reported as
+                     ``infos["episode"]`` (``{"r", "l"}`` tensors, valid where done) and ``infos[i]["episode"]``
+    stats            an ``EpisodeStats``: finished episodes are reduced into it inside the kernel (needs ``monitor=True``)
     """
 
     metadata = {"render_modes": [], "render_fps": 1}
@@ -134,7 +143,8 @@ class HedgingVecEnv:
                  profile_print_interval=0,
                  record_metrics=True,
                  *, num_envs=1, data=None, device="cuda", precision="fp32", version="v2",
-                 episode_sampler=None, seed=None, record_info=False, auto_reset=True, env_offset=0):
+                 episode_sampler=None, seed=None, record_info=False, auto_reset=True, env_offset=0, monitor=False,
+                 stats=None):
         if version not in ("v1", "v2"):
             raise ValueError("version must be 'v1' or 'v2'")
         if version == "v1" and (theta_weight != 0.0 or slippage_bps != 0.0):
@@ -210,6 +220,21 @@ class HedgingVecEnv:
         self._cash = torch.zeros(n, dtype=ftype, device=dev)
         self._pv_prev = torch.zeros(n, dtype=torch.float64, device=dev) if precision == "fp64" else None
         self._state = _lib.EnvState(self._core.data_ptr(), self._cash.data_ptr(), _lib.ptr(self._pv_prev))
+        self.monitor = bool(monitor)
+        self.stats = stats
+        self._ep_acc = self._ep_return = self._ep_length = self._stats_c = None
+        if stats is not None and not monitor:
+            raise ValueError("stats needs monitor=True")
+        if monitor:
+            self._ep_acc = torch.zeros((n, 4), dtype=ftype, device=dev)
+            self._ep_return = torch.zeros(n, dtype=ftype, device=dev)
+            self._ep_length = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._state.episode_acc = self._ep_acc.data_ptr()
+            self._state.episode_return = self._ep_return.data_ptr()
+            self._state.episode_length = self._ep_length.data_ptr()
+            if stats is not None:
+                self._stats_c = stats.c_struct()                       # kept alive: the state holds a pointer to it
+                self._state.stats = C.cast(C.pointer(self._stats_c), C.c_void_p)
         self._obs = torch.zeros((n, _lib.OBS_DIM), dtype=torch.float32, device=dev)
         self._reward = torch.zeros(n, dtype=ftype, device=dev)
         self._done = torch.zeros(n, dtype=torch.uint8, device=dev)

@@ -1,0 +1,142 @@
+"""Device-resident ``VecNormalize``: the wrapper the reference puts around its env, without a device->host round trip.
+
+Reference use: ``VecNormalize(env, norm_obs=True, norm_reward=True, clip_obs=10.0, gamma=gamma)``
+(``src/agents/train_ppo_v2.py:204-208, 305-309``), saved / loaded with the model (``:315-317, 449-455``), its statistics
+exported for deployment (``quantconnect/extract_model.py:62-79``; applied as ``(obs - mean) / sqrt(var + 1e-8)``,
+``quantconnect/model_wrapper.py:131``).  Stable-Baselines3 is an un-vendored dependency, so this mirrors its public
+behaviour (attribute and method names included); all arithmetic runs in ``cantor_vecnorm_step`` (three chained kernels).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class RunningMeanStdView:
+    """``mean`` / ``var`` / ``count`` of one running statistic (views of the device buffer, float64)."""
+
+    def __init__(self, mean, var, count):
+        self.mean, self.var, self._count = mean, var, count
+
+    @property
+    def count(self):
+        return float(self._count)
+
+
+class VecNormalize:
+    def __init__(self, venv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0, gamma=0.99,
+                 epsilon=1e-8, keep_original=False):
+        _lib.lib()
+        self.venv = venv
+        self.num_envs = venv.num_envs
+        self.observation_space, self.action_space = venv.observation_space, venv.action_space
+        self.training, self.norm_obs, self.norm_reward = bool(training), bool(norm_obs), bool(norm_reward)
+        self.clip_obs, self.clip_reward, self.gamma, self.epsilon = float(clip_obs), float(clip_reward), float(gamma), float(epsilon)
+        self.device = venv.device
+        self._rms = torch.zeros(_lib.VECNORM_DOUBLES, dtype=torch.float64, device=self.device)
+        self.returns = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cantor_vecnorm_init(self._rms.data_ptr(), self.returns.data_ptr(), self.num_envs,
+                                                      _lib.current_stream_ptr(self.device)), "cantor_vecnorm_init")
+        self.obs_rms = RunningMeanStdView(self._rms[0:13], self._rms[13:26], self._rms[26])
+        self.ret_rms = RunningMeanStdView(self._rms[27], self._rms[28], self._rms[29])
+        self.keep_original = bool(keep_original)
+        self.old_obs = self.old_reward = None
+        self._zero_done = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        self._dummy_reward = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------------------------------------ core
+    def _apply(self, obs, reward, done_u8, terminal_obs, norm_reward):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().cantor_vecnorm_step(
+                self._rms.data_ptr(), self.returns.data_ptr(), self.num_envs, obs.data_ptr(), reward.data_ptr(),
+                _lib.F64 if reward.dtype == torch.float64 else _lib.F32, done_u8.data_ptr(), _lib.ptr(terminal_obs),
+                self.gamma, self.clip_obs, self.clip_reward, self.epsilon, int(self.training), int(self.norm_obs),
+                int(norm_reward), _lib.current_stream_ptr(self.device)), "cantor_vecnorm_step")
+
+    def reset(self, *args, **kwargs):
+        obs = self.venv.reset(*args, **kwargs)
+        if self.keep_original:
+            self.old_obs = obs.clone()
+        self.returns.zero_()
+        self._apply(obs, self._dummy_reward, self._zero_done, None, False)
+        return obs
+
+    def step(self, actions):
+        """``venv.step`` followed by SB3's ``VecNormalize.step_wait``; obs / rewards are normalised in place."""
+        obs, reward, done, infos = self.venv.step(actions)
+        if self.keep_original:
+            self.old_obs, self.old_reward = obs.clone(), reward.clone()
+        term = infos["terminal_observation"] if hasattr(infos, "__getitem__") else None
+        self._apply(obs, reward, done.view(torch.uint8), term, self.norm_reward)
+        return obs, reward, done, infos
+
+    def step_async(self, actions):
+        self._pending = actions
+
+    def step_wait(self):
+        return self.step(self._pending)
+
+    # ------------------------------------------------------------------------------------- SB3 conveniences
+    def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:
+        if not self.norm_obs:
+            return obs
+        x = (obs.double() - self.obs_rms.mean) / torch.sqrt(self.obs_rms.var + self.epsilon)
+        return torch.clamp(x, -self.clip_obs, self.clip_obs).float()
+
+    def normalize_reward(self, reward: torch.Tensor) -> torch.Tensor:
+        if not self.norm_reward:
+            return reward
+        return torch.clamp(reward.double() / torch.sqrt(self.ret_rms.var + self.epsilon), -self.clip_reward, self.clip_reward).to(reward.dtype)
+
+    def get_original_obs(self):
+        if self.old_obs is None:
+            raise RuntimeError("construct VecNormalize(keep_original=True) to keep the unnormalised observations")
+        return self.old_obs
+
+    def get_original_reward(self):
+        if self.old_reward is None:
+            raise RuntimeError("construct VecNormalize(keep_original=True) to keep the unnormalised rewards")
+        return self.old_reward
+
+    def policy_normalisation(self):
+        """(mean, var) float32 tensors for ``pack_mlp(..., obs_mean=, obs_var=)``: the fused rollout applies them itself."""
+        return self.obs_rms.mean.float(), self.obs_rms.var.float()
+
+    def get_attr(self, name, indices=None):
+        return self.venv.get_attr(name, indices)
+
+    def close(self):
+        self.venv.close()
+
+    # --------------------------------------------------------------------------------------- checkpoint / resume
+    def state_dict(self):
+        return {"rms": self._rms[:32].cpu(), "returns": self.returns.cpu(), "clip_obs": self.clip_obs, "clip_reward": self.clip_reward,
+                "gamma": self.gamma, "epsilon": self.epsilon, "norm_obs": self.norm_obs, "norm_reward": self.norm_reward}
+
+    def load_state_dict(self, sd):
+        self._rms[:32].copy_(sd["rms"])
+        if sd["returns"].numel() == self.returns.numel():
+            self.returns.copy_(sd["returns"])
+        for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs", "norm_reward"):
+            setattr(self, k, sd[k])
+
+    def save(self, path):
+        """Like ``VecNormalize.save`` (train_ppo_v2.py:315-317, save_vecnormalize=True): statistics only, not the env."""
+        torch.save(self.state_dict(), path)
+
+    @classmethod
+    def load(cls, path, venv):
+        sd = torch.load(path, weights_only=False)
+        self = cls(venv, norm_obs=sd["norm_obs"], norm_reward=sd["norm_reward"], clip_obs=sd["clip_obs"], clip_reward=sd["clip_reward"],
+                   gamma=sd["gamma"], epsilon=sd["epsilon"])
+        self.load_state_dict(sd)
+        return self
+
+    def export_stats(self):
+        """NumPy dict in the shape the reference ships (quantconnect/extract_model.py:62-79)."""
+        return {"obs_mean": self.obs_rms.mean.cpu().numpy().astype(np.float32), "obs_var": self.obs_rms.var.cpu().numpy().astype(np.float32),
+                "ret_mean": float(self.ret_rms.mean), "ret_var": float(self.ret_rms.var), "clip_obs": self.clip_obs,
+                "clip_reward": self.clip_reward, "gamma": self.gamma, "epsilon": self.epsilon}

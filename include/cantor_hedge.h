@@ -86,6 +86,7 @@ typedef struct cantor_replay_book {
 } cantor_replay_book;
 
 /* Per-env state, struct of arrays, caller-owned.  Packed so one env-step moves 20 B (F32) of state each way. */
+struct cantor_stats_out;
 typedef struct cantor_env_state {
     int32_t* core;         /* [n_envs * 4] 16-byte records {pos, step, path, s0}:
                               pos  = call contracts (low int16) | put contracts (high int16)
@@ -93,6 +94,13 @@ typedef struct cantor_env_state {
                               s0   = float bits of initial_S0_for_episode (after the < 1e-6 -> 1.0 rule, :157) */
     void* cash;            /* [n_envs] float (F32) or double (F64): cash_balance */
     double* pv_prev;       /* [n_envs] F64 only: portfolio_value_t_minus_1; NULL in F32 mode */
+    /* Optional Monitor (SB3 `Monitor` + the evaluation statistics of train_ppo_v2.py:482-530) fused into the step kernel;
+     * all NULL = off (the 137-byte fast path).  episode_acc is state: zeroed by cantor_env_reset and at every episode end. */
+    void* episode_acc;     /* [n_envs * 4] float (F32) / double (F64): running sums over the current episode of
+                              {reward, per_share_step_pnl, |per_share_step_pnl|, transaction_costs_total} */
+    void* episode_return;  /* [n_envs] float / double, written when an env finishes: Monitor's info["episode"]["r"] */
+    int32_t* episode_length;               /* [n_envs], written when an env finishes: info["episode"]["l"] */
+    const struct cantor_stats_out* stats;  /* or NULL: finished episodes are reduced (warp -> block -> atomics) into it */
 } cantor_env_state;
 
 typedef struct cantor_reset_rule {
@@ -221,6 +229,20 @@ int cantor_env_step_many(const cantor_env_params* params, const cantor_replay_bo
                          const cantor_env_state* state, int64_t n_envs, int32_t precision, int32_t n_steps,
                          const float* actions, float* obs, void* reward, uint8_t* done, float* terminal_obs,
                          const cantor_reset_rule* reset_rule, void* stream);
+
+/* ---- VecNormalize on the device -------------------------------------------------------------------------------
+ * Replaces Stable-Baselines3's VecNormalize as the reference uses it around its env (src/agents/train_ppo_v2.py:204-208,
+ * 305-309; statistics consumed at quantconnect/model_wrapper.py:131): RunningMeanStd of observations and of discounted
+ * returns, normalisation + clipping in place.  rms is CANTOR_VECNORM_DOUBLES doubles of device memory (layout: obs mean
+ * [0,13), obs var [13,26), obs count [26], return mean / var / count [27..29], then library scratch); returns is
+ * [n_envs] doubles.  cantor_vecnorm_init sets mean 0, var 1, count 1e-4, returns 0 (it synchronises the stream).
+ * cantor_vecnorm_step = VecNormalize.step_wait() on the arrays a cantor_env_step just wrote: obs [n_envs, 13] and reward
+ * [n_envs] (float / double by reward_precision) are normalised IN PLACE, terminal_obs (or NULL) where done. */
+#define CANTOR_VECNORM_DOUBLES 96
+int cantor_vecnorm_init(double* rms, double* returns, int64_t n_envs, void* stream);
+int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs, float* obs, void* reward, int32_t reward_precision,
+                        const uint8_t* done, float* terminal_obs, double gamma, double clip_obs, double clip_reward,
+                        double epsilon, int32_t training, int32_t norm_obs, int32_t norm_reward, void* stream);
 
 /* ---- episode-fused rollout + statistics ------------------------------------------------------------------
  * Replaces the evaluation loops around the env: evaluate_baseline_policy (src/agents/baselines.py:32-72),

@@ -29,13 +29,31 @@ def test_library_exports_every_declared_symbol():
     assert handle.cantor_abi_version() == 1
 
 
-def test_struct_layouts_match_the_header():
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct, as gcc sees include/cantor_hedge.h (plain C), equal the ctypes mirrors."""
+    import subprocess
     from cantorrl_b200 import _lib
-    assert C.sizeof(_lib.EnvParams) == 8 * 8 + 6 * 4
-    assert C.sizeof(_lib.ReplayBook) == 8 + 8 + 2 * 4
-    assert C.sizeof(_lib.EnvState) == 3 * 8
-    assert C.sizeof(_lib.ResetRule) == 2 * 4 + 8 + 8 + 8 + 8
-    assert C.sizeof(_lib.InfoOut) == 16
+    pairs = {"cantor_env_params": _lib.EnvParams, "cantor_replay_book": _lib.ReplayBook, "cantor_env_state": _lib.EnvState,
+             "cantor_reset_rule": _lib.ResetRule, "cantor_info_out": _lib.InfoOut, "cantor_sim_params": _lib.SimParams,
+             "cantor_policy": _lib.Policy, "cantor_stats_out": _lib.StatsOut, "cantor_rollout_out": _lib.RolloutOut}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cantor_hedge.h"', 'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['printf("VECNORM %d STATS %d MLP %d OBS %d\\n", CANTOR_VECNORM_DOUBLES, CANTOR_STATS_LEN, CANTOR_MLP_FLOATS, CANTOR_OBS_DIM);',
+              'return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.rsplit(" ", 1) for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()[:-1])
+    for cname, ct in pairs.items():
+        assert int(out[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+    consts = subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines()[-1].split()
+    assert [int(consts[1]), int(consts[3]), int(consts[5]), int(consts[7])] == [_lib.VECNORM_DOUBLES, _lib.STATS_LEN, _lib.MLP_FLOATS, _lib.OBS_DIM]
 
 
 def test_argument_validation_needs_no_gpu():

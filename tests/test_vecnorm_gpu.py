@@ -1,0 +1,123 @@
+"""GPU tests of the fused Monitor (episode return / length / statistics in the step kernel) and the device VecNormalize."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bs_oracle, rollout_oracle, sim_oracle
+from oracle.hedge_oracle import EnvParams, OracleVecEnv
+from oracle.vecnorm_oracle import VecNormalizeOracle
+
+pytestmark = pytest.mark.gpu
+KW = dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3, lambda_cost=1e-4)
+
+
+def _data(n_paths=40, T=9, seed=2):
+    S, V = sim_oracle.heston_paths(seed, np.arange(n_paths), T)
+    C, P = bs_oracle.atm_book(S.astype(np.float64), V.astype(np.float64))
+    return S, V, C.astype(np.float32), P.astype(np.float32)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp64"])
+def test_monitor_returns_lengths_and_statistics_match_oracle(prec):
+    from cantorrl_b200 import HedgingVecEnv
+    from cantorrl_b200.stats import EpisodeStats
+    S, V, C, P = _data()
+    n, T, steps = 300, S.shape[1] - 1, 31
+    stats = EpisodeStats("cuda", hist_bins=256, hist_max=4.0)
+    env = HedgingVecEnv(data=dict(paths=S, volatilities=V, call_prices_atm=C, put_prices_atm=P), num_envs=n, precision=prec,
+                        episode_sampler="same_path", monitor=True, stats=stats, **KW)
+    orc = OracleVecEnv(S, V, C, P, EnvParams(**KW), n)
+    idx = np.arange(n) % S.shape[0]
+    env.reset(path_idx=idx)
+    orc.reset(idx)
+    rng = np.random.default_rng(4)
+    ep_r = np.zeros(n)
+    cur = {k: np.zeros((n, T)) for k in ("pps", "cost", "reward")}
+    fin = {k: [] for k in cur}
+    rtol = 1e-6 if prec == "fp64" else 1e-4
+    for g in range(steps):
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        t = orc.step_count.copy()
+        _, r_ref, d_ref, _, info = orc.step_autoreset(a, orc.idx.copy())
+        _, r, d, infos = env.step(a)
+        ep_r += r_ref
+        rows = np.arange(n)
+        cur["pps"][rows, t], cur["cost"][rows, t], cur["reward"][rows, t] = info["per_share_step_pnl"], info["transaction_costs_total"], r_ref
+        assert np.array_equal(d.cpu().numpy(), d_ref)
+        if d_ref.any():
+            ep = infos["episode"]
+            np.testing.assert_allclose(ep["r"].cpu().numpy()[d_ref], ep_r[d_ref], rtol=rtol, atol=1e-6)
+            assert (ep["l"].cpu().numpy()[d_ref] == T).all()
+            one = infos[int(np.nonzero(d_ref)[0][0])]
+            assert set(one["episode"]) == {"r", "l", "t"} and one["episode"]["l"] == T
+            for k in fin:
+                fin[k].append(cur[k][d_ref].copy())
+            ep_r[d_ref] = 0
+    want, _ = rollout_oracle.stats_vector(*(np.concatenate(fin[k]) for k in ("pps", "cost", "reward")), T)
+    sums = stats.sums.cpu().numpy()
+    assert sums[0] == want[0] == n * (steps // T) and sums[11] == n * steps
+    np.testing.assert_allclose(sums[1:11], want[1:], rtol=2e-4, atol=1e-4 * want[0])
+    assert int(stats.hist.sum()) == int(want[0])
+
+
+def test_vecnormalize_matches_oracle_over_many_steps_and_checkpoints():
+    from cantorrl_b200 import HedgingVecEnv
+    from cantorrl_b200.vecnorm import VecNormalize
+    S, V, C, P = _data(n_paths=64, T=7)
+    n, T = 1000, 7
+    env = HedgingVecEnv(data=dict(paths=S, volatilities=V, call_prices_atm=C, put_prices_atm=P), num_envs=n, precision="fp64",
+                        episode_sampler="same_path", **KW)
+    vn = VecNormalize(env, gamma=0.95, clip_obs=5.0, clip_reward=3.0)
+    orc_env = OracleVecEnv(S, V, C, P, EnvParams(**KW), n)
+    orc = VecNormalizeOracle(n, gamma=0.95, clip_obs=5.0, clip_reward=3.0)
+    idx = np.arange(n) % 64
+    obs = vn.reset(path_idx=idx)
+    want = orc.reset(orc_env.reset(idx))
+    np.testing.assert_allclose(obs.cpu().numpy(), want, rtol=1e-5, atol=2e-6)
+    rng = np.random.default_rng(8)
+    for g in range(20):
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        o_ref, r_ref, d_ref, t_ref, _ = orc_env.step_autoreset(a, orc_env.idx.copy())
+        wo, wr, wt = orc.step(o_ref, r_ref, d_ref, t_ref)
+        o, r, d, infos = vn.step(a)
+        np.testing.assert_allclose(o.cpu().numpy(), wo, rtol=1e-5, atol=5e-6)
+        np.testing.assert_allclose(r.cpu().numpy(), wr, rtol=1e-6, atol=1e-9)
+        if d_ref.any():
+            np.testing.assert_allclose(infos["terminal_observation"].cpu().numpy()[d_ref], wt[d_ref], rtol=1e-5, atol=5e-6)
+        np.testing.assert_allclose(vn.returns.cpu().numpy(), orc.returns, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(vn.obs_rms.mean.cpu().numpy(), orc.obs_rms.mean, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(vn.obs_rms.var.cpu().numpy(), orc.obs_rms.var, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(float(vn.ret_rms.var), orc.ret_rms.var, rtol=1e-9)
+    assert abs(vn.obs_rms.count - orc.obs_rms.count) < 1e-6 and abs(vn.ret_rms.count - orc.ret_rms.count) < 1e-6
+    # checkpoint / resume: statistics survive a save / load; evaluation mode stops updating them
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "vecnormalize.pkl")
+        vn.save(f)
+        vn2 = VecNormalize.load(f, env)
+    assert torch.equal(vn2._rms[:30], vn._rms[:30]) and vn2.gamma == 0.95
+    vn2.training = False
+    before = vn2._rms[:30].clone()
+    vn2.step(torch.zeros((n, 2), device="cuda"))
+    assert torch.equal(vn2._rms[:30], before)
+    st = vn.export_stats()
+    assert st["obs_mean"].shape == (13,) and st["obs_var"].dtype == np.float32
+
+
+def test_vecnormalize_fp32_rewards_and_full_size():
+    """2^20 envs, float32 rewards: normalised observations have ~zero mean / unit variance after a few steps."""
+    from cantorrl_b200 import HedgingVecEnv, sim
+    from cantorrl_b200.vecnorm import VecNormalize
+    n = 1 << 20
+    book = sim.generate_paths_and_options(n, n_steps=16, model="heston")
+    vn = VecNormalize(HedgingVecEnv(data=book, num_envs=n, episode_sampler="same_path", **KW))
+    obs = vn.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for _ in range(6):
+        obs, r, d, _ = vn.step(torch.rand((n, 2), device="cuda", generator=g) * 2 - 1)
+    assert bool(torch.isfinite(obs).all()) and float(obs.abs().max()) <= 10.0 and float(r.abs().max()) <= 10.0
+    raw_like = obs[:, [0, 1, 2, 5, 7]]                  # columns with real cross-sectional spread
+    assert float(raw_like.mean(0).abs().max()) < 0.5 and 0.3 < float(raw_like.std(0).mean()) < 3.0
+    assert abs(vn.obs_rms.count - (7 * n + 1e-4)) < 1e-3

@@ -18,7 +18,10 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "launch__registers_per_thread", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps", "lts__t_sector_hit_rate.pct",
         "smsp__inst_executed.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size"]
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_blocks", "sm__maximum_warps_per_active_cycle_pct",
+        "launch__grid_size", "launch__block_size"]
 for w in want:
     for i, h in enumerate(hdr):
         if h == w:
