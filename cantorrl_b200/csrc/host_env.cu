@@ -76,7 +76,7 @@ int alloc_book(cantor_vecenv* e, int32_t n_paths, int32_t T) {
 cantor_replay_book book_of(const cantor_vecenv* e) { return cantor_replay_book{e->book, e->ld, e->n_paths, e->T}; }
 
 cantor_env_state state_of(const cantor_vecenv* e, int64_t first) {
-    cantor_env_state st;
+    cantor_env_state st = {};                      // Monitor fields stay NULL on the host-buffer face
     st.core = e->core + first * 4;
     st.cash = (char*)e->cash + first * reward_bytes(e);
     st.pv_prev = e->pv_prev ? e->pv_prev + first : nullptr;
