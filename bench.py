@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--e2e-steps", type=int, default=2, help="episode sweeps timed through the host-buffer API")
     ap.add_argument("--rollout-steps", type=int, default=3, help="episode sweeps of the on-the-fly rollout kernel (extra)")
+    ap.add_argument("--mlp-rollout-steps", type=int, default=1000, help="steps of the MLP-policy rollout (configs[4] shape; 0 = skip)")
+    ap.add_argument("--book-strikes", type=int, default=8, help="strikes of the multi-strike book extra (configs[2] shape; 0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -335,11 +337,51 @@ def main():
         barrier()
         roll = (r0.elapsed_time(r1), rstats.result())
 
+    # ---- configs[4] shape: on-policy rollout, MLP actor 13-64-64-2 on the tensor cores fused with the env step ------
+    # 2^19 envs per GPU x 1000 steps (4 M envs on 8 GPUs), GBM on the fly, bf16 tcgen05.mma actor, statistics all-reduced.
+    mlp_roll = None
+    if args.mlp_rollout_steps > 0:
+        from cantorrl_b200.rollout import HedgingRollout, pack_mlp
+        n5 = min(n, 1 << 19)
+        gw = np.random.default_rng(5)
+        wts = pack_mlp(gw.normal(0, .5, (64, 13)), gw.normal(0, .1, 64), gw.normal(0, .2, (64, 64)), gw.normal(0, .1, 64),
+                       gw.normal(0, .3, (2, 64)), gw.normal(0, .1, 2), gw.normal(0, .2, 13), gw.uniform(.05, 2, 13), device=dev)
+        ro5 = HedgingRollout(simulate=dict(model="gbm", seed=42, s0=S0, v0=XI, n_steps=T), num_envs=n5, device=dev,
+                             env_offset=rank * n5, total_envs=world * n5, **ENV_KW)
+        st5 = ro5.new_stats()
+        ro5.run(args.mlp_rollout_steps, "mlp_bf16", mlp=wts, stats=st5)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st5.zero_()
+        m0.record(stream)
+        ro5.run(args.mlp_rollout_steps, "mlp_bf16", mlp=wts, stats=st5)
+        st5.all_reduce()
+        m1.record(stream)
+        barrier()
+        assert float(st5.sums[15]) == 0.0, "a tcgen05 MMA timed out"
+        mlp_roll = (m0.elapsed_time(m1), n5, st5.result())
+
+    # ---- configs[2] shape: Heston paths + multi-strike float32 Black-Scholes book (8 strikes, maturities to episode end) ---
+    book_ms = None
+    if args.book_strikes > 0 and rank == 0:
+        from cantorrl_b200 import sim as _sim
+        hb = _sim.generate_paths_and_options(n, R, DT, 42, n_steps=T, model="heston", reprice=False, device=dev)
+        mult = np.linspace(0.9, 1.1, args.book_strikes).astype(np.float32)
+        _sim.reprice_book(hb, mult, sigma="book")
+        torch.cuda.synchronize(dev)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        out_book = _sim.reprice_book(hb, mult, sigma="book")
+        b1.record(stream)
+        torch.cuda.synchronize(dev)
+        book_ms = b0.elapsed_time(b1)
+        del out_book, hb
+
     # ---- reduce over ranks ------------------------------------------------------------------------------------
-    tt = torch.tensor([ms, e2e_s, roll[0] if roll else 0.0], dtype=torch.float64, device=dev)
+    tt = torch.tensor([ms, e2e_s, roll[0] if roll else 0.0, mlp_roll[0] if mlp_roll else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, e2e_s, roll_ms = float(tt[0]), float(tt[1]), float(tt[2])
+    ms, e2e_s, roll_ms, mlp_ms = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
     if rank == 0:
         env_steps = float(n) * world * T * K
         value = env_steps / (ms * 1e-3)
@@ -384,6 +426,21 @@ def main():
                        "statistics buffers (NCCL) once per sweep", sweeps=args.rollout_steps, ms_per_sweep=roll_ms / args.rollout_steps,
                 env_steps_per_s=float(n) * world * T * args.rollout_steps / (roll_ms * 1e-3),
                 stats={k: rs[k] for k in ("n_episodes", "mean_abs_pnl", "std_abs_pnl", "mean_cost", "mean_reward", "cvar95_abs_pnl")})
+        if mlp_roll is not None:
+            line["extra"]["rollout_mlp_policy"] = dict(
+                kernel="rollout_kernel<GBM on the fly, MLP 13-64-64-2 actor as bf16 tcgen05.mma (TMEM accumulators), env step, "
+                       "episode statistics> + NCCL all-reduce of the statistics", envs_per_gpu=mlp_roll[1],
+                steps=args.mlp_rollout_steps, ms=mlp_ms,
+                env_steps_per_s=float(mlp_roll[1]) * world * args.mlp_rollout_steps / (mlp_ms * 1e-3),
+                actor_tflops=float(mlp_roll[1]) * world * args.mlp_rollout_steps * 2 * (16 * 64 + 80 * 64 + 80 * 16) / (mlp_ms * 1e-3) / 1e12,
+                n_episodes=mlp_roll[2]["n_episodes"])
+        if book_ms is not None:
+            cells = float(n) * (T + 1)
+            line["extra"]["multi_strike_book"] = dict(
+                kernel="book_f32_kernel (Heston book variance, %d strikes, price only)" % args.book_strikes, ms=book_ms,
+                reprices_per_s=cells * args.book_strikes / (book_ms * 1e-3),
+                algorithmic_gbs=cells * (16 + 8 * args.book_strikes) / (book_ms * 1e-3) / 1e9,
+                mufu_per_s=cells * (5 + 3 * args.book_strikes) / (book_ms * 1e-3))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)

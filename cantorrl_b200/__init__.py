@@ -6,7 +6,8 @@ in hand-written CUDA kernels reached through the C ABI of ``include/cantor_hedge
 fallback and importing the env without the built library raises.
 """
 from ._lib import CantorError, build, lib  # noqa: F401
-from .data import ReplayData  # noqa: F401
+from .data import ReplayData, load_schema_b, save_schema_b  # noqa: F401
 from .env import Box, HedgingEnv, HedgingVecEnv, VecInfo  # noqa: F401
 
-__all__ = ["CantorError", "build", "lib", "ReplayData", "HedgingVecEnv", "HedgingEnv", "VecInfo", "Box"]
+__all__ = ["CantorError", "build", "lib", "ReplayData", "HedgingVecEnv", "HedgingEnv", "VecInfo", "Box", "load_schema_b",
+           "save_schema_b"]

@@ -137,3 +137,69 @@ class ReplayData:
         """Write the reference's env-schema file (float64 arrays like rbergomi_sim.py:528)."""
         arrs = {k: v.cpu().numpy() for k, v in self.to_path_major(torch.float64).items()}
         (np.savez_compressed if compressed else np.savez)(path, **arrs)
+
+    # -- bare price paths (data/paths.npy) -> env schema ---------------------------------------------------------
+    @classmethod
+    def from_paths(cls, paths, variances="realised", r=0.04, tenor=30 / 252, device="cuda") -> "ReplayData":
+        """Env-schema book from a bare ``(n, T+1)`` price array such as the reference's ``data/paths.npy``.
+
+        The reference ships price paths and a schema-B option file, but no env-schema file (SURVEY.md section 8c);
+        this builds one on the GPU: ``volatilities`` = per-step VARIANCE -- ``"realised"``: the square of the reference's
+        realised annualised volatility of the path prefix (``option_price_assignment.py:23-31``; columns 0 and 1, which
+        are 0 / NaN there, take column 2's value), or a constant (e.g. xi = 0.02903 from ``estimate_base_params``) --
+        and ``call_prices_atm / put_prices_atm`` = closed-form ATM Black-Scholes (K = round(S_t), tenor 30/252) in the
+        kernel that K1 uses.
+        """
+        from . import sim                                    # local import: sim imports this module
+        dev = torch.device(device)
+        p = torch.as_tensor(np.asarray(paths, np.float64) if not isinstance(paths, torch.Tensor) else paths).to(dev, torch.float64)
+        if p.dim() != 2 or p.shape[1] < 3:
+            raise ValueError("Data shapes are inconsistent.")
+        n, T = int(p.shape[0]), int(p.shape[1]) - 1
+        if isinstance(variances, str):
+            if variances != "realised":
+                raise ValueError("variances must be 'realised', a number or an array")
+            vol = sim.calculate_annualized_vol_matrix(p, device=dev).clone()
+            vol[:, 0] = vol[:, 2]
+            vol[:, 1] = vol[:, 2]
+            v = vol * vol
+        elif np.isscalar(variances):
+            v = torch.full_like(p, float(variances))
+        else:
+            v = torch.as_tensor(np.asarray(variances, np.float64)).to(dev)
+            if v.shape != p.shape:
+                raise ValueError("Data shapes are inconsistent.")
+        zeros = torch.zeros((n, T), dtype=torch.float64, device=dev)
+        book = cls.from_arrays(p, v, zeros, zeros, device=dev)
+        return sim.reprice_atm(book, r=r, tenor=tenor)
+
+    @classmethod
+    def from_paths_npy(cls, path, **kw) -> "ReplayData":
+        """``np.load`` of a ``paths.npy``-style file -> ``from_paths``; load failures are FileNotFoundError like the env's."""
+        try:
+            arr = np.load(path)
+        except Exception as e:
+            raise FileNotFoundError(f"Could not load or parse data from {path}. Error: {e}")
+        return cls.from_paths(arr, **kw)
+
+
+SCHEMA_B_KEYS = ("calls", "puts")                                                  # option_price_assignment.py:51
+
+
+def save_schema_b(path, calls, puts, compressed=False):
+    """``np.savez(OUTPUT_FILE, calls=..., puts=...)`` (option_price_assignment.py:51): path-major ``(n, T+1)`` float64."""
+    c = calls.detach().cpu().numpy() if isinstance(calls, torch.Tensor) else np.asarray(calls)
+    q = puts.detach().cpu().numpy() if isinstance(puts, torch.Tensor) else np.asarray(puts)
+    if c.shape != q.shape or c.ndim not in (2, 3):
+        raise ValueError("Data shapes are inconsistent.")
+    (np.savez_compressed if compressed else np.savez)(path, calls=c.astype(np.float64), puts=q.astype(np.float64))
+
+
+def load_schema_b(path, device="cuda"):
+    """The reference's ``data/paths_options.npz`` -> ``(calls, puts)`` device tensors, float64, path-major."""
+    try:
+        with np.load(path) as z:
+            c, q = z["calls"], z["puts"]
+    except Exception as e:
+        raise FileNotFoundError(f"Could not load or parse data from {path}. Error: {e}")
+    return torch.as_tensor(c).to(device), torch.as_tensor(q).to(device)

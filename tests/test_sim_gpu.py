@@ -146,3 +146,40 @@ def test_formats_roundtrip_and_npz_drop_in():
         env = HedgingVecEnv(f, num_envs=8, episode_sampler="same_path")
     assert env.episode_length == 17 and env.num_episodes == 300
     assert torch.equal(env.data.tensor[:, :300], book.tensor[:, :300])
+
+
+def test_env_schema_from_bare_paths_and_schema_b_files():
+    """data/paths.npy-style input -> env-schema book on the GPU, and the schema-B file round trip."""
+    from cantorrl_b200 import HedgingVecEnv, ReplayData, load_schema_b, save_schema_b, sim
+    z = np.load(os.path.join(GOLDEN, "schema_b_golden.npz"))
+    paths = z["paths"][:20]
+    book = ReplayData.from_paths(paths)
+    pm = {k: v.cpu().numpy() for k, v in book.to_path_major(torch.float64).items()}
+    sig = bs_oracle.realised_vol_matrix(paths)
+    sig[:, 0] = sig[:, 2]
+    sig[:, 1] = sig[:, 2]
+    np.testing.assert_allclose(pm["paths"], paths.astype(np.float32), rtol=0)
+    np.testing.assert_allclose(pm["volatilities"], (sig ** 2).astype(np.float32), rtol=1e-6)
+    C, P = bs_oracle.atm_book(pm["paths"], pm["volatilities"])
+    np.testing.assert_allclose(pm["call_prices_atm"], C, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(pm["put_prices_atm"], P, rtol=1e-4, atol=1e-4)
+    const = ReplayData.from_paths(paths, variances=0.02903)
+    assert bool((const.v[:, :20] == np.float32(0.02903)).all())
+    env = HedgingVecEnv(data=book, num_envs=20, episode_sampler="same_path")
+    assert env.episode_length == 252 and bool(torch.isfinite(env.reset()).all())
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "paths.npy")
+        np.save(f, paths)
+        again = ReplayData.from_paths_npy(f)
+        assert torch.equal(again.tensor, book.tensor)
+        with pytest.raises(FileNotFoundError):
+            ReplayData.from_paths_npy(os.path.join(d, "missing.npy"))
+        calls, puts = sim.process_price_paths(paths)
+        g = os.path.join(d, "paths_options.npz")
+        save_schema_b(g, calls, puts)
+        with np.load(g) as w:
+            assert sorted(w.files) == ["calls", "puts"] and w["calls"].dtype == np.float64 and w["calls"].shape == (20, 253)
+        c2, p2 = load_schema_b(g)
+        assert torch.equal(c2.nan_to_num(-1), calls.nan_to_num(-1)) and torch.equal(p2.nan_to_num(-1), puts.nan_to_num(-1))
+        with pytest.raises(FileNotFoundError):          # the reference env cannot load a schema-B file either (missing keys)
+            HedgingVecEnv(g, num_envs=4)
