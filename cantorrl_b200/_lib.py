@@ -69,6 +69,13 @@ class SimParams(C.Structure):
                 ("path_offset", C.c_int64)]
 
 
+class RbergomiParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("s0", "xi", "H", "eta", "rho", "perturb_s0", "perturb_xi", "perturb_H", "perturb_eta",
+                                          "perturb_rho", "min_xi_factor", "min_eta_factor", "clip_H_min", "clip_H_max",
+                                          "clip_rho_min", "clip_rho_max", "r", "dt", "tenor")] + \
+               [("n_mc", C.c_int32), ("shared_draws", C.c_int32), ("seed", C.c_uint64), ("path_offset", C.c_int64)]
+
+
 POLICY_NO_HEDGE, POLICY_RANDOM, POLICY_DELTA_BASELINES, POLICY_DELTA_BENCHMARK, POLICY_MLP, POLICY_ACTIONS = range(6)
 MLP_FLOATS = 5212
 STATS_LEN = 16
@@ -108,6 +115,12 @@ SIGNATURES = {
     "cantor_reprice_atm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p]),
     "cantor_euler_from_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_int32, C.c_int64, C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "cantor_rbergomi_paths": (C.c_int, [C.POINTER(RbergomiParams), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_rbergomi_price_atm": (C.c_int, [C.POINTER(RbergomiParams), C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_int32, C.c_int32, C.c_void_p]),
+    "cantor_rbergomi_price_from_increments": (C.c_int, [C.POINTER(RbergomiParams)] + [C.c_void_p] * 8 +
+                                              [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cantor_bs_price": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_schema_b_book": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_double, C.c_void_p, C.c_int32,

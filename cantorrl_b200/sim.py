@@ -168,3 +168,117 @@ def bs_delta_hedge(paths, r=R, dt=DT, device="cuda"):
         _lib.check(_lib.lib().cantor_bs_delta_hedge(tm.data_ptr(), n, T1 - 1, n, float(r), float(dt), pnl.data_ptr(),
                                                     _stream(dev)), "cantor_bs_delta_hedge")
     return pnl.T
+
+
+# ---------------------------------------------------------------------------------------------- rough Bergomi
+# module constants of the reference simulator (rbergomi_sim.py:13-40)
+N_PATHS_OPTION_MC = 5000
+H_DEFAULT, ETA_DEFAULT = 0.1, 1.0
+RBERGOMI_DEFAULTS = dict(s0=S0_DEFAULT, xi=XI_DEFAULT, H=H_DEFAULT, eta=ETA_DEFAULT, rho=RHO_DEFAULT,
+                         perturb_s0=0.01, perturb_xi=0.20, perturb_H=0.20, perturb_eta=0.20, perturb_rho=0.10,
+                         min_xi_factor=0.5, min_eta_factor=0.5, clip_H_min=0.01, clip_H_max=0.49, clip_rho_min=-0.99,
+                         clip_rho_max=-0.01)
+
+
+def _rb_params(base_params, r, dt, tenor, n_mc, shared_draws, seed, path_offset):
+    kw = dict(RBERGOMI_DEFAULTS)
+    if base_params is not None:
+        if isinstance(base_params, dict):
+            unknown = set(base_params) - set(kw)
+            if unknown:
+                raise TypeError(f"unknown rBergomi parameters: {sorted(unknown)}")
+            kw.update(base_params)
+        else:                                         # (S0, xi, H, eta, rho) as estimate_base_params returns them (:171-193)
+            kw.update(dict(zip(("s0", "xi", "H", "eta", "rho"), (float(x) for x in base_params))))
+    return _lib.RbergomiParams(*(float(kw[n]) for n, _ in _lib.RbergomiParams._fields_[:16]), float(r), float(dt), float(tenor),
+                               int(n_mc), int(bool(shared_draws)), int(seed) & (2 ** 64 - 1), int(path_offset))
+
+
+class RbergomiBook:
+    """What ``generate_rbergomi_paths_and_options`` returns: the env-schema book plus the per-path parameters."""
+
+    def __init__(self, book: ReplayData, path_params: torch.Tensor, params: "_lib.RbergomiParams"):
+        self.book, self.path_params, self._params = book, path_params, params
+
+    S0 = property(lambda self: self.path_params[0])
+    xi = property(lambda self: self.path_params[1])
+    H = property(lambda self: self.path_params[2])
+    eta = property(lambda self: self.path_params[3])
+    rho = property(lambda self: self.path_params[4])
+
+    def price_days(self, t_begin: int, t_end: int):
+        """Nested-MC ATM call / put prices of days ``[t_begin, t_end)`` into the book (resumable: any range, any order)."""
+        b = self.book
+        with torch.cuda.device(b.device):
+            _lib.check(_lib.lib().cantor_rbergomi_price_atm(C_byref(self._params), b.tensor.data_ptr(), b.ld, b.n_paths,
+                                                            b.episode_length, self.path_params.data_ptr(), int(t_begin), int(t_end),
+                                                            _stream(b.device)), "cantor_rbergomi_price_atm")
+        return self
+
+
+def C_byref(x):
+    import ctypes
+    return ctypes.byref(x)
+
+
+def generate_rbergomi_paths_and_options(num_paths, r=R, dt=DT, seed=SEED, *, base_params=None, n_steps=N_STEPS,
+                                        n_mc=N_PATHS_OPTION_MC, tenor=T_OPTION_TENOR, price=True, days_per_launch=32,
+                                        shared_draws=False, path_offset=0, device="cuda", exported=None) -> RbergomiBook:
+    """The reference's data generator (``generate_paths_and_options``, rbergomi_sim.py:309-499) on the GPU.
+
+    ``base_params`` = ``(S0, xi, H, eta, rho)`` from ``estimate_base_params`` (or a dict also overriding the perturbation
+    constants); every path gets its own perturbed parameters.  Returns the packed env-schema book
+    (``.book.save_npz(path)`` writes the reference's ``paths_rbergomi_options_100k.npz`` schema) with the ATM call / put
+    columns priced by ``n_mc`` inner rough-Bergomi paths per (path, day), calls and puts on independent draws like the
+    reference unless ``shared_draws``.  ``exported=dict(params=[5, n], dW1=[n, M], dW2=[n, M])`` replays exported draws.
+    """
+    dev = torch.device(device)
+    p = _rb_params(base_params, r, dt, tenor, n_mc, shared_draws, seed, path_offset)
+    book = ReplayData.empty(num_paths, n_steps, dev)
+    book.tensor.zero_()
+    pp = torch.empty((5, num_paths), dtype=torch.float64, device=dev)
+    ex = exported or {}
+    prm = _as_f64(ex["params"], dev) if "params" in ex else None
+    d1 = _as_f64(ex["dW1"], dev) if "dW1" in ex else None
+    d2 = _as_f64(ex["dW2"], dev) if "dW2" in ex else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cantor_rbergomi_paths(C_byref(p), num_paths, n_steps, _lib.ptr(prm), _lib.ptr(d1), _lib.ptr(d2),
+                                                    int(d1.shape[1]) if d1 is not None else 0, book.tensor.data_ptr(), book.ld,
+                                                    pp.data_ptr(), None, None, _stream(dev)), "cantor_rbergomi_paths")
+    out = RbergomiBook(book, pp, p)
+    if price:
+        for t0 in range(0, n_steps, max(1, int(days_per_launch))):
+            out.price_days(t0, min(n_steps, t0 + int(days_per_launch)))
+    return out
+
+
+def rbergomi_outer_paths(num_paths, n_steps, params, dW1, dW2, r=R, dt=DT, device="cuda"):
+    """Float64 paths and variances ``(n, n_steps + 1)`` of the outer generator on exported parameters / increments."""
+    dev = torch.device(device)
+    p = _rb_params(None, r, dt, T_OPTION_TENOR, 1, False, 0, 0)
+    prm, d1, d2 = _as_f64(params, dev), _as_f64(dW1, dev), _as_f64(dW2, dev)
+    paths = torch.empty((num_paths, n_steps + 1), dtype=torch.float64, device=dev)
+    v = torch.empty_like(paths)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cantor_rbergomi_paths(C_byref(p), num_paths, n_steps, prm.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+                                                    int(d1.shape[1]), None, 0, None, paths.data_ptr(), v.data_ptr(), _stream(dev)),
+                   "cantor_rbergomi_paths")
+    return paths, v
+
+
+def price_rbergomi_option(S0, K, T_opt, r, xi, H, eta, rho, option_type, dW1, dW2, dt=DT, device="cuda"):
+    """``price_rbergomi_option_gpu`` (rbergomi_sim.py:246-306) on exported increments ``dW1, dW2 [batch, n_mc, 32]``."""
+    if option_type not in ("call", "put"):
+        raise ValueError("option_type must be 'call' or 'put'")
+    dev = torch.device(device)
+    p = _rb_params(None, r, dt, T_opt, 1, False, 0, 0)
+    arrs = [_as_f64(a, dev) for a in (S0, K, xi, H, eta, rho)]
+    d1, d2 = _as_f64(dW1, dev), _as_f64(dW2, dev)
+    B, n_mc, M = d1.shape
+    out = torch.empty(B, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().cantor_rbergomi_price_from_increments(C_byref(p), *(a.data_ptr() for a in arrs), d1.data_ptr(),
+                                                                    d2.data_ptr(), B, n_mc, M, int(option_type == "put"),
+                                                                    out.data_ptr(), _stream(dev)),
+                   "cantor_rbergomi_price_from_increments")
+    return out

@@ -173,6 +173,40 @@ int cantor_euler_from_normals(const double* S0, const double* v, const double* d
                               const double* rho, int32_t n_paths, int32_t episode_length, int64_t ld,
                               double r, double dt, double* paths, void* stream);
 
+/* ---- rough-Bergomi generator + nested-Monte-Carlo ATM pricer (the reference's own data generator) -----------------
+ * Replaces generate_paths_and_options of src/sim/rbergomi_sim.py (:309-499) and price_rbergomi_option_gpu (:246-306):
+ * per-path perturbed parameters (:363-367, clips :35-40), Brownian increments, the "fractional" variance driver
+ * (:206-243; evaluated as the circular FIR filter it is equal to, no FFT), the log-Euler step (:454-464), and for every
+ * (path, day) the ATM call and put priced by n_mc inner paths x 30 steps from (S_t, K = round(S_t), xi := v_t, H, eta, rho).
+ * Defaults in the comments are the reference's module constants. */
+typedef struct cantor_rbergomi_params {
+    double s0, xi, H, eta, rho;              /* base parameters: estimate_base_params (:171-193); defaults 100, .04, .1, 1, -.7 (:23-27) */
+    double perturb_s0, perturb_xi, perturb_H, perturb_eta, perturb_rho;      /* .01 .20 .20 .20 .10 (:29-33) */
+    double min_xi_factor, min_eta_factor;    /* .5 .5 (:35-36) */
+    double clip_H_min, clip_H_max, clip_rho_min, clip_rho_max;               /* .01 .49 -.99 -.01 (:37-40) */
+    double r, dt, tenor;                     /* .04, 1/252, 30/252 (:13-14, :19) */
+    int32_t n_mc;                            /* 5000 (:20) */
+    int32_t shared_draws;                    /* 0 = call and put on independent draws like the reference (:437-446); 1 = the same draws */
+    uint64_t seed;                           /* 42 (:17) */
+    int64_t path_offset;                     /* global index of path 0 of this shard */
+} cantor_rbergomi_params;
+/* Outer generator.  Writes S, v (C = P = 0) of the packed book svcp (or NULL), the per-path parameters path_params
+ * [5, n_paths] = {S0, xi, H, eta, rho} (float64; needed by the pricer), and optionally float64 paths64 / v64
+ * [n_paths, T + 1].  For parity runs the draws can be supplied: params_in [5, n_paths] and / or the unscaled increments
+ * dW1_in, dW2_in [n_paths, M_in] with M_in = next_power_of_two(T + 1) (:200-204, :380-382). */
+int cantor_rbergomi_paths(const cantor_rbergomi_params* params, int32_t n_paths, int32_t episode_length,
+                          const double* params_in, const double* dW1_in, const double* dW2_in, int32_t M_in, float* svcp,
+                          int64_t ld, double* path_params, double* paths64, double* v64, void* stream);
+/* Nested-MC ATM prices of days [t_begin, t_end) (t_end <= T) into the C, P columns of the packed book (row T repeats
+ * row T - 1).  Any day range can be run at any time and on any shard: the draws depend on (seed, global path, day) only. */
+int cantor_rbergomi_price_atm(const cantor_rbergomi_params* params, float* svcp, int64_t ld, int32_t n_paths,
+                              int32_t episode_length, const double* path_params, int32_t t_begin, int32_t t_end, void* stream);
+/* The same inner-path arithmetic on exported increments dW1, dW2 [batch, n_mc, 32] (parity with the reference's draws). */
+int cantor_rbergomi_price_from_increments(const cantor_rbergomi_params* params, const double* S0, const double* K,
+                                          const double* xi, const double* H, const double* eta, const double* rho,
+                                          const double* dW1, const double* dW2, int32_t batch, int32_t n_mc, int32_t M,
+                                          int32_t is_put, double* price, void* stream);
+
 /* ---- K2: Black-Scholes repricing in float64 (src/sim/option_price_assignment.py, src/tools/bs_delta.py) ---
  * black_scholes_vectorized (:10-21), elementwise over n outputs; stride 0 broadcasts a scalar input. */
 int cantor_bs_price(const double* S, const double* K, const double* T, const double* sigma, int64_t n,

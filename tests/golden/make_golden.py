@@ -242,6 +242,52 @@ def make_policy_golden():
     print(f"policy_golden: {n} observations through the unmodified policies")
 
 
+def make_rbergomi_golden():
+    """Run the unmodified rBergomi building blocks (rbergomi_sim.py:206-306, 357-406, 454-464) on the CPU under the cupy
+    stand-in and export inputs, draws and outputs: the nested-MC pricer on a small batch, and the full generator."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_cupy_stub"))
+    rb = _load("ref_rbergomi2", f"{REF}/src/sim/rbergomi_sim.py")
+    import cupy as cp
+    rng = np.random.default_rng(77)
+    B, n_mc = 6, 96
+    S0 = rng.uniform(80, 520, B)
+    K = np.round(S0)
+    xi = rng.uniform(0.01, 0.09, B)
+    H = np.array([0.01, 0.07, 0.1, 0.25, 0.4656, 0.49])
+    eta = rng.uniform(0.5, 2.2, B)
+    rho = rng.uniform(-0.95, -0.05, B)
+    out = dict(S0=S0, K=K, xi=xi, H=H, eta=eta, rho=rho, r=rb.R, dt=rb.DT, tenor=rb.T_OPTION_TENOR)
+    for kind in ("call", "put"):
+        cp.random.seed(1000 + len(kind))
+        price = rb.price_rbergomi_option_gpu(S0, K, rb.T_OPTION_TENOR, rb.R, xi, H, eta, rho, kind, n_mc, rb.DT)
+        cp.random.seed(1000 + len(kind))                       # the same draws, in the order the function takes them (:271-272)
+        M = rb.next_power_of_two(int(rb.T_OPTION_TENOR / rb.DT) + 1)
+        Z = cp.random.normal(size=(B, n_mc, M)) + 1j * cp.random.normal(size=(B, n_mc, M))
+        out[f"Z_{kind}"], out[f"price_{kind}"] = Z, np.asarray(price)
+    # the generator itself, constants shrunk (12 days, 40 inner paths): per-path parameters, main increments, variance, paths
+    rb.N_STEPS, rb.N_PATHS_OPTION_MC, rb.OPTION_PRICING_MINI_BATCH_SIZE = 12, 40, 16
+    rb.tqdm = lambda it, **kw: _NoBar(it)
+    hist = np.loadtxt(f"{REF}/data/historical_prices.csv", dtype=np.float64, delimiter=",")
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.chdir(d)
+        try:
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                paths, v, calls, puts = rb.generate_paths_and_options(hist, 24, rb.R, rb.DT, 42)
+            chk = dict(np.load(rb.CHECKPOINT_FILE, allow_pickle=True))
+        finally:
+            os.chdir(cwd)
+    out.update(gen_paths=np.asarray(paths), gen_v=np.asarray(v), gen_S0=chk["S0_arr_gpu"], gen_xi=chk["xi_arr_gpu"], gen_H=chk["H_arr_gpu"],
+               gen_eta=chk["eta_arr_gpu"], gen_rho=chk["rho_arr_gpu"], gen_dW1=chk["dW1_unscaled_main_gpu"],
+               gen_dW2=chk["dW2_unscaled_main_gpu"], gen_Z=chk["Z_main_gpu"],
+               gen_base=np.array([chk["S0_base"], chk["xi_base"], chk["H_base"], chk["eta_base"], chk["rho_base"]], np.float64),
+               gen_n_steps=12)
+    np.savez_compressed(os.path.join(HERE, "rbergomi_golden.npz"), **out)
+    print(f"rbergomi_golden: pricer batch of {B} x {n_mc} inner paths (call, put) + generator 24 paths x 12 days")
+
+
 class _NoBar:
     def __init__(self, it):
         self.it = it
@@ -257,6 +303,9 @@ class _NoBar:
 
 
 if __name__ == "__main__":
+    if "--rbergomi-only" in sys.argv:
+        make_rbergomi_golden()
+        sys.exit(0)
     if "--policy-only" in sys.argv:
         make_policy_golden()
         sys.exit(0)
@@ -264,3 +313,4 @@ if __name__ == "__main__":
         main()
         make_policy_golden()
     make_outer_euler_golden()
+    make_rbergomi_golden()
