@@ -73,7 +73,8 @@ class RbergomiParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("s0", "xi", "H", "eta", "rho", "perturb_s0", "perturb_xi", "perturb_H", "perturb_eta",
                                           "perturb_rho", "min_xi_factor", "min_eta_factor", "clip_H_min", "clip_H_max",
                                           "clip_rho_min", "clip_rho_max", "r", "dt", "tenor")] + \
-               [("n_mc", C.c_int32), ("shared_draws", C.c_int32), ("seed", C.c_uint64), ("path_offset", C.c_int64)]
+               [("n_mc", C.c_int32), ("shared_draws", C.c_int32), ("tensor_cores", C.c_int32), ("reserved", C.c_int32),
+                ("seed", C.c_uint64), ("path_offset", C.c_int64)]
 
 
 POLICY_NO_HEDGE, POLICY_RANDOM, POLICY_DELTA_BASELINES, POLICY_DELTA_BENCHMARK, POLICY_MLP, POLICY_ACTIONS = range(6)

@@ -155,23 +155,6 @@ struct InnerConsts {
     float log2_xi_plus_dk[kInnerSteps];   // log2(xi) + dk * log2(e): v_k = exp2(X_k log2e + this)
     float rho, rho_c, r_dt, half_dt, sqrt_dt, log_s0;
 };
-// `L` = the filter taps in REGISTERS (copied once per thread); `c` may live in shared memory (one read per step).
-__device__ __forceinline__ float inner_log_terminal(const float (&w1)[kInnerM], const float (&w2)[kInnerSteps],
-                                                    const float (&L)[kInnerSteps + 1], const InnerConsts& c) {
-    float logS = c.log_s0;
-#pragma unroll
-    for (int kk = 0; kk < kInnerSteps; ++kk) {
-        float acc = 0.f;
-#pragma unroll
-        for (int n = 1; n <= kInnerSteps; ++n) acc = fmaf(L[n], w1[(kk - n) & (kInnerM - 1)], acc);
-        const float v = mufu_ex2(fmaf(acc, kLog2ef, c.log2_xi_plus_dk[kk]));                    // xi exp(X_k - eta^2 lambda_k)
-        const float dW = fmaf(c.rho, w1[kk], c.rho_c * w2[kk]);
-        logS += fmaf(mufu_sqrt_rb(v) * c.sqrt_dt, dW, fmaf(-c.half_dt, v, c.r_dt));             // (r - v/2) dt + sqrt(v) sqrt(dt) dW
-        logS = fmaxf(logS, -18.420680743952367f);                                               // ln(1e-8)
-    }
-    return logS;
-}
-
 __device__ __forceinline__ void fill_inner_consts(InnerConsts& c, float S, float xi, double H, double eta, double rho,
                                                   const RbConsts& k) {
     const double cc = sqrt(2.0 * H) * eta / sqrt((double)kInnerM);
@@ -205,78 +188,253 @@ __device__ __forceinline__ float block_sum(float x, float* smem /* [NW] */) {
     return t;
 }
 
-// grid = (n_paths, n_days, 2): CTA (p, d, kind) prices the ATM call (kind 0) or put (1) of path p at day t_begin + d.
-__global__ void __launch_bounds__(kPriceThreads)
-rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, int n_paths, int T, int t_begin,
-                      const double* __restrict__ path_params) {
-    __shared__ InnerConsts sc;
-    __shared__ float red[kPriceThreads / 32];
-    const int p = blockIdx.x, t = t_begin + blockIdx.y, kind = blockIdx.z;
-    const float4 st = rec[(long long)t * ld + p];
-    const float S = st.x, K = rintf(S);                                                         // :418
-    if (threadIdx.x == 0)
-        fill_inner_consts(sc, S, st.y, path_params[2LL * n_paths + p], path_params[3LL * n_paths + p],
-                          path_params[4LL * n_paths + p], k);                                   // xi := v_t (:439)
-    __syncthreads();
-    float L[kInnerSteps + 1];
+// ---- tensor-core FIR ------------------------------------------------------------------------------------------------
+// X[128 inner paths x 32] = W1[128 x 32] * Lambda^T, Lambda[k][j] = L[(k - j) & 31] (the circulant of the filter taps):
+// GEMM-shaped, so it runs on tcgen05 (kind::tf32, M = 128 = the CTA's inner paths, N = 32, K = 32 in four K = 8 steps,
+// float32 accumulators in 32 TMEM columns).  TF32 keeps 10 mantissa bits, so both operands are split hi + lo
+// (hi = the upper 19 bits, lo = x - hi, exact) and X = A_hi B_hi + A_hi B_lo + A_lo B_hi: float32-level accuracy from
+// 12 small MMAs.  Operand tiles use the canonical K-major no-swizzle core-matrix layout (8 rows x 16 bytes).
+namespace rbtc {
+constexpr int kLbo = 128, kSbo = (kInnerM / 4) * 128;              // fp32: 4 elements per 16-byte core-matrix row; K = 32 -> 8 chunks
+constexpr int kABytes = kPriceThreads * kInnerM * 4;              // 16 KB per A tile
+constexpr int kBBytes = kInnerM * kInnerM * 4;                    // 4 KB per B tile
+constexpr int kSmemBytes = 2 * kABytes + 2 * kBBytes + 16;
+constexpr int kTmemCols = 32;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kLbo >> 4) << 16) | ((uint64_t)(kSbo >> 4) << 32) | (1ull << 46);
+}
+// kind::tf32: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), K-major, M = 128, N = 32
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kInnerM >> 3) << 17) | ((uint32_t)(kPriceThreads >> 4) << 24);
+__device__ __forceinline__ void umma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d), "l"(a), "l"(b), "r"(kIdesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+                   "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int n = 0; n <= kInnerSteps; ++n) L[n] = sc.L[n];                                      // taps in registers
-    const unsigned long long gp = (unsigned long long)(k.path_offset + p);
-    const uint2 key = make_uint2(k.seed_lo, k.seed_hi);
-    const unsigned c1 = (unsigned)t | ((k.shared_draws ? 0u : (unsigned)kind) << 24);           // independent draws per kind (:437-446)
-    float pay = 0.f;
-    for (int q = threadIdx.x; q < k.n_mc; q += kPriceThreads) {
-        float w1[kInnerM], w2[kInnerM];
+    for (int j = 0; j < 16; ++j) r[j] = __uint_as_float(u[j]);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+}  // namespace rbtc
+
+// Where an inner path's increments come from: Philox (production) or the caller's exported arrays (parity).
+// Philox layout: call j < 8 of (path, day | kind, inner path q) gives w1[4j .. 4j + 3]; call 8 + c gives w2[4c .. 4c + 3].
+struct InnerDraws {
+    const double* dW1;      // exported [*, n_mc, 32] or NULL
+    const double* dW2;
+    unsigned c0, c1;
+    uint2 key;
+};
+__device__ __forceinline__ void draw_w1(const InnerDraws& d, long long row, unsigned q, float (&w1)[kInnerM]) {
+    if (d.dW1 != nullptr) {
+        const double* a = d.dW1 + (row + q) * kInnerM;
 #pragma unroll
-        for (int j = 0; j < kInnerM / 2; ++j) {                                                 // 16 Philox calls -> 64 normals
-            const uint4 x = philox4x32_10(make_uint4((unsigned)gp, c1, (unsigned)q, kStreamRbInner | (unsigned)j), key);
-            box_muller_f32(x.x, x.y, w1[2 * j], w1[2 * j + 1]);
-            box_muller_f32(x.z, x.w, w2[2 * j], w2[2 * j + 1]);
+        for (int j = 0; j < kInnerM; ++j) w1[j] = (float)a[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < kInnerM / 4; ++j) {
+            const uint4 x = philox4x32_10(make_uint4(d.c0, d.c1, q, kStreamRbInner | (unsigned)j), d.key);
+            box_muller_f32(x.x, x.y, w1[4 * j], w1[4 * j + 1]);
+            box_muller_f32(x.z, x.w, w1[4 * j + 2], w1[4 * j + 3]);
         }
-        float w2s[kInnerSteps];
-#pragma unroll
-        for (int j = 0; j < kInnerSteps; ++j) w2s[j] = w2[j];
-        const float ST = __expf(inner_log_terminal(w1, w2s, L, sc));
-        pay += kind == 0 ? fmaxf(ST - K, 0.f) : fmaxf(K - ST, 0.f);                             // :299-302
     }
-    const float tot = block_sum<kPriceThreads / 32>(pay, red);
-    if (threadIdx.x == 0) {
-        const float price = tot / (float)k.n_mc * k.disc_f;                                     // :304
-        float* out = reinterpret_cast<float*>(rec + (long long)t * ld + p) + (kind == 0 ? 2 : 3);
-        *out = price;
-        if (t == T - 1) reinterpret_cast<float*>(rec + (long long)T * ld + p)[kind == 0 ? 2 : 3] = price;   // stale marks of row T
+}
+__device__ __forceinline__ void draw_w2(const InnerDraws& d, long long row, unsigned q, int chunk, float (&w2)[4]) {
+    if (d.dW2 != nullptr) {
+        const double* a = d.dW2 + (row + q) * kInnerM + 4 * chunk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w2[j] = (float)a[j];
+    } else {
+        const uint4 x = philox4x32_10(make_uint4(d.c0, d.c1, q, kStreamRbInner | (unsigned)(8 + chunk)), d.key);
+        box_muller_f32(x.x, x.y, w2[0], w2[1]);
+        box_muller_f32(x.z, x.w, w2[2], w2[3]);
     }
 }
 
-// Parity entry: the same inner-path function on exported increments.  One CTA per batch element.
+// One step of the inner log-Euler loop given X_k (:285-295), in log space.
+__device__ __forceinline__ float inner_step(float logS, float Xk, float w1k, float w2k, int kk, const InnerConsts& c) {
+    const float v = mufu_ex2(fmaf(Xk, kLog2ef, c.log2_xi_plus_dk[kk]));                          // xi exp(X_k - eta^2 lambda_k)
+    const float dW = fmaf(c.rho, w1k, c.rho_c * w2k);
+    logS += fmaf(mufu_sqrt_rb(v) * c.sqrt_dt, dW, fmaf(-c.half_dt, v, c.r_dt));
+    return fmaxf(logS, -18.420680743952367f);                                                    // S >= 1e-8 (:295)
+}
+
+// grid = (n_paths, n_days, 2): CTA (p, d, kind) prices the ATM call (kind 0) or put (1) of path p at day t_begin + d;
+// with exported draws: grid = (batch), inputs from the arrays, price written to price_out.
+template <bool TC>
 __global__ void __launch_bounds__(kPriceThreads)
-rbergomi_price_from_increments_kernel(const RbConsts k, const double* __restrict__ S0, const double* __restrict__ Kk,
-                                      const double* __restrict__ xi, const double* __restrict__ H, const double* __restrict__ eta,
-                                      const double* __restrict__ rho, const double* __restrict__ dW1, const double* __restrict__ dW2,
-                                      int n_mc, int is_put, double* __restrict__ price) {
+rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, int n_paths, int T, int t_begin,
+                      const double* __restrict__ path_params, const double* __restrict__ ex_S0, const double* __restrict__ ex_K,
+                      const double* __restrict__ ex_xi, const double* __restrict__ ex_dW1, const double* __restrict__ ex_dW2,
+                      int ex_is_put, double* __restrict__ price_out) {
     __shared__ InnerConsts sc;
     __shared__ float red[kPriceThreads / 32];
-    const int b = blockIdx.x;
-    if (threadIdx.x == 0) fill_inner_consts(sc, (float)S0[b], (float)xi[b], H[b], eta[b], rho[b], k);
-    __syncthreads();
-    float L[kInnerSteps + 1];
-#pragma unroll
-    for (int n = 0; n <= kInnerSteps; ++n) L[n] = sc.L[n];
-    const float K = (float)Kk[b];
-    float pay = 0.f;
-    for (int q = threadIdx.x; q < n_mc; q += kPriceThreads) {
-        const double* a = dW1 + ((long long)b * n_mc + q) * kInnerM;
-        const double* d = dW2 + ((long long)b * n_mc + q) * kInnerM;
-        float w1[kInnerM], w2[kInnerSteps];
-#pragma unroll
-        for (int j = 0; j < kInnerM; ++j) w1[j] = (float)a[j];
-#pragma unroll
-        for (int j = 0; j < kInnerSteps; ++j) w2[j] = (float)d[j];
-        const float ST = __expf(inner_log_terminal(w1, w2, L, sc));
-        pay += is_put ? fmaxf(K - ST, 0.f) : fmaxf(ST - K, 0.f);
+    extern __shared__ __align__(128) unsigned char dyn[];                                       // TC: A_hi, A_lo, B_hi, B_lo, mbarrier, TMEM slot
+    const bool exported = ex_dW1 != nullptr;
+    const int p = blockIdx.x, t = t_begin + blockIdx.y;
+    const int kind = exported ? ex_is_put : blockIdx.z;
+    float S, K, xi0;
+    if (exported) {
+        S = (float)ex_S0[p];
+        K = (float)ex_K[p];
+        xi0 = (float)ex_xi[p];
+    } else {
+        const float4 st = rec[(long long)t * ld + p];
+        S = st.x;
+        K = rintf(S);                                                                           // :418
+        xi0 = st.y;                                                                             // xi := v_t (:439)
     }
+    const int n_mc = k.n_mc;
+    if (threadIdx.x == 0)
+        fill_inner_consts(sc, S, xi0, path_params[2LL * n_paths + p], path_params[3LL * n_paths + p], path_params[4LL * n_paths + p], k);
+    const unsigned long long gp = (unsigned long long)(k.path_offset + p);
+    InnerDraws dr{ex_dW1, ex_dW2, (unsigned)gp, (unsigned)t | ((k.shared_draws ? 0u : (unsigned)kind) << 24),   // independent draws per kind (:437-446)
+                  make_uint2(k.seed_lo, k.seed_hi)};
+    const long long row = (long long)p * n_mc;
+    float pay = 0.f;
+
+    if (!TC) {
+        __syncthreads();
+        float L[kInnerSteps + 1];
+#pragma unroll
+        for (int n = 0; n <= kInnerSteps; ++n) L[n] = sc.L[n];                                  // filter taps in registers
+        for (int q = threadIdx.x; q < n_mc; q += kPriceThreads) {
+            float w1[kInnerM];
+            draw_w1(dr, row, (unsigned)q, w1);
+            float logS = sc.log_s0;
+#pragma unroll
+            for (int kk = 0; kk < kInnerSteps; ++kk) {
+                float w2[4];
+                if ((kk & 3) == 0) draw_w2(dr, row, (unsigned)q, kk >> 2, w2);
+                float acc = 0.f;
+#pragma unroll
+                for (int n = 1; n <= kInnerSteps; ++n) acc = fmaf(L[n], w1[(kk - n) & (kInnerM - 1)], acc);
+                logS = inner_step(logS, acc, w1[kk], w2[kk & 3], kk, sc);
+            }
+            const float ST = __expf(logS);
+            pay += kind == 0 ? fmaxf(ST - K, 0.f) : fmaxf(K - ST, 0.f);                         // :299-302
+        }
+    } else {
+        unsigned char* a_hi = dyn;
+        unsigned char* a_lo = a_hi + rbtc::kABytes;
+        unsigned char* b_hi = a_lo + rbtc::kABytes;
+        unsigned char* b_lo = b_hi + rbtc::kBBytes;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + rbtc::kBBytes);
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+        const uint32_t mbar = rbtc::smem_u32(bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"(rbtc::smem_u32(tmem_slot)), "r"((uint32_t)rbtc::kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        __syncthreads();                                                                        // sc.L is ready
+        // B[n = k][j] = L[(k - j) & 31] split hi / lo, core-matrix layout: (n / 8) SBO + (j / 4) LBO + (n % 8) 16 + (j % 4) 4
+        for (int e = threadIdx.x; e < kInnerM * kInnerM; e += kPriceThreads) {
+            const int n = e >> 5, j = e & 31;
+            const int tap = (n - j) & (kInnerM - 1);
+            const float v = tap <= kInnerSteps ? sc.L[tap] : 0.f;                               // L[0] = 0, tap 31 does not exist
+            const float hi = rbtc::tf32_hi(v);
+            const int off = (n >> 3) * rbtc::kSbo + (j >> 2) * rbtc::kLbo + (n & 7) * 16 + (j & 3) * 4;
+            *reinterpret_cast<float*>(b_hi + off) = hi;
+            *reinterpret_cast<float*>(b_lo + off) = v - hi;
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        fence_proxy_async_smem();
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem = *tmem_slot;
+        const uint32_t lane_addr = tmem + ((uint32_t)(threadIdx.x & ~31) << 16);
+        unsigned char* row_hi = a_hi + (threadIdx.x >> 3) * rbtc::kSbo + (threadIdx.x & 7) * 16;
+        unsigned char* row_lo = a_lo + (threadIdx.x >> 3) * rbtc::kSbo + (threadIdx.x & 7) * 16;
+        uint32_t phase = 0;
+        bool timed_out = false;
+        const int iters = (n_mc + kPriceThreads - 1) / kPriceThreads;
+        for (int it = 0; it < iters; ++it) {
+            const int q = it * kPriceThreads + threadIdx.x;
+            const bool live = q < n_mc;
+            float w1[kInnerM];
+            draw_w1(dr, row, (unsigned)(live ? q : 0), w1);
+#pragma unroll
+            for (int cch = 0; cch < kInnerM / 4; ++cch) {                                       // this thread's A row, hi and lo
+                float4 h, l;
+                h.x = rbtc::tf32_hi(w1[4 * cch]);     l.x = w1[4 * cch] - h.x;
+                h.y = rbtc::tf32_hi(w1[4 * cch + 1]); l.y = w1[4 * cch + 1] - h.y;
+                h.z = rbtc::tf32_hi(w1[4 * cch + 2]); l.z = w1[4 * cch + 2] - h.z;
+                h.w = rbtc::tf32_hi(w1[4 * cch + 3]); l.w = w1[4 * cch + 3] - h.w;
+                *reinterpret_cast<float4*>(row_hi + cch * rbtc::kLbo) = h;
+                *reinterpret_cast<float4*>(row_lo + cch * rbtc::kLbo) = l;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                    // earlier tcgen05.ld of the accumulator
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ah = rbtc::smem_u32(a_hi), al = rbtc::smem_u32(a_lo), bh = rbtc::smem_u32(b_hi), bl = rbtc::smem_u32(b_lo);
+#pragma unroll
+                for (int ks = 0; ks < kInnerM / 8; ++ks) {                                      // K = 8 per instruction = 2 chunks
+                    const uint32_t o = ks * 2 * rbtc::kLbo;
+                    rbtc::umma_tf32(tmem, rbtc::smem_desc(ah + o), rbtc::smem_desc(bh + o), ks > 0 ? 1u : 0u);
+                    rbtc::umma_tf32(tmem, rbtc::smem_desc(ah + o), rbtc::smem_desc(bl + o), 1u);
+                    rbtc::umma_tf32(tmem, rbtc::smem_desc(al + o), rbtc::smem_desc(bh + o), 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
+            }
+            {
+                uint32_t done = 0;
+                unsigned spins = 0;
+                while (!done && !timed_out) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+                    if (!done && ++spins > (1u << 24)) timed_out = true;
+                }
+                phase ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            float logS = sc.log_s0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float X[16];
+                rbtc::tmem_ld16(lane_addr + half * 16, X);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int kk = half * 16 + j;
+                    if (kk < kInnerSteps) {
+                        float w2[4];
+                        if ((kk & 3) == 0) draw_w2(dr, row, (unsigned)(live ? q : 0), kk >> 2, w2);
+                        logS = inner_step(logS, X[j], w1[kk], w2[kk & 3], kk, sc);
+                    }
+                }
+            }
+            const float ST = __expf(logS);
+            if (live) pay += kind == 0 ? fmaxf(ST - K, 0.f) : fmaxf(K - ST, 0.f);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)rbtc::kTmemCols) : "memory");
+        if (timed_out) pay = __int_as_float(0x7fc00000);                                        // NaN price: an MMA never completed
+    }
+
     const float tot = block_sum<kPriceThreads / 32>(pay, red);
-    if (threadIdx.x == 0) price[b] = (double)(tot / (float)n_mc * k.disc_f);
+    if (threadIdx.x == 0) {
+        const float price = tot / (float)n_mc * k.disc_f;                                       // :304
+        if (exported) {
+            price_out[p] = (double)price;
+        } else {
+            reinterpret_cast<float*>(rec + (long long)t * ld + p)[kind == 0 ? 2 : 3] = price;
+            if (t == T - 1) reinterpret_cast<float*>(rec + (long long)T * ld + p)[kind == 0 ? 2 : 3] = price;   // stale marks of row T
+        }
+    }
 }
 
 static int make_rb_consts(const cantor_rbergomi_params* p, RbConsts* k) {
@@ -332,8 +490,14 @@ extern "C" int cantor_rbergomi_price_atm(const cantor_rbergomi_params* params, f
     CANTOR_REQUIRE(t_end - t_begin <= 65535, "at most 65535 days per launch");
     if (t_end == t_begin) return CANTOR_OK;
     const dim3 grid((unsigned)n_paths, (unsigned)(t_end - t_begin), 2u);
-    rbergomi_price_kernel<<<grid, kPriceThreads, 0, (cudaStream_t)stream>>>(k, (float4*)svcp, ld, n_paths, episode_length,
-                                                                            t_begin, path_params);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (params->tensor_cores)
+        rbergomi_price_kernel<true><<<grid, kPriceThreads, rbtc::kSmemBytes, s>>>(k, (float4*)svcp, ld, n_paths, episode_length, t_begin,
+                                                                                  path_params, nullptr, nullptr, nullptr, nullptr,
+                                                                                  nullptr, 0, nullptr);
+    else
+        rbergomi_price_kernel<false><<<grid, kPriceThreads, 0, s>>>(k, (float4*)svcp, ld, n_paths, episode_length, t_begin, path_params,
+                                                                    nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
     return check_launch("rbergomi_price_kernel");
 }
 
@@ -347,7 +511,16 @@ extern "C" int cantor_rbergomi_price_from_increments(const cantor_rbergomi_param
     CANTOR_REQUIRE(S0 && K && xi && H && eta && rho && dW1 && dW2 && price, "array is NULL");
     CANTOR_REQUIRE(batch > 0 && n_mc > 0 && M == kInnerM, "increments must be [batch, n_mc, 32]");
     CANTOR_REQUIRE((int)(params->tenor / params->dt) == kInnerSteps, "the nested-MC pricer is built for int(tenor / dt) == 30 inner steps");
-    rbergomi_price_from_increments_kernel<<<(unsigned)batch, kPriceThreads, 0, (cudaStream_t)stream>>>(
-        k, S0, K, xi, H, eta, rho, dW1, dW2, n_mc, is_put, price);
-    return check_launch("rbergomi_price_from_increments_kernel");
+    // path_params layout [5, batch] = {S0, xi, H, eta, rho}: the kernel reads rows 2..4; S0 / K / xi come from their own arrays
+    CANTOR_REQUIRE(H + batch == eta && eta + batch == rho, "H, eta, rho must be consecutive rows of one [3, batch] array");
+    k.n_mc = n_mc;
+    const double* pp = H - 2LL * batch;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (params->tensor_cores)
+        rbergomi_price_kernel<true><<<(unsigned)batch, kPriceThreads, rbtc::kSmemBytes, s>>>(k, nullptr, 0, batch, 0, 0, pp, S0, K, xi, dW1,
+                                                                                             dW2, is_put, price);
+    else
+        rbergomi_price_kernel<false><<<(unsigned)batch, kPriceThreads, 0, s>>>(k, nullptr, 0, batch, 0, 0, pp, S0, K, xi, dW1, dW2, is_put,
+                                                                               price);
+    return check_launch("rbergomi_price_kernel (exported increments)");
 }

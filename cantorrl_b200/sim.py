@@ -180,7 +180,7 @@ RBERGOMI_DEFAULTS = dict(s0=S0_DEFAULT, xi=XI_DEFAULT, H=H_DEFAULT, eta=ETA_DEFA
                          clip_rho_max=-0.01)
 
 
-def _rb_params(base_params, r, dt, tenor, n_mc, shared_draws, seed, path_offset):
+def _rb_params(base_params, r, dt, tenor, n_mc, shared_draws, seed, path_offset, tensor_cores=True):
     kw = dict(RBERGOMI_DEFAULTS)
     if base_params is not None:
         if isinstance(base_params, dict):
@@ -191,7 +191,8 @@ def _rb_params(base_params, r, dt, tenor, n_mc, shared_draws, seed, path_offset)
         else:                                         # (S0, xi, H, eta, rho) as estimate_base_params returns them (:171-193)
             kw.update(dict(zip(("s0", "xi", "H", "eta", "rho"), (float(x) for x in base_params))))
     return _lib.RbergomiParams(*(float(kw[n]) for n, _ in _lib.RbergomiParams._fields_[:16]), float(r), float(dt), float(tenor),
-                               int(n_mc), int(bool(shared_draws)), int(seed) & (2 ** 64 - 1), int(path_offset))
+                               int(n_mc), int(bool(shared_draws)), int(bool(tensor_cores)), 0, int(seed) & (2 ** 64 - 1),
+                               int(path_offset))
 
 
 class RbergomiBook:
@@ -223,17 +224,19 @@ def C_byref(x):
 
 def generate_rbergomi_paths_and_options(num_paths, r=R, dt=DT, seed=SEED, *, base_params=None, n_steps=N_STEPS,
                                         n_mc=N_PATHS_OPTION_MC, tenor=T_OPTION_TENOR, price=True, days_per_launch=32,
-                                        shared_draws=False, path_offset=0, device="cuda", exported=None) -> RbergomiBook:
+                                        shared_draws=False, path_offset=0, device="cuda", exported=None,
+                                        tensor_cores=True) -> RbergomiBook:
     """The reference's data generator (``generate_paths_and_options``, rbergomi_sim.py:309-499) on the GPU.
 
     ``base_params`` = ``(S0, xi, H, eta, rho)`` from ``estimate_base_params`` (or a dict also overriding the perturbation
     constants); every path gets its own perturbed parameters.  Returns the packed env-schema book
     (``.book.save_npz(path)`` writes the reference's ``paths_rbergomi_options_100k.npz`` schema) with the ATM call / put
     columns priced by ``n_mc`` inner rough-Bergomi paths per (path, day), calls and puts on independent draws like the
-    reference unless ``shared_draws``.  ``exported=dict(params=[5, n], dW1=[n, M], dW2=[n, M])`` replays exported draws.
+    reference unless ``shared_draws``.  ``tensor_cores`` runs the 30-tap variance filter as split-TF32 ``tcgen05.mma``
+    (float32-level accuracy) instead of float32 FFMAs.  ``exported=dict(params=[5, n], dW1=[n, M], dW2=[n, M])`` replays exported draws.
     """
     dev = torch.device(device)
-    p = _rb_params(base_params, r, dt, tenor, n_mc, shared_draws, seed, path_offset)
+    p = _rb_params(base_params, r, dt, tenor, n_mc, shared_draws, seed, path_offset, tensor_cores)
     book = ReplayData.empty(num_paths, n_steps, dev)
     book.tensor.zero_()
     pp = torch.empty((5, num_paths), dtype=torch.float64, device=dev)
@@ -266,13 +269,15 @@ def rbergomi_outer_paths(num_paths, n_steps, params, dW1, dW2, r=R, dt=DT, devic
     return paths, v
 
 
-def price_rbergomi_option(S0, K, T_opt, r, xi, H, eta, rho, option_type, dW1, dW2, dt=DT, device="cuda"):
+def price_rbergomi_option(S0, K, T_opt, r, xi, H, eta, rho, option_type, dW1, dW2, dt=DT, device="cuda", tensor_cores=True):
     """``price_rbergomi_option_gpu`` (rbergomi_sim.py:246-306) on exported increments ``dW1, dW2 [batch, n_mc, 32]``."""
     if option_type not in ("call", "put"):
         raise ValueError("option_type must be 'call' or 'put'")
     dev = torch.device(device)
-    p = _rb_params(None, r, dt, T_opt, 1, False, 0, 0)
-    arrs = [_as_f64(a, dev) for a in (S0, K, xi, H, eta, rho)]
+    p = _rb_params(None, r, dt, T_opt, 1, False, 0, 0, tensor_cores)
+    arrs = [_as_f64(a, dev) for a in (S0, K, xi)]
+    hep = torch.stack([_as_f64(a, dev) for a in (H, eta, rho)]).contiguous()        # consecutive rows, as the C ABI asks
+    arrs += [hep[0], hep[1], hep[2]]
     d1, d2 = _as_f64(dW1, dev), _as_f64(dW2, dev)
     B, n_mc, M = d1.shape
     out = torch.empty(B, dtype=torch.float64, device=dev)

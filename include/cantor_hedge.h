@@ -187,6 +187,8 @@ typedef struct cantor_rbergomi_params {
     double r, dt, tenor;                     /* .04, 1/252, 30/252 (:13-14, :19) */
     int32_t n_mc;                            /* 5000 (:20) */
     int32_t shared_draws;                    /* 0 = call and put on independent draws like the reference (:437-446); 1 = the same draws */
+    int32_t tensor_cores;                    /* 1 = the 30-tap filter as split-TF32 tcgen05.mma (throughput form); 0 = float32 FFMA */
+    int32_t reserved;
     uint64_t seed;                           /* 42 (:17) */
     int64_t path_offset;                     /* global index of path 0 of this shard */
 } cantor_rbergomi_params;
@@ -201,7 +203,8 @@ int cantor_rbergomi_paths(const cantor_rbergomi_params* params, int32_t n_paths,
  * row T - 1).  Any day range can be run at any time and on any shard: the draws depend on (seed, global path, day) only. */
 int cantor_rbergomi_price_atm(const cantor_rbergomi_params* params, float* svcp, int64_t ld, int32_t n_paths,
                               int32_t episode_length, const double* path_params, int32_t t_begin, int32_t t_end, void* stream);
-/* The same inner-path arithmetic on exported increments dW1, dW2 [batch, n_mc, 32] (parity with the reference's draws). */
+/* The same inner-path arithmetic on exported increments dW1, dW2 [batch, n_mc, 32] (parity with the reference's draws).
+ * H, eta, rho must be consecutive rows of one [3, batch] float64 array. */
 int cantor_rbergomi_price_from_increments(const cantor_rbergomi_params* params, const double* S0, const double* K,
                                           const double* xi, const double* H, const double* eta, const double* rho,
                                           const double* dW1, const double* dW2, int32_t batch, int32_t n_mc, int32_t M,

@@ -33,23 +33,25 @@ def test_outer_generator_on_the_reference_run_draws():
     np.testing.assert_allclose(rb.H.cpu().numpy(), Z["gen_H"], rtol=0)
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["ffma", "tcgen05"])
 @pytest.mark.parametrize("kind", ["call", "put"])
-def test_nested_mc_price_on_the_reference_draws(kind):
+def test_nested_mc_price_on_the_reference_draws(kind, tc):
     """price_rbergomi_option_gpu (:246-306) on its own complex draws, float32 inner arithmetic: 1e-4 relative."""
     from cantorrl_b200 import sim
     dW1, dW2 = ro.brownian_from_Z(Z[f"Z_{kind}"])
     got = sim.price_rbergomi_option(Z["S0"], Z["K"], float(Z["tenor"]), float(Z["r"]), Z["xi"], Z["H"], Z["eta"], Z["rho"], kind,
-                                    dW1, dW2, float(Z["dt"]))
+                                    dW1, dW2, float(Z["dt"]), tensor_cores=tc)
     np.testing.assert_allclose(got.cpu().numpy(), Z[f"price_{kind}"], rtol=1e-4)
 
 
-def test_generated_book_statistics_and_resumability():
+@pytest.mark.parametrize("tc", [False, True], ids=["ffma", "tcgen05"])
+def test_generated_book_statistics_and_resumability(tc):
     """Philox mode: parameters within the reference's clips, unbiased increments, prices consistent with an independent
     oracle Monte Carlo within sampling error, and pricing any day range in any order gives the same book."""
     from cantorrl_b200 import sim
     base = (496.48, 0.02903, 0.4656, 1.985, -0.2022)              # estimate_base_params on the shipped CSV (SURVEY [probe])
     n, T, n_mc = 512, 8, 4000
-    rb = sim.generate_rbergomi_paths_and_options(n, base_params=base, n_steps=T, n_mc=n_mc, seed=7, days_per_launch=3)
+    rb = sim.generate_rbergomi_paths_and_options(n, base_params=base, n_steps=T, n_mc=n_mc, seed=7, days_per_launch=3, tensor_cores=tc)
     H, rho, xi, eta = (getattr(rb, a).cpu().numpy() for a in ("H", "rho", "xi", "eta"))
     assert H.min() >= 0.01 and H.max() <= 0.49 and rho.min() >= -0.99 and rho.max() <= -0.01
     assert (xi >= 0.5 * base[1] - 1e-15).all() and (eta >= 0.5 * base[3] - 1e-15).all()
@@ -57,7 +59,7 @@ def test_generated_book_statistics_and_resumability():
     book = rb.book
     assert torch.equal(book.C[T, :n], book.C[T - 1, :n]) and bool((book.C[:T, :n] > 0).all()) and bool((book.P[:T, :n] > 0).all())
     # resumability / order independence
-    again = sim.generate_rbergomi_paths_and_options(n, base_params=base, n_steps=T, n_mc=n_mc, seed=7, price=False)
+    again = sim.generate_rbergomi_paths_and_options(n, base_params=base, n_steps=T, n_mc=n_mc, seed=7, price=False, tensor_cores=tc)
     again.price_days(5, 8).price_days(0, 5)
     assert torch.equal(again.book.tensor, book.tensor)
     # independent Monte Carlo of the same (S, K, v, H, eta, rho) states by the oracle
