@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--rollout-steps", type=int, default=3, help="episode sweeps of the on-the-fly rollout kernel (extra)")
     ap.add_argument("--mlp-rollout-steps", type=int, default=1000, help="steps of the MLP-policy rollout (configs[4] shape; 0 = skip)")
     ap.add_argument("--book-strikes", type=int, default=8, help="strikes of the multi-strike book extra (configs[2] shape; 0 = skip)")
+    ap.add_argument("--rbergomi-paths", type=int, default=512, help="paths of the rough-Bergomi nested-MC extra (x 32 days; 0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -377,6 +378,21 @@ def main():
         book_ms = b0.elapsed_time(b1)
         del out_book, hb
 
+    # ---- the reference's own data generator: rough-Bergomi paths + nested-MC ATM prices (5000 inner paths x 30 steps) ----
+    rb_res = None
+    if args.rbergomi_paths > 0 and rank == 0:
+        from cantorrl_b200 import sim as _sim
+        base = (496.48, 0.02903, 0.4656, 1.985, -0.2022)           # estimate_base_params on the shipped CSV (SURVEY [probe])
+        _sim.generate_rbergomi_paths_and_options(64, base_params=base, n_steps=8, n_mc=64, device=dev)
+        torch.cuda.synchronize(dev)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rbk = _sim.generate_rbergomi_paths_and_options(args.rbergomi_paths, base_params=base, n_steps=32, n_mc=5000, price=False, device=dev)
+        q0.record(stream)
+        rbk.price_days(0, 32)
+        q1.record(stream)
+        torch.cuda.synchronize(dev)
+        rb_res = (q0.elapsed_time(q1), args.rbergomi_paths * 32 * 2)
+
     # ---- reduce over ranks ------------------------------------------------------------------------------------
     tt = torch.tensor([ms, e2e_s, roll[0] if roll else 0.0, mlp_roll[0] if mlp_roll else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -441,6 +457,11 @@ def main():
                 reprices_per_s=cells * args.book_strikes / (book_ms * 1e-3),
                 algorithmic_gbs=cells * (16 + 8 * args.book_strikes) / (book_ms * 1e-3) / 1e9,
                 mufu_per_s=cells * (5 + 3 * args.book_strikes) / (book_ms * 1e-3))
+        if rb_res is not None:
+            line["extra"]["rbergomi_nested_mc"] = dict(
+                kernel="rbergomi_price_kernel<tcgen05 split-TF32 FIR> (5000 inner paths x 30 steps per ATM call / put)", ms=rb_res[0],
+                pricings=rb_res[1], inner_path_steps_per_s=rb_res[1] * 5000.0 * 30 / (rb_res[0] * 1e-3),
+                reference_workload_seconds=100000 * 252 * 2 / (rb_res[1] / (rb_res[0] * 1e-3)))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)

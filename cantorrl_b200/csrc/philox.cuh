@@ -13,13 +13,9 @@ constexpr unsigned kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-#ifdef __CUDA_ARCH__
-        const unsigned hi0 = __umulhi(kPhiloxM0, c.x), hi1 = __umulhi(kPhiloxM1, c.z);
-#else
-        const unsigned hi0 = (unsigned)(((unsigned long long)kPhiloxM0 * c.x) >> 32);
-        const unsigned hi1 = (unsigned)(((unsigned long long)kPhiloxM1 * c.z) >> 32);
-#endif
-        const unsigned lo0 = kPhiloxM0 * c.x, lo1 = kPhiloxM1 * c.z;
+        // one 32 x 32 -> 64 multiply per lane pair (IMAD.WIDE.U32 on the device), not separate hi / lo products
+        const unsigned long long p0 = (unsigned long long)kPhiloxM0 * c.x, p1 = (unsigned long long)kPhiloxM1 * c.z;
+        const unsigned hi0 = (unsigned)(p0 >> 32), lo0 = (unsigned)p0, hi1 = (unsigned)(p1 >> 32), lo1 = (unsigned)p1;
         c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
         k.x += kPhiloxW0;
         k.y += kPhiloxW1;

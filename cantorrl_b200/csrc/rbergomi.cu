@@ -57,9 +57,11 @@ __device__ __forceinline__ void box_muller_f64(unsigned x0, unsigned x1, double&
     n1 = rad * s;
 }
 __device__ __forceinline__ float mufu_sqrt_rb(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Uniforms by the mantissa trick (bits -> [1, 2) -> subtract): ALU-pipe instructions instead of int-to-float conversions,
+// which share the quarter-rate XU pipe with the MUFU transcendentals this kernel is bound by.  23-bit resolution.
 __device__ __forceinline__ void box_muller_f32(unsigned x0, unsigned x1, float& n0, float& n1) {
-    const float u1 = ((float)x0 + 1.0f) * 2.3283064365386963e-10f;
-    const float u2 = (float)x1 * 2.3283064365386963e-10f;
+    const float u1 = 2.0f - __uint_as_float(0x3F800000u | (x0 >> 9));         // (0, 1]
+    const float u2 = __uint_as_float(0x3F800000u | (x1 >> 9)) - 1.0f;         // [0, 1)
     const float rad = mufu_sqrt_rb(-2.0f * kLn2f * mufu_lg2(u1));
     const float ang = 6.283185307179586f * u2;
     n0 = rad * __cosf(ang);
@@ -259,9 +261,11 @@ __device__ __forceinline__ void draw_w2(const InnerDraws& d, long long row, unsi
 
 // One step of the inner log-Euler loop given X_k (:285-295), in log space.
 __device__ __forceinline__ float inner_step(float logS, float Xk, float w1k, float w2k, int kk, const InnerConsts& c) {
-    const float v = mufu_ex2(fmaf(Xk, kLog2ef, c.log2_xi_plus_dk[kk]));                          // xi exp(X_k - eta^2 lambda_k)
+    // sqrt(v) = exp2(arg / 2), v = sqrt(v)^2: one MUFU per step instead of two.  v = xi exp(X_k - eta^2 lambda_k)
+    const float sv = mufu_ex2(0.5f * fmaf(Xk, kLog2ef, c.log2_xi_plus_dk[kk]));
+    const float v = sv * sv;
     const float dW = fmaf(c.rho, w1k, c.rho_c * w2k);
-    logS += fmaf(mufu_sqrt_rb(v) * c.sqrt_dt, dW, fmaf(-c.half_dt, v, c.r_dt));
+    logS += fmaf(sv * c.sqrt_dt, dW, fmaf(-c.half_dt, v, c.r_dt));
     return fmaxf(logS, -18.420680743952367f);                                                    // S >= 1e-8 (:295)
 }
 
