@@ -80,7 +80,7 @@ class RbergomiParams(C.Structure):
 POLICY_NO_HEDGE, POLICY_RANDOM, POLICY_DELTA_BASELINES, POLICY_DELTA_BENCHMARK, POLICY_MLP, POLICY_ACTIONS = range(6)
 MLP_FLOATS = 5212
 STATS_LEN = 16
-VECNORM_DOUBLES = 96
+VECNORM_DOUBLES = 16704
 
 
 class Policy(C.Structure):

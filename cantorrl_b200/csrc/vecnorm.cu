@@ -10,9 +10,9 @@
 //                 reward <- clip(reward / sqrt(ret_var + eps), +-clip_reward);  returns[done] <- 0
 //   RunningMeanStd.update(x): batch mean / population variance / count folded in with the parallel (Chan) formula,
 //                 initial mean 0, var 1, count 1e-4.
-// Three small kernels chained with programmatic dependent launch: batch moments (coalesced, column-aligned grid-stride
-// loop + one atomic per column per CTA), the fold (one warp), the in-place apply.  HBM-bound: 52 B read for the
-// moments, 104 + ~18 B for the apply, per env-step.
+// Three small kernels chained with programmatic dependent launch: batch moments (16-byte vector loads of 128-env chunks,
+// per-CTA partial sums, no atomics), the fold (fixed-order sum of the partials -> bitwise reproducible statistics, then
+// the Chan update), the in-place apply.  HBM-bound: 52 B read for the moments, 104 + ~18 B for the apply, per env-step.
 #include "common.cuh"
 
 namespace cantor {
@@ -21,36 +21,113 @@ constexpr int kVnCols = CANTOR_OBS_DIM;            // 13
 constexpr int kVnThreads = kVnCols * 32;           // 416: a thread's flat index keeps (index % 13) fixed across the stride
 // rms[] layout (doubles)
 constexpr int kObsMean = 0, kObsVar = 13, kObsCount = 26, kRetMean = 27, kRetVar = 28, kRetCount = 29;
-constexpr int kScratch = 32;                       // [32..58): batch sums: obs sum[13], obs sumsq[13], ret sum, ret sumsq
-constexpr int kDerived = 64;                       // [64..78): float-free derived values for the apply kernel: inv_std[13], ret_inv_std
+constexpr int kDerived = 32;                       // [32..46): derived values for the apply kernel: 1 / sqrt(var + eps) [13], return 1 / std
+constexpr int kPartial = 64;                       // [64, 64 + 28 * 592): per-CTA partial sums of the moments kernel, [statistic][CTA]
 
-__global__ void __launch_bounds__(kVnThreads)
-vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, long long n, const float* __restrict__ obs,
-                       const void* __restrict__ reward, int reward_f64, double gamma, int norm_obs, int norm_reward) {
-    __shared__ double s_sum[kVnThreads], s_sq[kVnThreads];
-    pdl_wait_prior_grid();
-    const long long total = n * kVnCols;
-    const long long stride = (long long)gridDim.x * kVnThreads;              // multiple of 13: the column of a thread is fixed
-    double sum = 0.0, sq = 0.0;
-    if (norm_obs) {
-        for (long long e = (long long)blockIdx.x * kVnThreads + threadIdx.x; e < total; e += stride) {
-            const double x = (double)__ldg(obs + e);
-            sum += x;
-            sq += x * x;
+constexpr int kVnRows = 128;                       // envs per chunk: 128 x 13 floats = 416 float4 = one float4 per thread
+constexpr int kVnSums = 2 * kVnCols + 2;           // per-CTA partial sums: obs sum[13], obs sumsq[13], ret sum, ret sumsq
+constexpr int kVnMaxGrid = 148 * 4;
+
+// The chunk mapping shared by the moments and the apply kernel: a CTA walks chunks of 128 envs; thread i owns the
+// float4 number i of a chunk, i.e. elements 4i .. 4i + 3, whose (row within the chunk, column) never change from chunk
+// to chunk because 128 * 13 is a multiple of 4 and of 13.  Full chunks move as aligned 16-byte vectors.
+struct ChunkMap {
+    int col[4], row[4];
+    __device__ __forceinline__ ChunkMap() {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = 4 * (int)threadIdx.x + j;
+            col[j] = e % kVnCols;
+            row[j] = e / kVnCols;
         }
     }
-    s_sum[threadIdx.x] = sum;
-    s_sq[threadIdx.x] = sq;
-    // discounted returns (one thread per env), their batch sums in registers
+};
+
+__global__ void __launch_bounds__(kVnThreads, 3)
+vecnorm_moments_kernel(double* __restrict__ partial /* [kVnSums, gridDim.x] */, double* __restrict__ returns, long long n,
+                       const float* __restrict__ obs, const void* __restrict__ reward, int reward_f64, double gamma,
+                       int norm_obs, int norm_reward, int vec_ok) {
+    __shared__ double part[8][kVnThreads];
+    __shared__ double cols[kVnSums];
+    const ChunkMap cm;
+    pdl_wait_prior_grid();
+    double sum[4] = {0.0, 0.0, 0.0, 0.0}, sq[4] = {0.0, 0.0, 0.0, 0.0};
     double rsum = 0.0, rsq = 0.0;
-    if (norm_reward) {
-        for (long long i = (long long)blockIdx.x * kVnThreads + threadIdx.x; i < n; i += stride) {
-            const double r = reward_f64 ? reinterpret_cast<const double*>(reward)[i] : (double)reinterpret_cast<const float*>(reward)[i];
-            const double ret = returns[i] * gamma + r;
-            returns[i] = ret;
-            rsum += ret;
-            rsq += ret * ret;
+    const long long n_chunks = (n + kVnRows - 1) / kVnRows;
+    const long long n_full = vec_ok ? n / kVnRows : 0;                               // chunks that move as whole float4 vectors
+    constexpr int U = 4;                                                             // independent 16-byte loads in flight per thread
+    long long c = blockIdx.x;
+    if (norm_obs) {
+        for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(obs) + (c + u * (long long)gridDim.x) * kVnThreads + threadIdx.x);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double d0 = v[u].x, d1 = v[u].y, d2 = v[u].z, d3 = v[u].w;
+                sum[0] += d0; sq[0] = fma(d0, d0, sq[0]);
+                sum[1] += d1; sq[1] = fma(d1, d1, sq[1]);
+                sum[2] += d2; sq[2] = fma(d2, d2, sq[2]);
+                sum[3] += d3; sq[3] = fma(d3, d3, sq[3]);
+            }
         }
+        for (; c < n_chunks; c += gridDim.x) {                                       // leftovers and the ragged last chunk
+            const long long base = c * kVnRows;
+            float x[4] = {0.f, 0.f, 0.f, 0.f};
+            if (c < n_full) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(obs) + c * kVnThreads + threadIdx.x);
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (base + cm.row[j] < n) x[j] = __ldg(obs + base * kVnCols + 4 * threadIdx.x + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double d = (double)x[j];
+                sum[j] += d;
+                sq[j] = fma(d, d, sq[j]);
+            }
+        }
+    }
+    if (norm_reward && threadIdx.x < kVnRows) {                                      // discounted returns, one thread per env
+        for (long long cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
+            const long long i = cc * kVnRows + threadIdx.x;
+            if (i < n) {
+                const double r = reward_f64 ? reinterpret_cast<const double*>(reward)[i] : (double)reinterpret_cast<const float*>(reward)[i];
+                const double ret = fma(returns[i], gamma, r);
+                returns[i] = ret;
+                rsum += ret;
+                rsq = fma(ret, ret, rsq);
+            }
+        }
+    }
+    pdl_launch_dependents();
+    // deterministic CTA reduction: threads with equal (i % 13) own the same four columns
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        part[j][threadIdx.x] = sum[j];
+        part[4 + j][threadIdx.x] = sq[j];
+    }
+    __shared__ double p104[8 * kVnCols];
+    __syncthreads();
+    if (threadIdx.x < 8 * kVnCols) {                                                 // (value v, group g): sum the 32 members g, g + 13, ...
+        const int v = threadIdx.x / kVnCols, g = threadIdx.x % kVnCols;
+        double a = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < kVnThreads / kVnCols; ++m) a += part[v][g + kVnCols * m];
+        p104[threadIdx.x] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kVnCols) {                                                 // column c of {sum, sumsq}: its four (group, slot) owners
+        const int kind = threadIdx.x / kVnCols, c = threadIdx.x % kVnCols;
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int g = ((c - j + kVnCols) * 10) % kVnCols;                        // 4 g + j = c (mod 13); 4^-1 = 10 (mod 13)
+            a += p104[(4 * kind + j) * kVnCols + g];
+        }
+        cols[threadIdx.x] = a;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -58,84 +135,141 @@ vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, l
         rsq += __shfl_down_sync(0xffffffffu, rsq, off);
     }
     __syncthreads();
-    pdl_launch_dependents();
-    if (norm_obs && threadIdx.x < kVnCols) {                                 // column c: threads c, c + 13, c + 26, ...
-        double a = 0.0, q = 0.0;
-        for (int j = threadIdx.x; j < kVnThreads; j += kVnCols) {
-            a += s_sum[j];
-            q += s_sq[j];
-        }
-        atomicAdd(rms + kScratch + threadIdx.x, a);
-        atomicAdd(rms + kScratch + kVnCols + threadIdx.x, q);
+    if ((threadIdx.x & 31) == 0 && threadIdx.x < kVnRows) part[0][threadIdx.x >> 5] = rsum, part[1][threadIdx.x >> 5] = rsq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cols[2 * kVnCols] = part[0][0] + part[0][1] + part[0][2] + part[0][3];
+        cols[2 * kVnCols + 1] = part[1][0] + part[1][1] + part[1][2] + part[1][3];
     }
-    if (norm_reward && (threadIdx.x & 31) == 0) {
-        atomicAdd(rms + kScratch + 2 * kVnCols, rsum);
-        atomicAdd(rms + kScratch + 2 * kVnCols + 1, rsq);
-    }
+    __syncthreads();
+    if (threadIdx.x < kVnSums) partial[(long long)threadIdx.x * gridDim.x + blockIdx.x] = cols[threadIdx.x];
 }
 
-// RunningMeanStd.update_from_moments for each observation column and for the returns; clears the scratch sums.
-__global__ void vecnorm_fold_kernel(double* __restrict__ rms, long long n, double epsilon, int training, int norm_obs,
-                                    int norm_reward) {
+// Sums the per-CTA partials in a fixed order (one warp per statistic), then RunningMeanStd.update_from_moments for each
+// observation column and for the returns.  One CTA of kVnSums warps.
+__global__ void __launch_bounds__(kVnSums * 32)
+vecnorm_fold_kernel(double* __restrict__ rms, const double* __restrict__ partial, int n_partial, long long n, double epsilon,
+                    int training, int norm_obs, int norm_reward) {
+    __shared__ double tot[kVnSums];
     pdl_wait_prior_grid();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double a = 0.0;
+    if (training)
+        for (int j = lane; j < n_partial; j += 32) a += partial[(long long)w * n_partial + j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+    if (lane == 0) tot[w] = a;
+    __syncthreads();
+    pdl_launch_dependents();
     const int j = threadIdx.x;
     const double bc = (double)n;
+    const double count = rms[kObsCount];
     if (j < kVnCols) {
         if (training && norm_obs) {
-            const double bmean = rms[kScratch + j] / bc;
-            const double bvar = fmax(rms[kScratch + kVnCols + j] / bc - bmean * bmean, 0.0);
-            const double count = rms[kObsCount], mean = rms[kObsMean + j], var = rms[kObsVar + j];
-            const double tot = count + bc, delta = bmean - mean;
-            rms[kObsMean + j] = mean + delta * bc / tot;
-            rms[kObsVar + j] = (var * count + bvar * bc + delta * delta * count * bc / tot) / tot;
+            const double bmean = tot[j] / bc;
+            const double bvar = fmax(tot[kVnCols + j] / bc - bmean * bmean, 0.0);
+            const double mean = rms[kObsMean + j], var = rms[kObsVar + j];
+            const double t = count + bc, delta = bmean - mean;
+            rms[kObsMean + j] = mean + delta * bc / t;
+            rms[kObsVar + j] = (var * count + bvar * bc + delta * delta * count * bc / t) / t;
         }
         rms[kDerived + j] = 1.0 / sqrt(rms[kObsVar + j] + epsilon);
     } else if (j == kVnCols) {
         if (training && norm_reward) {
-            const double bmean = rms[kScratch + 2 * kVnCols] / bc;
-            const double bvar = fmax(rms[kScratch + 2 * kVnCols + 1] / bc - bmean * bmean, 0.0);
-            const double count = rms[kRetCount], mean = rms[kRetMean], var = rms[kRetVar];
-            const double tot = count + bc, delta = bmean - mean;
-            rms[kRetMean] = mean + delta * bc / tot;
-            rms[kRetVar] = (var * count + bvar * bc + delta * delta * count * bc / tot) / tot;
-            rms[kRetCount] = tot;
+            const double bmean = tot[2 * kVnCols] / bc;
+            const double bvar = fmax(tot[2 * kVnCols + 1] / bc - bmean * bmean, 0.0);
+            const double rc = rms[kRetCount], mean = rms[kRetMean], var = rms[kRetVar];
+            const double t = rc + bc, delta = bmean - mean;
+            rms[kRetMean] = mean + delta * bc / t;
+            rms[kRetVar] = (var * rc + bvar * bc + delta * delta * rc * bc / t) / t;
+            rms[kRetCount] = t;
         }
         rms[kDerived + kVnCols] = 1.0 / sqrt(rms[kRetVar] + epsilon);
     }
-    __syncwarp();
-    if (j == 0 && training && norm_obs) rms[kObsCount] += bc;                  // after every column used the old count
-    if (j < 2 * kVnCols + 2) rms[kScratch + j] = 0.0;
-    pdl_launch_dependents();
+    __syncthreads();
+    if (j == 0 && training && norm_obs) rms[kObsCount] = count + bc;            // after every column used the old count
 }
 
-__global__ void __launch_bounds__(kVnThreads)
+__global__ void __launch_bounds__(kVnThreads, 3)
 vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ returns, long long n, float* __restrict__ obs,
                      void* __restrict__ reward, int reward_f64, const unsigned char* __restrict__ done,
-                     float* __restrict__ terminal_obs, double clip_obs, double clip_reward, int norm_obs, int norm_reward) {
+                     float* __restrict__ terminal_obs, double clip_obs, double clip_reward, int norm_obs, int norm_reward,
+                     int vec_ok) {
+    const ChunkMap cm;
     pdl_wait_prior_grid();
-    const long long total = n * kVnCols;
-    const long long stride = (long long)gridDim.x * kVnThreads;
-    const int col = threadIdx.x % kVnCols;                                   // fixed across the stride
-    if (norm_obs) {
-        const double mean = rms[kObsMean + col], inv = rms[kDerived + col];
-        for (long long e = (long long)blockIdx.x * kVnThreads + threadIdx.x; e < total; e += stride) {
-            obs[e] = (float)fmin(fmax(((double)obs[e] - mean) * inv, -clip_obs), clip_obs);
-            if (terminal_obs != nullptr && done[e / kVnCols])
-                terminal_obs[e] = (float)fmin(fmax(((double)terminal_obs[e] - mean) * inv, -clip_obs), clip_obs);
-        }
+    double mean[4];
+    float inv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        mean[j] = rms[kObsMean + cm.col[j]];
+        inv[j] = (float)rms[kDerived + cm.col[j]];
     }
+    const float lo = (float)-clip_obs, hi = (float)clip_obs;
     const double rinv = rms[kDerived + kVnCols];
-    for (long long i = (long long)blockIdx.x * kVnThreads + threadIdx.x; i < n; i += stride) {
-        if (norm_reward) {
-            if (reward_f64) {
-                double* r = reinterpret_cast<double*>(reward) + i;
-                *r = fmin(fmax(*r * rinv, -clip_reward), clip_reward);
-            } else {
-                float* r = reinterpret_cast<float*>(reward) + i;
-                *r = (float)fmin(fmax((double)*r * rinv, -clip_reward), clip_reward);
+    // (x - mean) in float64 (no cancellation error), scale and clip in float32 -- the result is a float32 anyway
+    auto norm1 = [&](float x, int j) { return fminf(fmaxf((float)((double)x - mean[j]) * inv[j], lo), hi); };
+    const long long n_chunks = (n + kVnRows - 1) / kVnRows;
+    const long long n_full = vec_ok ? n / kVnRows : 0;
+    constexpr int U = 4;
+    long long c = blockIdx.x;
+    if (norm_obs) {
+        for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {
+            float4* p[U];
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                p[u] = reinterpret_cast<float4*>(obs) + (c + u * (long long)gridDim.x) * kVnThreads + threadIdx.x;
+                v[u] = *p[u];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                v[u].x = norm1(v[u].x, 0); v[u].y = norm1(v[u].y, 1); v[u].z = norm1(v[u].z, 2); v[u].w = norm1(v[u].w, 3);
+                *p[u] = v[u];
             }
         }
-        if (done[i]) returns[i] = 0.0;
+        for (; c < n_chunks; c += gridDim.x) {
+            const long long base = c * kVnRows;
+            if (c < n_full) {
+                float4* p = reinterpret_cast<float4*>(obs) + c * kVnThreads + threadIdx.x;
+                float4 v = *p;
+                v.x = norm1(v.x, 0); v.y = norm1(v.y, 1); v.z = norm1(v.z, 2); v.w = norm1(v.w, 3);
+                *p = v;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (base + cm.row[j] < n) {
+                        float* p = obs + base * kVnCols + 4 * threadIdx.x + j;
+                        *p = norm1(*p, j);
+                    }
+            }
+        }
+        if (terminal_obs != nullptr) {                                           // rows of envs that just finished (rare)
+            for (long long cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
+                const long long base = cc * kVnRows;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (base + cm.row[j] < n && done[base + cm.row[j]]) {
+                        float* p = terminal_obs + base * kVnCols + 4 * threadIdx.x + j;
+                        *p = norm1(*p, j);
+                    }
+            }
+        }
+    }
+    if (threadIdx.x < kVnRows) {
+        for (long long cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
+            const long long i = cc * kVnRows + threadIdx.x;
+            if (i >= n) continue;
+            if (norm_reward) {
+                if (reward_f64) {
+                    double* r = reinterpret_cast<double*>(reward) + i;
+                    *r = fmin(fmax(*r * rinv, -clip_reward), clip_reward);
+                } else {
+                    float* r = reinterpret_cast<float*>(reward) + i;
+                    *r = (float)fmin(fmax((double)*r * rinv, -clip_reward), clip_reward);
+                }
+            }
+            if (done[i]) returns[i] = 0.0;
+        }
     }
 }
 
@@ -145,12 +279,13 @@ using namespace cantor;
 
 extern "C" int cantor_vecnorm_init(double* rms, double* returns, int64_t n_envs, void* stream) {
     CANTOR_REQUIRE(rms != nullptr && returns != nullptr && n_envs >= 0, "bad arguments");
-    double h[CANTOR_VECNORM_DOUBLES] = {0};
+    double h[32] = {0};
     for (int j = 0; j < kVnCols; ++j) h[kObsVar + j] = 1.0;
     h[kObsCount] = 1e-4;
     h[kRetVar] = 1.0;
     h[kRetCount] = 1e-4;
     cudaStream_t s = (cudaStream_t)stream;
+    CANTOR_CUDA(cudaMemsetAsync(rms, 0, sizeof(double) * CANTOR_VECNORM_DOUBLES, s));
     CANTOR_CUDA(cudaMemcpyAsync(rms, h, sizeof(h), cudaMemcpyHostToDevice, s));
     CANTOR_CUDA(cudaStreamSynchronize(s));                                   // h is a stack buffer
     CANTOR_CUDA(cudaMemsetAsync(returns, 0, sizeof(double) * (size_t)n_envs, s));
@@ -168,21 +303,36 @@ extern "C" int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs,
     cudaStream_t s = (cudaStream_t)stream;
     long long n = n_envs;
     const int f64 = reward_precision == CANTOR_F64;
-    const long long want = (n * kVnCols + kVnThreads - 1) / kVnThreads;
-    const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);       // grid-stride: at most 8 CTAs per SM
+    const long long n_chunks = (n + kVnRows - 1) / kVnRows;
+    // grid-stride over chunks of 128 envs with exactly one resident wave: SMs x (CTAs that fit per SM), so no partial tail wave
+    static int occ_moments = 0, occ_apply = 0, n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        CANTOR_CUDA(cudaGetDevice(&dev));
+        CANTOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_moments, vecnorm_moments_kernel, kVnThreads, 0));
+        CANTOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_apply, vecnorm_apply_kernel, kVnThreads, 0));
+        CANTOR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long cap_m = (long long)n_sm * (occ_moments > 0 ? occ_moments : 1), cap_a = (long long)n_sm * (occ_apply > 0 ? occ_apply : 1);
+    const unsigned grid = (unsigned)(n_chunks < cap_m ? n_chunks : (cap_m < kVnMaxGrid ? cap_m : kVnMaxGrid));
+    const unsigned grid_apply = (unsigned)(n_chunks < cap_a ? n_chunks : cap_a);
+    int n_partial = (int)grid;
+    int vec_ok = aligned16(obs) && (terminal_obs == nullptr || aligned16(terminal_obs)) ? 1 : 0;
+    double* partial = rms + kPartial;
     int rc;
     const float* obs_c = obs;
     const void* rew_c = reward;
     if (training) {
-        void* a1[] = {&rms, &returns, &n, &obs_c, &rew_c, (void*)&f64, &gamma, &norm_obs, &norm_reward};
+        void* a1[] = {&partial, &returns, &n, &obs_c, &rew_c, (void*)&f64, &gamma, &norm_obs, &norm_reward, &vec_ok};
         rc = launch_pdl((const void*)vecnorm_moments_kernel, dim3(grid), dim3(kVnThreads), s, a1);
         if (rc) return rc;
     }
-    void* a2[] = {&rms, &n, &epsilon, &training, &norm_obs, &norm_reward};
-    rc = launch_pdl((const void*)vecnorm_fold_kernel, dim3(1), dim3(32), s, a2);
+    const double* partial_c = partial;
+    void* a2[] = {&rms, &partial_c, &n_partial, &n, &epsilon, &training, &norm_obs, &norm_reward};
+    rc = launch_pdl((const void*)vecnorm_fold_kernel, dim3(1), dim3(kVnSums * 32), s, a2);
     if (rc) return rc;
     const double* rms_c = rms;
     void* a3[] = {&rms_c, &returns, &n, &obs, &reward, (void*)&f64, &done, &terminal_obs, &clip_obs, &clip_reward, &norm_obs,
-                  &norm_reward};
-    return launch_pdl((const void*)vecnorm_apply_kernel, dim3(grid), dim3(kVnThreads), s, a3);
+                  &norm_reward, &vec_ok};
+    return launch_pdl((const void*)vecnorm_apply_kernel, dim3(grid_apply), dim3(kVnThreads), s, a3);
 }

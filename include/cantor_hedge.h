@@ -271,11 +271,11 @@ int cantor_env_step_many(const cantor_env_params* params, const cantor_replay_bo
  * Replaces Stable-Baselines3's VecNormalize as the reference uses it around its env (src/agents/train_ppo_v2.py:204-208,
  * 305-309; statistics consumed at quantconnect/model_wrapper.py:131): RunningMeanStd of observations and of discounted
  * returns, normalisation + clipping in place.  rms is CANTOR_VECNORM_DOUBLES doubles of device memory (layout: obs mean
- * [0,13), obs var [13,26), obs count [26], return mean / var / count [27..29], then library scratch); returns is
+ * [0,13), obs var [13,26), obs count [26], return mean / var / count [27..29], then library scratch incl. per-CTA partial sums); returns is
  * [n_envs] doubles.  cantor_vecnorm_init sets mean 0, var 1, count 1e-4, returns 0 (it synchronises the stream).
  * cantor_vecnorm_step = VecNormalize.step_wait() on the arrays a cantor_env_step just wrote: obs [n_envs, 13] and reward
  * [n_envs] (float / double by reward_precision) are normalised IN PLACE, terminal_obs (or NULL) where done. */
-#define CANTOR_VECNORM_DOUBLES 96
+#define CANTOR_VECNORM_DOUBLES 16704      /* 64 + 28 * 592 (per-CTA partial sums of the moments kernel) rounded up */
 int cantor_vecnorm_init(double* rms, double* returns, int64_t n_envs, void* stream);
 int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs, float* obs, void* reward, int32_t reward_precision,
                         const uint8_t* done, float* terminal_obs, double gamma, double clip_obs, double clip_reward,
