@@ -424,6 +424,11 @@ def main():
             roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                           kernel=kname,
                           algorithmic_bytes_per_env_step=B_ALG[args.precision], launch_us=launch_ms * 1e3, peak_source=peak_src,
+                          dram_side=dict(bytes_per_env_step=B_ALG[args.precision] - 56,
+                                         gbs=(B_ALG[args.precision] - 56) * n / (launch_ms * 1e-3) / 1e9,
+                                         frac=(B_ALG[args.precision] - 56) * n / (launch_ms * 1e-3) / 1e9 / peak,
+                                         what="the same launches counted without the 40 B of state and the 16 B lagged path record "
+                                              "that stay in L2 from one launch to the next: what HBM itself has to move"),
                           note="achieved counts the 137 algorithmic B/env-step; 40 B of them (the env state, read + written every "
                                "step) are served by the 126 MB L2 between consecutive launches, so DRAM traffic per launch is lower "
                                "than the algorithmic bytes and frac can read above 1 against a plain-copy peak"),

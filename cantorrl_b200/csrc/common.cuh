@@ -46,6 +46,15 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint3
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
 }
+// the same with an L2 evict-first policy: data that nobody on the device reads again should not displace what is re-read
+__device__ __forceinline__ void tma_store_1d_evict_first(void* gdst, const void* ssrc, uint32_t bytes) {
+    uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(s), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the bulk copies have finished READING shared memory (the CTA may then exit / reuse it)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -15,8 +15,14 @@
 #define CANTOR_STEP_THREADS 128
 #endif
 #ifndef CANTOR_STEP_MIN_BLOCKS
-#define CANTOR_STEP_MIN_BLOCKS 12
+#define CANTOR_STEP_MIN_BLOCKS 16   // 32 registers, no spills; round-1 sweep: 12 -> 17.97 us, 14/16 -> 17.5 us per 2^20-env launch
 #endif
+#ifndef CANTOR_STEP_PREFETCH          // prefetch.global.L2 of the path record the NEXT step needs.  Measured (round 1): it HURTS
+#define CANTOR_STEP_PREFETCH 0        // (21.25 -> 23.63 us per launch; 18.05 -> 19.84 with evict-first stores), so it is off.
+#endif
+#ifndef CANTOR_OBS_EVICT_FIRST        // observation tiles leave through L2 with an evict-first policy: they are never re-read by
+#define CANTOR_OBS_EVICT_FIRST 1      // the env, and must not displace the state / path rows that the next launch re-reads
+#endif                                // (21.25 -> 18.05 us per launch).
 
 namespace cantor {
 
@@ -71,7 +77,11 @@ __device__ __forceinline__ void store_obs_tile(float* __restrict__ obs, const fl
         fence_proxy_async_smem();
         __syncthreads();
         if (threadIdx.x == 0) {
+#if CANTOR_OBS_EVICT_FIRST
+            tma_store_1d_evict_first(obs + first_env * CANTOR_OBS_DIM, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
+#else
             tma_store_1d(obs + first_env * CANTOR_OBS_DIM, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
+#endif
             tma_store_commit();
             tma_store_wait_read();
         }
@@ -257,6 +267,10 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         else make_observation_f32(o, k, S_new, v_new, C_new, P_new, inv_s0, pos_c, pos_p, step, S_prev, v_prev);
         core.x = pack_pos(pos_c, pos_p);
         core.y = step;
+#if CANTOR_STEP_PREFETCH
+        // the next step of this env reads rows `step` (just read: L2-resident) and `step + 1` (new): start that DRAM read now
+        if (!terminated) prefetch_l2(rp + 2 * b.ld);
+#endif
 
         if (terminated) {
             if (terminal_obs != nullptr) {

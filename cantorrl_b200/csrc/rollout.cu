@@ -246,7 +246,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                     fence_proxy_async_smem();
                     __syncthreads();
                     if (threadIdx.x == 0) {
-                        tma_store_1d(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
+                        tma_store_1d_evict_first(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
                         tma_store_commit();
                         tma_store_wait_read();
                     }

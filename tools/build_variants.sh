@@ -7,7 +7,7 @@ mkdir -p build/variants
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   d=build/variants/$name; mkdir -p $d
-  for f in abi hedge_step formats; do
+  for f in abi hedge_step formats path_sim reprice book_f32 host_env rollout vecnorm rbergomi; do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr \
       $flags -Icantorrl_b200/csrc -c cantorrl_b200/csrc/$f.cu -o $d/$f.o -Xptxas -v 2> $d/$f.ptxas.log &
   done
