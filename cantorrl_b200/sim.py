@@ -11,6 +11,8 @@ Each forwards to one CUDA kernel through the C ABI; tensors are the buffers.  No
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -211,15 +213,10 @@ class RbergomiBook:
         """Nested-MC ATM call / put prices of days ``[t_begin, t_end)`` into the book (resumable: any range, any order)."""
         b = self.book
         with torch.cuda.device(b.device):
-            _lib.check(_lib.lib().cantor_rbergomi_price_atm(C_byref(self._params), b.tensor.data_ptr(), b.ld, b.n_paths,
+            _lib.check(_lib.lib().cantor_rbergomi_price_atm(C.byref(self._params), b.tensor.data_ptr(), b.ld, b.n_paths,
                                                             b.episode_length, self.path_params.data_ptr(), int(t_begin), int(t_end),
                                                             _stream(b.device)), "cantor_rbergomi_price_atm")
         return self
-
-
-def C_byref(x):
-    import ctypes
-    return ctypes.byref(x)
 
 
 def generate_rbergomi_paths_and_options(num_paths, r=R, dt=DT, seed=SEED, *, base_params=None, n_steps=N_STEPS,
@@ -245,7 +242,7 @@ def generate_rbergomi_paths_and_options(num_paths, r=R, dt=DT, seed=SEED, *, bas
     d1 = _as_f64(ex["dW1"], dev) if "dW1" in ex else None
     d2 = _as_f64(ex["dW2"], dev) if "dW2" in ex else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().cantor_rbergomi_paths(C_byref(p), num_paths, n_steps, _lib.ptr(prm), _lib.ptr(d1), _lib.ptr(d2),
+        _lib.check(_lib.lib().cantor_rbergomi_paths(C.byref(p), num_paths, n_steps, _lib.ptr(prm), _lib.ptr(d1), _lib.ptr(d2),
                                                     int(d1.shape[1]) if d1 is not None else 0, book.tensor.data_ptr(), book.ld,
                                                     pp.data_ptr(), None, None, _stream(dev)), "cantor_rbergomi_paths")
     out = RbergomiBook(book, pp, p)
@@ -263,7 +260,7 @@ def rbergomi_outer_paths(num_paths, n_steps, params, dW1, dW2, r=R, dt=DT, devic
     paths = torch.empty((num_paths, n_steps + 1), dtype=torch.float64, device=dev)
     v = torch.empty_like(paths)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().cantor_rbergomi_paths(C_byref(p), num_paths, n_steps, prm.data_ptr(), d1.data_ptr(), d2.data_ptr(),
+        _lib.check(_lib.lib().cantor_rbergomi_paths(C.byref(p), num_paths, n_steps, prm.data_ptr(), d1.data_ptr(), d2.data_ptr(),
                                                     int(d1.shape[1]), None, 0, None, paths.data_ptr(), v.data_ptr(), _stream(dev)),
                    "cantor_rbergomi_paths")
     return paths, v
@@ -282,7 +279,7 @@ def price_rbergomi_option(S0, K, T_opt, r, xi, H, eta, rho, option_type, dW1, dW
     B, n_mc, M = d1.shape
     out = torch.empty(B, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().cantor_rbergomi_price_from_increments(C_byref(p), *(a.data_ptr() for a in arrs), d1.data_ptr(),
+        _lib.check(_lib.lib().cantor_rbergomi_price_from_increments(C.byref(p), *(a.data_ptr() for a in arrs), d1.data_ptr(),
                                                                     d2.data_ptr(), B, n_mc, M, int(option_type == "put"),
                                                                     out.data_ptr(), _stream(dev)),
                    "cantor_rbergomi_price_from_increments")

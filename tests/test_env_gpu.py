@@ -212,3 +212,29 @@ def test_full_size_invariants(prec):
             assert bool((env.cash_balance <= cash0).all())                           # costs are non-negative
         assert int(c.abs().max()) <= 200
         prev_c, cash0 = c.clone(), env.cash_balance.clone()
+
+
+def test_config4_shard_size_full_episode():
+    """BASELINE configs[3] per-GPU shard: 2^23 envs x 252 steps replayed from a 34 GB book simulated in HBM.  Size-independent
+    checks: done flags only at the episode end, the unhedged reward in closed form on a sample, auto-reset to step 0."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 * 2 ** 30:
+        pytest.skip("needs ~50 GB of free HBM")
+    from cantorrl_b200 import HedgingVecEnv, sim
+    n, T = 1 << 23, 252
+    book = sim.generate_paths_and_options(n, n_steps=T, model="gbm")
+    env = HedgingVecEnv(data=book, num_envs=n, episode_sampler="same_path", slippage_bps=1.0, theta_weight=2e-4,
+                        pnl_penalty_weight=1e-3, lambda_cost=1e-4)
+    env.reset()
+    zero = torch.zeros((n, 2), device="cuda")
+    sample = torch.arange(0, n, 4099, device="cuda")
+    S = book.S
+    for t in range(T):
+        obs, r, d, _ = env.step(zero)
+        if t in (0, 100, T - 1):
+            s_new = (torch.tensor(10000.0, device="cuda") * S[t + 1, sample]).double()
+            s_old = (torch.tensor(10000.0, device="cuda") * S[t, sample]).double()
+            want = -(1e-3 * torch.abs((s_new - s_old) / 10000.0) / torch.clamp(S[0, sample], min=25.0).double()) - 2e-4 * (T - t - 1) / 252
+            torch.testing.assert_close(r[sample].double(), want, rtol=1e-4, atol=1e-7)
+        assert bool(d.all()) == (t == T - 1) and bool(d.any()) == (t == T - 1)
+    assert int(env.current_step.max()) == 0 and bool(torch.isfinite(obs).all())
