@@ -103,52 +103,56 @@ book_f32_kernel(const float4* __restrict__ rec, long long ld, int n_paths, int T
         const float sst = sigma * sq;
         const float inv_sst = mufu_rcp(sigma) * g_isq[t];
         const float l0 = logf(__fdiv_rn(S, K0));                              // ln(S / K_0), |.| small: ~1e-7 absolute
-        const float drift = fmaf(0.5f * sigma, sigma, r) * Tt;                // (r + sigma^2 / 2) T
-        const float s_over_k0 = S * mufu_rcp(K0) * g_idisc[t];                // S / (K_0 e^{-rT})
+        const float base = (l0 + fmaf(0.5f * sigma, sigma, r) * Tt) * inv_sst;    // d1 of the strike K_0 itself
+        const float k0d = K0 * disc;                                          // K_0 e^{-rT}
+        const float s_over_k0d = S * mufu_rcp(K0) * g_idisc[t];               // S / (K_0 e^{-rT})
         const float gamma_scale = GREEKS ? inv_sst * mufu_rcp(S) : 0.f;
-        const long long at = (long long)t * ld + p;
+        float* pc = out.calls + (long long)t * ld + p;                        // strike m lives `m * plane` further on
+        float* pp = out.puts + (long long)t * ld + p;
+        float* pd = (GREEKS && out.deltas != nullptr) ? out.deltas + (long long)t * ld + p : nullptr;
+        float* pg = (GREEKS && out.gammas != nullptr) ? out.gammas + (long long)t * ld + p : nullptr;
+        if (Tt <= 0.f) {                                                      // :17-20 intrinsic value at expiry (uniform in t)
+            for (int m = 0; m < M; ++m) {
+                const float K = K0 * s_mult[m], kd = k0d * s_mult[m];
+                __stcs(pc, fmaxf(S - kd, 0.f));
+                __stcs(pp, fmaxf(kd - S, 0.f));
+                if (pd != nullptr) { __stcs(pd, (S > K) ? 1.f : (S == K ? 0.5f : 0.f)); pd += plane; }   // hedging_env_v2.py:90-92
+                if (pg != nullptr) { __stcs(pg, 0.f); pg += plane; }
+                pc += plane;
+                pp += plane;
+            }
+            continue;
+        }
 #pragma unroll 4
         for (int m = 0; m < M; ++m) {
-            const float K = K0 * s_mult[m];
-            const float kd = K * disc;
-            float call, put, delta = 0.f, gamma = 0.f;
-            if (Tt <= 0.f) {                                                  // :17-20 intrinsic value at expiry
-                call = fmaxf(S - kd, 0.f);
-                put = fmaxf(kd - S, 0.f);
-                if (GREEKS) delta = (S > K) ? 1.f : (S == K ? 0.5f : 0.f);    // hedging_env_v2.py:90-92
-            } else {
-                const float d1 = (l0 - s_lnm[m] + drift) * inv_sst;
-                const float d2 = d1 - sst;
-                // Phi(d1) with its own exponential; phi(d2) = phi(d1) * S / (K e^{-rT})
-                float c1, c1m;
-                const float pdf1 = normal_pdf_cdf(d1, &c1, &c1m);
-                const float pdf2 = pdf1 * (s_over_k0 * s_invm[m]);
-                const float a2 = fabsf(d2);
-                const float t2 = mufu_rcp(fmaf(0.2316419f, a2, 1.0f));
-                float poly = fmaf(t2, 1.330274429f, -1.821255978f);
-                poly = fmaf(t2, poly, 1.781477937f);
-                poly = fmaf(t2, poly, -0.356563782f);
-                poly = fmaf(t2, poly, 0.319381530f);
-                // far in the tail pdf1 underflows while the ratio overflows (0 * inf): the tail mass is 0 there
-                const float q2 = (pdf1 > 0.f) ? pdf2 * (poly * t2) : 0.f;
-                const bool pos2 = d2 >= 0.f;
-                const float c2 = pos2 ? 1.0f - q2 : q2;
-                const float c2m = pos2 ? -q2 : q2 - 1.0f;
-                call = fmaf(S, c1, -kd * c2);                                 // S Phi(d1) - K e^{-rT} Phi(d2)
-                put = fmaf(S, c1m, -kd * c2m);                                // K e^{-rT} Phi(-d2) - S Phi(-d1)
-                call = (call < 0.f) ? 0.f : call;                             // cancellation noise of a price that is >= 0
-                put = (put < 0.f) ? 0.f : put;                                // (a NaN stays a NaN)
-                if (GREEKS) {
-                    delta = c1;
-                    gamma = pdf1 * gamma_scale;                               // phi(d1) / (S sigma sqrt(T))
-                }
-            }
-            const long long o = (long long)m * plane + at;
-            __stcs(out.calls + o, call);
-            __stcs(out.puts + o, put);
+            const float kd = k0d * s_mult[m];
+            const float d1 = fmaf(-s_lnm[m], inv_sst, base);                  // (ln(S / K_m) + (r + sigma^2 / 2) T) / (sigma sqrt T)
+            const float d2 = d1 - sst;
+            // Phi(d1) with its own exponential; phi(d2) = phi(d1) * S / (K e^{-rT})
+            float c1, c1m;
+            const float pdf1 = normal_pdf_cdf(d1, &c1, &c1m);
+            const float pdf2 = pdf1 * (s_over_k0d * s_invm[m]);
+            const float t2 = mufu_rcp(fmaf(0.2316419f, fabsf(d2), 1.0f));
+            float poly = fmaf(t2, 1.330274429f, -1.821255978f);
+            poly = fmaf(t2, poly, 1.781477937f);
+            poly = fmaf(t2, poly, -0.356563782f);
+            poly = fmaf(t2, poly, 0.319381530f);
+            // far in the tail pdf1 underflows while the ratio overflows (0 * inf): the tail mass is 0 there
+            const float q2 = (pdf1 > 0.f) ? pdf2 * (poly * t2) : 0.f;
+            const bool pos2 = d2 >= 0.f;
+            const float c2 = pos2 ? 1.0f - q2 : q2;
+            const float c2m = pos2 ? -q2 : q2 - 1.0f;
+            float call = fmaf(S, c1, -kd * c2);                               // S Phi(d1) - K e^{-rT} Phi(d2)
+            float put = fmaf(S, c1m, -kd * c2m);                              // K e^{-rT} Phi(-d2) - S Phi(-d1)
+            call = (call < 0.f) ? 0.f : call;                                 // cancellation noise of a price that is >= 0
+            put = (put < 0.f) ? 0.f : put;                                    // (a NaN stays a NaN)
+            __stcs(pc, call);
+            __stcs(pp, put);
+            pc += plane;
+            pp += plane;
             if (GREEKS) {
-                if (out.deltas != nullptr) __stcs(out.deltas + o, delta);
-                if (out.gammas != nullptr) __stcs(out.gammas + o, gamma);
+                if (pd != nullptr) { __stcs(pd, c1); pd += plane; }           // call delta = Phi(d1)
+                if (pg != nullptr) { __stcs(pg, pdf1 * gamma_scale); pg += plane; }   // phi(d1) / (S sigma sqrt(T))
             }
         }
     }
