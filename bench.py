@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--mlp-rollout-steps", type=int, default=1000, help="steps of the MLP-policy rollout (configs[4] shape; 0 = skip)")
     ap.add_argument("--book-strikes", type=int, default=8, help="strikes of the multi-strike book extra (configs[2] shape; 0 = skip)")
     ap.add_argument("--rbergomi-paths", type=int, default=512, help="paths of the rough-Bergomi nested-MC extra (x 32 days; 0 = skip)")
+    ap.add_argument("--no-fused-allreduce", action="store_true", help="all-reduce the statistics with NCCL instead of in-kernel")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -321,6 +322,12 @@ def main():
         ro = HedgingRollout(simulate=dict(model="gbm", seed=42, s0=S0, v0=XI, n_steps=T), num_envs=n, device=dev,
                             env_offset=rank * n, total_envs=world * n, one_call_only=True, **ENV_KW)
         rstats = ro.new_stats()
+        stats_transport = "nccl all_reduce" if world > 1 else "single GPU"
+        if world > 1 and not args.no_fused_allreduce:
+            try:      # all-reduce fused into the kernel epilogue: multimem.red through the NVSwitch, or peer atomics over NVLink
+                stats_transport = "fused in-kernel: " + rstats.enable_fused_all_reduce()
+            except Exception as e:
+                stats_transport = f"nccl all_reduce (symmetric memory unavailable: {type(e).__name__})"
 
         def roll_sweep():
             rstats.zero_()
@@ -336,7 +343,7 @@ def main():
             roll_sweep()
         r1.record(stream)
         barrier()
-        roll = (r0.elapsed_time(r1), rstats.result())
+        roll = (r0.elapsed_time(r1), rstats.result(), stats_transport)
 
     # ---- configs[4] shape: on-policy rollout, MLP actor 13-64-64-2 on the tensor cores fused with the env step ------
     # 2^19 envs per GPU x 1000 steps (4 M envs on 8 GPUs), GBM on the fly, bf16 tcgen05.mma actor, statistics all-reduced.
@@ -444,7 +451,7 @@ def main():
             rs = roll[1]
             line["extra"]["rollout_on_the_fly"] = dict(
                 kernel="rollout_kernel<GBM on the fly, delta_every_step policy, episode statistics> + all-reduce of the "
-                       "statistics buffers (NCCL) once per sweep", sweeps=args.rollout_steps, ms_per_sweep=roll_ms / args.rollout_steps,
+                       "statistics buffers once per sweep", stats_all_reduce=roll[2], sweeps=args.rollout_steps, ms_per_sweep=roll_ms / args.rollout_steps,
                 env_steps_per_s=float(n) * world * T * args.rollout_steps / (roll_ms * 1e-3),
                 stats={k: rs[k] for k in ("n_episodes", "mean_abs_pnl", "std_abs_pnl", "mean_cost", "mean_reward", "cvar95_abs_pnl")})
         if mlp_roll is not None:

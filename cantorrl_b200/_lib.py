@@ -90,8 +90,9 @@ class Policy(C.Structure):
 
 class StatsOut(C.Structure):
     _fields_ = [("sums", C.c_void_p), ("hist", C.c_void_p), ("hist_sum", C.c_void_p), ("episode_b", C.c_void_p),
-                ("hist_max", C.c_double),
-                ("hist_bins", C.c_int32), ("reserved", C.c_int32), ("episode_slots", C.c_int64)]
+                ("hist_max", C.c_double), ("hist_bins", C.c_int32), ("reserved", C.c_int32), ("episode_slots", C.c_int64),
+                ("mc_global", C.c_void_p), ("peer_global", C.c_void_p * 8), ("n_peers", C.c_int32), ("reserved2", C.c_int32),
+                ("ticket", C.c_void_p)]
 
 
 class RolloutOut(C.Structure):

@@ -151,7 +151,60 @@ struct StatsOut {
     float hist_scale;           // bins / hist_max
     int hist_bins;
     long long episode_slots;    // capacity of episode_b in episodes per env
+    // fused all-reduce (ticket == NULL: off)
+    void* mc_global;            // NVLS multicast address of the global block {sums[16], hist[bins], hist_sum[bins]}, or NULL
+    void* peer_global[8];       // unicast addresses of every rank's global block
+    int n_peers;
+    unsigned* ticket;
 };
+
+// ---- fused statistics all-reduce --------------------------------------------------------------------------------------
+// multimem.red: one instruction adds a value into the same offset of every GPU's copy of a multicast-mapped buffer; the
+// reduction is performed by the NVSwitch (NVLS), the SM only issues the request.
+__device__ __forceinline__ void multimem_add_f64(double* mc, double v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" :: "l"(mc), "d"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_add_u64(unsigned long long* mc, unsigned long long v) {
+    asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(mc), "l"(v) : "memory");
+}
+
+// Called by every thread of every CTA at the very end of a kernel that accumulated into st.sums / hist / hist_sum.
+// The last CTA to arrive (atomic ticket) owns the finished local statistics: it pushes them to all ranks and clears them.
+template <int THREADS>
+__device__ __forceinline__ void push_statistics_to_all_ranks(const StatsOut& st) {
+    if (st.ticket == nullptr) return;
+    __shared__ int is_last;
+    __threadfence();                                   // this CTA's atomics are visible before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(st.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int n_words = CANTOR_STATS_LEN + 2 * st.hist_bins;           // global block, 8-byte words
+    for (int w = threadIdx.x; w < n_words; w += THREADS) {
+        const bool is_count = w >= CANTOR_STATS_LEN && w < CANTOR_STATS_LEN + st.hist_bins;
+        unsigned long long* lp;                                         // local word
+        if (w < CANTOR_STATS_LEN) lp = reinterpret_cast<unsigned long long*>(st.sums + w);
+        else if (is_count) lp = st.hist != nullptr ? st.hist + (w - CANTOR_STATS_LEN) : nullptr;
+        else lp = st.hist_sum != nullptr ? reinterpret_cast<unsigned long long*>(st.hist_sum + (w - CANTOR_STATS_LEN - st.hist_bins)) : nullptr;
+        if (lp == nullptr) continue;
+        const unsigned long long bits = __ldcg(lp);
+        if (bits == 0ull) continue;                                     // +0.0 / count 0: nothing to add
+        *lp = 0ull;                                                     // local accumulators are per-launch
+        if (st.mc_global != nullptr) {
+            if (is_count) multimem_add_u64(reinterpret_cast<unsigned long long*>(st.mc_global) + w, bits);
+            else multimem_add_f64(reinterpret_cast<double*>(st.mc_global) + w, __longlong_as_double((long long)bits));
+        } else {
+            for (int r = 0; r < st.n_peers; ++r) {
+                if (is_count) atomicAdd(reinterpret_cast<unsigned long long*>(st.peer_global[r]) + w, bits);
+                else atomicAdd(reinterpret_cast<double*>(st.peer_global[r]) + w, __longlong_as_double((long long)bits));
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *st.ticket = 0u;                              // ready for the next launch
+}
 
 // Block reduction of NS doubles per thread, then one atomicAdd per value per block.  smem: [NS * THREADS / 32] doubles.
 template <int NS, int THREADS>
@@ -200,12 +253,27 @@ __device__ __forceinline__ float episode_statistics(double (&stat)[11], float ac
 }
 
 inline int make_stats_out(const cantor_stats_out* stats, StatsOut* so) {
-    *so = StatsOut{nullptr, nullptr, nullptr, nullptr, 0.f, 0, 0};
+    *so = StatsOut{};
     if (stats == nullptr) return CANTOR_OK;
     CANTOR_REQUIRE(stats->sums != nullptr, "stats.sums is NULL");
     CANTOR_REQUIRE(stats->hist == nullptr || (stats->hist_bins > 0 && stats->hist_max > 0), "histogram needs bins and a range");
-    *so = StatsOut{stats->sums, (unsigned long long*)stats->hist, stats->hist ? stats->hist_sum : nullptr, stats->episode_b,
-                   stats->hist ? (float)(stats->hist_bins / stats->hist_max) : 0.f, stats->hist_bins, stats->episode_slots};
+    so->sums = stats->sums;
+    so->hist = (unsigned long long*)stats->hist;
+    so->hist_sum = stats->hist ? stats->hist_sum : nullptr;
+    so->episode_b = stats->episode_b;
+    so->hist_scale = stats->hist ? (float)(stats->hist_bins / stats->hist_max) : 0.f;
+    so->hist_bins = stats->hist ? stats->hist_bins : 0;
+    so->episode_slots = stats->episode_slots;
+    if (stats->ticket != nullptr) {
+        CANTOR_REQUIRE(stats->mc_global != nullptr || (stats->n_peers >= 1 && stats->n_peers <= 8), "fused all-reduce needs a multicast address or 1..8 peers");
+        so->mc_global = stats->mc_global;
+        so->n_peers = stats->mc_global != nullptr ? 0 : stats->n_peers;
+        for (int r = 0; r < so->n_peers; ++r) {
+            CANTOR_REQUIRE(stats->peer_global[r] != nullptr, "peer_global entry is NULL");
+            so->peer_global[r] = stats->peer_global[r];
+        }
+        so->ticket = stats->ticket;
+    }
     return CANTOR_OK;
 }
 

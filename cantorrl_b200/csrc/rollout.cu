@@ -292,6 +292,8 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
         if (actor.timed_out && st.sums != nullptr) atomicAdd(st.sums + 15, 1.0);   // an MMA never completed: results are invalid
         actor.teardown();
     }
+    // fused all-reduce: the last CTA adds this launch's statistics into every rank's global block (NVLS multimem.red / peer atomics)
+    push_statistics_to_all_ranks<kRollThreads>(st);
 }
 
 }  // namespace cantor

@@ -47,26 +47,84 @@ class EpisodeStats:
                  n_envs: int = 0):
         dev = torch.device(device)
         self.device = dev
-        self.sums = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=dev)
+        # local accumulators (what a kernel launch on this GPU adds into)
+        self._l_sums = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=dev)
         self.hist_bins, self.hist_max = int(hist_bins), float(hist_max)
-        self.hist = torch.zeros(self.hist_bins, dtype=torch.int64, device=dev) if hist_bins > 0 else None   # u64 counts
-        self.hist_sum = torch.zeros(self.hist_bins, dtype=torch.float64, device=dev) if hist_bins > 0 else None
+        self._l_hist = torch.zeros(self.hist_bins, dtype=torch.int64, device=dev) if hist_bins > 0 else None   # u64 counts
+        self._l_hist_sum = torch.zeros(self.hist_bins, dtype=torch.float64, device=dev) if hist_bins > 0 else None
+        # fused all-reduce (enable_fused_all_reduce): symmetric "global" block that every rank's kernels add into
+        self._g = self._hdl = self._ticket = None
+        self.fused_transport = None
         self.episode_slots = int(episode_slots)
         self.episode_b = (torch.full((self.episode_slots, int(n_envs)), float("nan"), dtype=torch.float32, device=dev)
                           if episode_slots > 0 else None)
 
+    # the buffers that hold the totals: the symmetric global block when the all-reduce is fused into the kernels, else local
+    @property
+    def sums(self):
+        return self._l_sums if self._g is None else self._g[:_lib.STATS_LEN]
+
+    @property
+    def hist(self):
+        if self._g is None or self._l_hist is None:
+            return self._l_hist
+        return self._g[_lib.STATS_LEN:_lib.STATS_LEN + self.hist_bins].view(torch.int64)
+
+    @property
+    def hist_sum(self):
+        if self._g is None or self._l_hist_sum is None:
+            return self._l_hist_sum
+        return self._g[_lib.STATS_LEN + self.hist_bins:_lib.STATS_LEN + 2 * self.hist_bins]
+
     def zero_(self):
-        self.sums.zero_()
-        if self.hist is not None:
-            self.hist.zero_()
-            self.hist_sum.zero_()
+        self._l_sums.zero_()
+        if self._l_hist is not None:
+            self._l_hist.zero_()
+            self._l_hist_sum.zero_()
         if self.episode_b is not None:
             self.episode_b.fill_(float("nan"))
+        if self._g is not None:                 # nobody may still be adding into a block that is being cleared, and vice versa
+            self._hdl.barrier(channel=1)
+            self._g.zero_()
+            self._hdl.barrier(channel=1)
         return self
 
+    def enable_fused_all_reduce(self, group=None) -> str:
+        """Fuse the all-reduce into the kernels: the last CTA of every launch adds the launch's statistics into every
+        rank's copy of a symmetric memory block -- with ``multimem.red`` through the NVLS multicast mapping (the NVSwitch
+        does the reduction) when the fabric offers one, else with peer atomics over NVLink -- so ``all_reduce`` shrinks
+        to a barrier and no NCCL collective runs.  Collective call (every rank of ``group``).  Returns the transport
+        (``"multimem"`` or ``"p2p"``); raises if symmetric memory cannot be set up (callers fall back to NCCL)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        if self.device.type != "cuda":
+            raise RuntimeError("fused all-reduce needs CUDA devices")
+        group = group if group is not None else dist.group.WORLD
+        world = dist.get_world_size(group)
+        if world > 8:
+            raise RuntimeError("fused all-reduce is built for one NVSwitch domain (<= 8 ranks)")
+        words = _lib.STATS_LEN + 2 * self.hist_bins
+        g = symm.empty(words, dtype=torch.float64, device=self.device)
+        g.zero_()
+        hdl = symm.rendezvous(g, group)
+        self._g, self._hdl = g, hdl
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", lambda *a: True) and hdl.multicast_ptr else 0
+        self._peers = [int(p) for p in hdl.buffer_ptrs]
+        self.fused_transport = "multimem" if self._mc else "p2p"
+        hdl.barrier(channel=1)                  # every block is zero before anyone adds into it
+        return self.fused_transport
+
     def c_struct(self) -> _lib.StatsOut:
-        return _lib.StatsOut(self.sums.data_ptr(), _lib.ptr(self.hist), _lib.ptr(self.hist_sum), _lib.ptr(self.episode_b),
-                             self.hist_max, self.hist_bins, 0, self.episode_slots)
+        st = _lib.StatsOut(self._l_sums.data_ptr(), _lib.ptr(self._l_hist), _lib.ptr(self._l_hist_sum), _lib.ptr(self.episode_b),
+                           self.hist_max, self.hist_bins, 0, self.episode_slots)
+        if self._g is not None:
+            st.mc_global = self._mc or None
+            for r, p in enumerate(self._peers):
+                st.peer_global[r] = p
+            st.n_peers = len(self._peers)
+            st.ticket = self._ticket.data_ptr()
+        return st
 
     # ------------------------------------------------------------------------------------------ collective
     def all_reduce(self, group=None, async_op: bool = False):
@@ -76,6 +134,9 @@ class EpisodeStats:
         exact (int64) and the sums in float64.  Both are latency-bound (<= 64 KB) on NVLink / NVSwitch.
         """
         import torch.distributed as dist
+        if self._g is not None:      # fused: the kernels already added into every rank's block; wait for all ranks' launches
+            self._hdl.barrier(channel=0)
+            return []
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return []
         works = [dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=group, async_op=async_op)]

@@ -327,6 +327,16 @@ typedef struct cantor_stats_out {
     int32_t hist_bins;
     int32_t reserved;
     int64_t episode_slots;
+    /* Fused all-reduce over NVLink / NVSwitch (optional; ticket == NULL = off).  The LAST CTA of a launch adds the launch's
+     * local statistics into EVERY rank's copy of a symmetric "global" block {double sums[CANTOR_STATS_LEN]; uint64 hist[hist_bins];
+     * double hist_sum[hist_bins]} and zeroes the local accumulators: through the NVLS multicast address with multimem.red
+     * (the reduction happens in the switch) when mc_global != NULL, else with one atomic per peer on the unicast addresses.
+     * The global blocks hold the all-reduced totals once every rank's launch has finished (a barrier, no NCCL call). */
+    void* mc_global;                     /* multicast address of the global block, or NULL */
+    void* peer_global[8];                /* unicast address of each rank's global block (n_peers entries, own rank included) */
+    int32_t n_peers;
+    int32_t reserved2;
+    uint32_t* ticket;                    /* [1] device counter, zero before the first launch; reset by the kernel */
 } cantor_stats_out;
 
 typedef struct cantor_rollout_out {      /* optional rollout storage, time-major */

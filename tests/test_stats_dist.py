@@ -42,23 +42,30 @@ def _fill(stats, vec, b, n_env_steps):
     stats.sums[:11] = torch.from_numpy(vec)
     stats.sums[11] = n_env_steps
     bins = np.minimum((b.astype(np.float32) * np.float32(BINS / HMAX)).astype(np.int64), BINS - 1)
-    stats.hist += torch.from_numpy(np.bincount(bins, minlength=BINS))
-    stats.hist_sum += torch.from_numpy(np.bincount(bins, weights=b, minlength=BINS))
+    stats.hist.add_(torch.from_numpy(np.bincount(bins, minlength=BINS)))
+    stats.hist_sum.add_(torch.from_numpy(np.bincount(bins, weights=b, minlength=BINS)))
 
 
 def _worker(rank, world, init_file, q):
-    from cantorrl_b200.distributed import shard
-    from cantorrl_b200.stats import EpisodeStats
-    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
-    off, cnt = shard(TOTAL, rank, world)
-    _, vec, b = _oracle_shard(off, cnt)
-    st = EpisodeStats("cpu", hist_bins=BINS, hist_max=HMAX)
-    _fill(st, vec, b, cnt * STEPS)
-    st.all_reduce()
-    if rank == 0:
-        q.put((st.sums.numpy().copy(), st.hist.numpy().copy(), st.result()))
-    dist.barrier()
-    dist.destroy_process_group()
+    try:
+        from cantorrl_b200.distributed import shard
+        from cantorrl_b200.stats import EpisodeStats
+        import datetime
+        dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=60))
+        off, cnt = shard(TOTAL, rank, world)
+        _, vec, b = _oracle_shard(off, cnt)
+        st = EpisodeStats("cpu", hist_bins=BINS, hist_max=HMAX)
+        _fill(st, vec, b, cnt * STEPS)
+        st.all_reduce()
+        if rank == 0:
+            q.put((st.sums.numpy().copy(), st.hist.numpy().copy(), st.result()))
+        dist.barrier()
+        dist.destroy_process_group()
+    except BaseException as e:          # never leave the parent waiting on the queue
+        if rank == 0:
+            q.put(("error", repr(e), None))
+        raise
 
 
 def test_all_reduced_statistics_equal_the_single_shard_statistics():
@@ -69,9 +76,17 @@ def test_all_reduced_statistics_equal_the_single_shard_statistics():
         procs = [ctx.Process(target=_worker, args=(r, 2, os.path.join(d, "rdzv"), q)) for r in range(2)]
         for p in procs:
             p.start()
+        import time
+        t0 = time.time()
+        while q.empty() and time.time() - t0 < 120 and any(p.is_alive() for p in procs):
+            time.sleep(0.2)
+        assert not q.empty(), "workers died or timed out without a result"
         sums, hist, res = q.get()
+        assert not isinstance(sums, str), hist
         for p in procs:
             p.join(60)
+            if p.is_alive():
+                p.kill()
             assert p.exitcode == 0
     out, vec, b = _oracle_shard(0, TOTAL)
     np.testing.assert_allclose(sums[:11], vec, rtol=1e-12)
@@ -98,8 +113,8 @@ def test_cvar_from_histogram_matches_sorted_definition():
         b[:3] = 5.0                                        # beyond hist_max: clamps to the last bin, sum kept exact
         st = EpisodeStats("cpu", hist_bins=4096, hist_max=2.0)
         bins = np.minimum((b * (4096 / 2.0)).astype(np.int64), 4095)
-        st.hist += torch.from_numpy(np.bincount(bins, minlength=4096))
-        st.hist_sum += torch.from_numpy(np.bincount(bins, weights=b, minlength=4096))
+        st.hist.add_(torch.from_numpy(np.bincount(bins, minlength=4096)))
+        st.hist_sum.add_(torch.from_numpy(np.bincount(bins, weights=b, minlength=4096)))
         sb = np.sort(b)
         want = sb[int(0.95 * n):].mean()
         assert abs(st.cvar95() - want) <= 2.0 / 4096 + 1e-12, n

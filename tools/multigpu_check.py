@@ -27,10 +27,29 @@ def main():
     st = part.run(steps, "delta_benchmark").stats
     st.all_reduce()
     torch.cuda.synchronize()
-    ok = True
+    # the same statistics with the all-reduce fused into the kernel epilogue (multimem.red / peer atomics, no NCCL collective)
+    fused_note = "fused all-reduce unavailable"
+    fused_ok = True
+    try:
+        fs = part.new_stats()
+        transport = fs.enable_fused_all_reduce()
+        for rep in range(2):                                  # twice: local accumulators must come back clean, global must re-zero
+            fs.zero_()
+            part.run(steps, "delta_benchmark", stats=fs)
+            fs.all_reduce()
+            torch.cuda.synchronize()
+            fused_ok &= torch.equal(fs.hist, st.hist)
+            fused_ok &= bool(np.allclose(fs.sums.cpu().numpy(), st.sums.cpu().numpy(), rtol=1e-10, atol=0))
+            fused_ok &= bool(np.allclose(fs.hist_sum.cpu().numpy(), st.hist_sum.cpu().numpy(), rtol=1e-10, atol=0))
+            fused_ok &= float(fs._l_sums.abs().sum()) == 0.0 and int(fs._l_hist.sum()) == 0
+        fused_note = f"fused all-reduce via {transport}: {'OK' if fused_ok else 'MISMATCH'}"
+    except Exception as e:                                    # symmetric memory not available on this box: NCCL stays the path
+        fused_note = f"fused all-reduce unavailable ({type(e).__name__}: {str(e)[:200]})"
+    ok = fused_ok
+    print(f"[rank {rank}] {fused_note}", flush=True)
     if rank == 0:
         whole = HedgingRollout(simulate=sim, num_envs=total, device=dev, **KW).run(steps, "delta_benchmark").stats
-        ok = torch.equal(whole.hist, st.hist)
+        ok &= torch.equal(whole.hist, st.hist)
         ok &= bool(np.allclose(whole.sums.cpu().numpy(), st.sums.cpu().numpy(), rtol=1e-10, atol=0))
         ok &= int(st.sums[0]) == total * (steps // T) and int(st.sums[11]) == total * steps
         r = st.result()
