@@ -89,12 +89,13 @@ class EpisodeStats:
             self._hdl.barrier(channel=1)
         return self
 
-    def enable_fused_all_reduce(self, group=None) -> str:
+    def enable_fused_all_reduce(self, group=None, transport: str = "auto") -> str:
         """Fuse the all-reduce into the kernels: the last CTA of every launch adds the launch's statistics into every
         rank's copy of a symmetric memory block -- with ``multimem.red`` through the NVLS multicast mapping (the NVSwitch
         does the reduction) when the fabric offers one, else with peer atomics over NVLink -- so ``all_reduce`` shrinks
         to a barrier and no NCCL collective runs.  Collective call (every rank of ``group``).  Returns the transport
-        (``"multimem"`` or ``"p2p"``); raises if symmetric memory cannot be set up (callers fall back to NCCL)."""
+        (``"multimem"`` or ``"p2p"``; ``transport="p2p"`` forces the peer-atomic form); raises if symmetric memory cannot be
+        set up (callers fall back to NCCL)."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         if self.device.type != "cuda":
@@ -109,7 +110,9 @@ class EpisodeStats:
         hdl = symm.rendezvous(g, group)
         self._g, self._hdl = g, hdl
         self._ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", lambda *a: True) and hdl.multicast_ptr else 0
+        if transport not in ("auto", "p2p"):
+            raise ValueError("transport must be 'auto' or 'p2p'")
+        self._mc = int(hdl.multicast_ptr) if transport == "auto" and hdl.multicast_ptr else 0
         self._peers = [int(p) for p in hdl.buffer_ptrs]
         self.fused_transport = "multimem" if self._mc else "p2p"
         hdl.barrier(channel=1)                  # every block is zero before anyone adds into it

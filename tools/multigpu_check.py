@@ -31,8 +31,9 @@ def main():
     fused_note = "fused all-reduce unavailable"
     fused_ok = True
     try:
+      for want in ("auto", "p2p"):
         fs = part.new_stats()
-        transport = fs.enable_fused_all_reduce()
+        transport = fs.enable_fused_all_reduce(transport=want)
         for rep in range(2):                                  # twice: local accumulators must come back clean, global must re-zero
             fs.zero_()
             part.run(steps, "delta_benchmark", stats=fs)
@@ -42,7 +43,7 @@ def main():
             fused_ok &= bool(np.allclose(fs.sums.cpu().numpy(), st.sums.cpu().numpy(), rtol=1e-10, atol=0))
             fused_ok &= bool(np.allclose(fs.hist_sum.cpu().numpy(), st.hist_sum.cpu().numpy(), rtol=1e-10, atol=0))
             fused_ok &= float(fs._l_sums.abs().sum()) == 0.0 and int(fs._l_hist.sum()) == 0
-        fused_note = f"fused all-reduce via {transport}: {'OK' if fused_ok else 'MISMATCH'}"
+        fused_note = (fused_note + "; " if want == "p2p" else "") + f"fused all-reduce via {transport}: {'OK' if fused_ok else 'MISMATCH'}"
     except Exception as e:                                    # symmetric memory not available on this box: NCCL stays the path
         fused_note = f"fused all-reduce unavailable ({type(e).__name__}: {str(e)[:200]})"
     ok = fused_ok
