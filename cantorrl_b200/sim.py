@@ -219,20 +219,27 @@ class RbergomiBook:
         return self
 
 
-def generate_rbergomi_paths_and_options(num_paths, r=R, dt=DT, seed=SEED, *, base_params=None, n_steps=N_STEPS,
+def generate_rbergomi_paths_and_options(num_paths, r=R, dt=DT, seed=SEED, *, base_params=None, historical_prices=None,
+                                        n_steps=N_STEPS,
                                         n_mc=N_PATHS_OPTION_MC, tenor=T_OPTION_TENOR, price=True, days_per_launch=32,
                                         shared_draws=False, path_offset=0, device="cuda", exported=None,
                                         tensor_cores=True) -> RbergomiBook:
     """The reference's data generator (``generate_paths_and_options``, rbergomi_sim.py:309-499) on the GPU.
 
-    ``base_params`` = ``(S0, xi, H, eta, rho)`` from ``estimate_base_params`` (or a dict also overriding the perturbation
-    constants); every path gets its own perturbed parameters.  Returns the packed env-schema book
+    ``historical_prices`` (the reference's first argument) is calibrated on the host with
+    ``calibration.estimate_base_params``; or pass ``base_params`` = ``(S0, xi, H, eta, rho)`` directly (or a dict also
+    overriding the perturbation constants); every path gets its own perturbed parameters.  Returns the packed env-schema book
     (``.book.save_npz(path)`` writes the reference's ``paths_rbergomi_options_100k.npz`` schema) with the ATM call / put
     columns priced by ``n_mc`` inner rough-Bergomi paths per (path, day), calls and puts on independent draws like the
     reference unless ``shared_draws``.  ``tensor_cores`` runs the 30-tap variance filter as split-TF32 ``tcgen05.mma``
     (float32-level accuracy) instead of float32 FFMAs.  ``exported=dict(params=[5, n], dW1=[n, M], dW2=[n, M])`` replays exported draws.
     """
     dev = torch.device(device)
+    if historical_prices is not None:                 # the reference's first argument: calibrate on the host (rbergomi_sim.py:360)
+        if base_params is not None:
+            raise ValueError("give historical_prices or base_params, not both")
+        from .calibration import estimate_base_params
+        base_params = estimate_base_params(historical_prices, dt)
     p = _rb_params(base_params, r, dt, tenor, n_mc, shared_draws, seed, path_offset, tensor_cores)
     book = ReplayData.empty(num_paths, n_steps, dev)
     book.tensor.zero_()

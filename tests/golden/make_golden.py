@@ -288,6 +288,27 @@ def make_rbergomi_golden():
     print(f"rbergomi_golden: pricer batch of {B} x {n_mc} inner paths (call, put) + generator 24 paths x 12 days")
 
 
+def make_calibration_golden():
+    """estimate_base_params (rbergomi_sim.py:171-193) of the unmodified reference on the shipped price history and on
+    synthetic histories of several lengths (short ones exercise the default / guard branches)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_cupy_stub"))
+    rb = _load("ref_rbergomi3", f"{REF}/src/sim/rbergomi_sim.py")
+    hist = np.loadtxt(f"{REF}/data/historical_prices.csv", dtype=np.float64, delimiter=",")
+    rng = np.random.default_rng(31)
+    series = {"shipped": hist}
+    for n in (5, 21, 25, 60, 333, 2500):
+        series[f"synthetic_{n}"] = 100 * np.exp(np.cumsum(rng.normal(0, 0.01 * (1 + 0.5 * np.sin(np.arange(n) / 7)), n)))
+    series["flat_40"] = np.full(40, 50.0)
+    out = {}
+    for k, p in series.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out[f"prices_{k}"] = p
+            out[f"params_{k}"] = np.array([float(x) for x in rb.estimate_base_params(p, rb.DT)], np.float64)
+    np.savez_compressed(os.path.join(HERE, "calibration_golden.npz"), **out)
+    print(f"calibration_golden: {len(series)} price histories; shipped -> {out['params_shipped']}")
+
+
 class _NoBar:
     def __init__(self, it):
         self.it = it
@@ -303,6 +324,9 @@ class _NoBar:
 
 
 if __name__ == "__main__":
+    if "--calibration-only" in sys.argv:
+        make_calibration_golden()
+        sys.exit(0)
     if "--rbergomi-only" in sys.argv:
         make_rbergomi_golden()
         sys.exit(0)
@@ -314,3 +338,4 @@ if __name__ == "__main__":
         make_policy_golden()
     make_outer_euler_golden()
     make_rbergomi_golden()
+    make_calibration_golden()

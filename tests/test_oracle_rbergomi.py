@@ -52,3 +52,16 @@ def test_parameter_perturbation_clips():
     assert H.max() <= 0.49 and H.min() >= 0.01 and rho.max() <= -0.01 and rho.min() >= -0.99    # :37-40
     # the reference run's own parameters respect the same clips
     assert Z["gen_H"].max() <= 0.49 and Z["gen_rho"].min() >= -0.99 and (Z["gen_xi"] >= 0.5 * base[1]).all()
+
+
+def test_host_calibration_matches_the_reference_estimate_base_params():
+    """cantorrl_b200.calibration (host-side scalar routine) against the unmodified reference's outputs."""
+    from cantorrl_b200.calibration import estimate_base_params
+    g = np.load(os.path.join(GOLDEN, "calibration_golden.npz"))
+    names = [k[len("prices_"):] for k in g.files if k.startswith("prices_")]
+    assert "shipped" in names and len(names) >= 8
+    for k in names:
+        with np.errstate(all="ignore"):
+            got = np.array(estimate_base_params(g[f"prices_{k}"]), np.float64)
+        np.testing.assert_allclose(got, g[f"params_{k}"], rtol=1e-10, atol=1e-13, err_msg=k)
+    np.testing.assert_allclose(g["params_shipped"], [496.48, 0.02903, 0.4656, 1.985, -0.2022], rtol=2e-4)   # SURVEY [probe]
