@@ -74,3 +74,25 @@ def test_env_without_cuda_device_raises():
     from cantorrl_b200 import CantorError, HedgingVecEnv
     with pytest.raises((CantorError, RuntimeError, AssertionError)):
         HedgingVecEnv(data={}, num_envs=4, device="cpu")
+
+
+def test_missing_library_fails_loudly_instead_of_falling_back():
+    """Without the built .so every product entry point raises (there is no CPU path to fall back to)."""
+    import subprocess
+    import sys
+    code = ("import numpy as np\n"
+            "from cantorrl_b200 import CantorError, HedgingVecEnv\n"
+            "from cantorrl_b200.host_env import HostVecEnv\n"
+            "from cantorrl_b200.rollout import HedgingRollout\n"
+            "for make in (lambda: HedgingVecEnv(data={}, num_envs=2), lambda: HostVecEnv(num_envs=2, data={}),\n"
+            "             lambda: HedgingRollout(num_envs=2, simulate={})):\n"
+            "    try:\n"
+            "        make()\n"
+            "    except CantorError as e:\n"
+            "        assert 'no CPU fallback' in str(e), e\n"
+            "    else:\n"
+            "        raise SystemExit('constructed without the library')\n"
+            "print('LOUD')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT,
+                         env=dict(os.environ, CANTOR_HEDGE_LIB="/nonexistent/libcantor_hedge.so"))
+    assert out.returncode == 0 and "LOUD" in out.stdout, out.stdout + out.stderr

@@ -238,3 +238,31 @@ def test_config4_shard_size_full_episode():
             torch.testing.assert_close(r[sample].double(), want, rtol=1e-4, atol=1e-7)
         assert bool(d.all()) == (t == T - 1) and bool(d.any()) == (t == T - 1)
     assert int(env.current_step.max()) == 0 and bool(torch.isfinite(obs).all())
+
+
+def test_empty_and_zero_length_calls_are_no_ops():
+    """n_envs = 0, n_steps = 0, empty day ranges: accepted, nothing launched, nothing written."""
+    import ctypes as C
+    from cantorrl_b200 import HedgingVecEnv, _lib, sim
+    from cantorrl_b200.rollout import HedgingRollout
+    book = sim.generate_paths_and_options(8, n_steps=4)
+    env = HedgingVecEnv(data=book, num_envs=8, episode_sampler="same_path")
+    env.reset()
+    L = _lib.lib()
+    sentinel = torch.full((8, 13), 7.0, device="cuda")
+    rew = torch.zeros(8, device="cuda")
+    done = torch.zeros(8, dtype=torch.uint8, device="cuda")
+    act = torch.zeros((8, 2), device="cuda")
+    rc = L.cantor_env_step(C.byref(env._params), C.byref(env._book), C.byref(env._state), 0, _lib.F32, act.data_ptr(),
+                           sentinel.data_ptr(), rew.data_ptr(), done.data_ptr(), None, 1, None, None, None)
+    assert rc == 0
+    rc = L.cantor_env_step_many(C.byref(env._params), C.byref(env._book), C.byref(env._state), 8, _lib.F32, 0, act.data_ptr(),
+                                sentinel.data_ptr(), rew.data_ptr(), done.data_ptr(), None, None, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert bool((sentinel == 7.0).all()) and int(env.current_step.max()) == 0
+    res = HedgingRollout(data=book, num_envs=8).run(0, "random")
+    assert float(res.stats.sums.abs().sum()) == 0.0
+    rb = sim.generate_rbergomi_paths_and_options(4, n_steps=3, n_mc=16, price=False)
+    rb.price_days(2, 2)
+    assert float(rb.book.C.abs().sum()) == 0.0
