@@ -18,6 +18,7 @@ OBS_DIM = 13
 F32, F64 = 32, 64
 LOSS_ABS, LOSS_MSE = 0, 1
 RESET_SAME_PATH, RESET_FROM_ARRAY, RESET_PHILOX = 0, 1, 2
+STEP_KEEP_OBS_IN_L2 = 1
 INFO_F64_KEYS = (
     "step_pnl_total", "per_share_step_pnl", "raw_pnl_deviation_abs", "transaction_costs_total",
     "commission_cost", "slippage_cost", "reward_pnl_component", "transaction_cost_penalty", "theta_penalty",
@@ -54,7 +55,7 @@ class EnvState(C.Structure):
 
 
 class ResetRule(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("next_path", C.c_void_p),
+    _fields_ = [("mode", C.c_int32), ("flags", C.c_int32), ("next_path", C.c_void_p),
                 ("seed", C.c_uint64), ("env_offset", C.c_int64), ("episode_counter", C.c_int64)]
 
 

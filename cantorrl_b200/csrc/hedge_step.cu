@@ -72,16 +72,16 @@ __device__ __forceinline__ int next_episode_path(const ResetRule& rr, const Book
 
 // Stage a CTA's observation rows in shared memory, then store the contiguous tile.
 __device__ __forceinline__ void store_obs_tile(float* __restrict__ obs, const float* tile, long long first_env,
-                                               int rows, bool use_tma) {
+                                               int rows, bool use_tma, bool keep_in_l2) {
     if (use_tma) {
         fence_proxy_async_smem();
         __syncthreads();
         if (threadIdx.x == 0) {
 #if CANTOR_OBS_EVICT_FIRST
-            tma_store_1d_evict_first(obs + first_env * CANTOR_OBS_DIM, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
-#else
-            tma_store_1d(obs + first_env * CANTOR_OBS_DIM, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
+            if (!keep_in_l2) tma_store_1d_evict_first(obs + first_env * CANTOR_OBS_DIM, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
+            else
 #endif
+            tma_store_1d(obs + first_env * CANTOR_OBS_DIM, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
             tma_store_commit();
             tma_store_wait_read();
         }
@@ -299,7 +299,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
     } else {
         pdl_launch_dependents();
     }
-    store_obs_tile(obs, tile, first_env, rows, obs_tma_ok && (rows % 4 == 0));
+    store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
     if (MON) {
         // finished episodes -> statistics vector: warp shuffle -> shared -> one atomic per statistic per CTA, only on the
         // steps where some env of this CTA finished (block-uniform vote, so the barrier inside is safe)
@@ -435,7 +435,7 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
         float* obs_t = obs + (size_t)t * n_envs * CANTOR_OBS_DIM;
         void* rew_t = (char*)reward + (size_t)t * n_envs * reward_bytes;
         unsigned char* done_t = done + (size_t)t * n_envs;
-        int tma_ok = aligned16(obs_t) ? 1 : 0;
+        int tma_ok = (aligned16(obs_t) ? 1 : 0) | ((reset_rule != nullptr && (reset_rule->flags & CANTOR_STEP_KEEP_OBS_IN_L2)) ? 2 : 0);
         void* args[] = {&k, &b, &core, &cash, &pv, &n, &a_t, &obs_t, &rew_t, &done_t, &terminal_obs, &auto_reset,
                         &rr, &io, &tma_ok, &mon};
         const void* fn;

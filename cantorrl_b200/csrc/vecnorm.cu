@@ -243,17 +243,6 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
                     }
             }
         }
-        if (terminal_obs != nullptr) {                                           // rows of envs that just finished (rare)
-            for (long long cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
-                const long long base = cc * kVnRows;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (base + cm.row[j] < n && done[base + cm.row[j]]) {
-                        float* p = terminal_obs + base * kVnCols + 4 * threadIdx.x + j;
-                        *p = norm1(*p, j);
-                    }
-            }
-        }
     }
     if (threadIdx.x < kVnRows) {
         for (long long cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
@@ -268,7 +257,15 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
                     *r = (float)fmin(fmax((double)*r * rinv, -clip_reward), clip_reward);
                 }
             }
-            if (done[i]) returns[i] = 0.0;
+            if (done[i]) {
+                returns[i] = 0.0;
+                if (norm_obs && terminal_obs != nullptr) {                       // the finished env's pre-reset observation (rare: whole row here)
+                    float* row = terminal_obs + i * kVnCols;
+#pragma unroll
+                    for (int j = 0; j < kVnCols; ++j)
+                        row[j] = fminf(fmaxf((float)((double)row[j] - rms[kObsMean + j]) * (float)rms[kDerived + j], lo), hi);
+                }
+            }
         }
     }
 }

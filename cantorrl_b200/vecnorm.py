@@ -35,6 +35,8 @@ class VecNormalize:
         self.training, self.norm_obs, self.norm_reward = bool(training), bool(norm_obs), bool(norm_reward)
         self.clip_obs, self.clip_reward, self.gamma, self.epsilon = float(clip_obs), float(clip_reward), float(gamma), float(epsilon)
         self.device = venv.device
+        if hasattr(venv, "_rule"):          # the observations are read again on the device right away: keep them in L2
+            venv._rule.flags |= _lib.STEP_KEEP_OBS_IN_L2
         self._rms = torch.zeros(_lib.VECNORM_DOUBLES, dtype=torch.float64, device=self.device)
         self.returns = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):

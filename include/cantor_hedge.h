@@ -103,9 +103,13 @@ typedef struct cantor_env_state {
     const struct cantor_stats_out* stats;  /* or NULL: finished episodes are reduced (warp -> block -> atomics) into it */
 } cantor_env_state;
 
+/* cantor_reset_rule.flags */
+#define CANTOR_STEP_KEEP_OBS_IN_L2 1   /* store the observations with the normal L2 policy because a device-side consumer (policy
+                                          network, cantor_vecnorm_step) reads them next; default: evict-first, which is faster for
+                                          the step itself when the observations leave for the host or for a later kernel */
 typedef struct cantor_reset_rule {
     int32_t mode;              /* CANTOR_RESET_* */
-    int32_t reserved;
+    int32_t flags;             /* CANTOR_STEP_* bits */
     const int32_t* next_path;  /* [n_envs] for FROM_ARRAY, else NULL */
     uint64_t seed;             /* PHILOX key */
     int64_t env_offset;        /* global index of local env 0 (rank * n_envs): results independent of GPU count */
