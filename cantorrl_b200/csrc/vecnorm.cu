@@ -302,14 +302,21 @@ extern "C" int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs,
     const int f64 = reward_precision == CANTOR_F64;
     const long long n_chunks = (n + kVnRows - 1) / kVnRows;
     // grid-stride over chunks of 128 envs with exactly one resident wave: SMs x (CTAs that fit per SM), so no partial tail wave
-    static int occ_moments = 0, occ_apply = 0, n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        CANTOR_CUDA(cudaGetDevice(&dev));
-        CANTOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_moments, vecnorm_moments_kernel, kVnThreads, 0));
-        CANTOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_apply, vecnorm_apply_kernel, kVnThreads, 0));
-        CANTOR_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    // (cached per device: the query costs microseconds and this runs every env-step)
+    static int occ_cache[64][3];                                             // [device] = {CTAs/SM moments, CTAs/SM apply, SM count}
+    int dev = 0;
+    CANTOR_CUDA(cudaGetDevice(&dev));
+    CANTOR_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    if (occ_cache[dev][2] == 0) {
+        int om = 0, oa = 0, sm = 0;
+        CANTOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&om, vecnorm_moments_kernel, kVnThreads, 0));
+        CANTOR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, vecnorm_apply_kernel, kVnThreads, 0));
+        CANTOR_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+        occ_cache[dev][0] = om;
+        occ_cache[dev][1] = oa;
+        occ_cache[dev][2] = sm;                                              // written last: a racing thread recomputes the same values
     }
+    const int occ_moments = occ_cache[dev][0], occ_apply = occ_cache[dev][1], n_sm = occ_cache[dev][2];
     const long long cap_m = (long long)n_sm * (occ_moments > 0 ? occ_moments : 1), cap_a = (long long)n_sm * (occ_apply > 0 ? occ_apply : 1);
     const unsigned grid = (unsigned)(n_chunks < cap_m ? n_chunks : (cap_m < kVnMaxGrid ? cap_m : kVnMaxGrid));
     const unsigned grid_apply = (unsigned)(n_chunks < cap_a ? n_chunks : cap_a);
