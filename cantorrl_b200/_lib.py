@@ -78,7 +78,8 @@ class RbergomiParams(C.Structure):
                 ("seed", C.c_uint64), ("path_offset", C.c_int64)]
 
 
-POLICY_NO_HEDGE, POLICY_RANDOM, POLICY_DELTA_BASELINES, POLICY_DELTA_BENCHMARK, POLICY_MLP, POLICY_ACTIONS = range(6)
+POLICY_NO_HEDGE, POLICY_RANDOM, POLICY_DELTA_BASELINES, POLICY_DELTA_BENCHMARK, POLICY_MLP, POLICY_ACTIONS, POLICY_LSTM = range(7)
+LSTM_IMAGE_BYTES = 178816
 MLP_FLOATS = 5212
 STATS_LEN = 16
 VECNORM_DOUBLES = 16704

@@ -13,6 +13,7 @@
 //   MLP actor 13-64-64-2          quantconnect/model_wrapper.py:131,177-185 (normalise, ReLU MLP, clip)
 // and the env step itself (hedge_core.cuh).
 #include "hedge_core.cuh"
+#include "lstm_tc.cuh"
 #include "mlp_tc.cuh"
 #include "sim_core.cuh"
 
@@ -126,8 +127,8 @@ __device__ __noinline__ float2 policy_mlp(const float* o, const float* __restric
 
 // SRC: 0 replay (packed book), 1 GBM on the fly, 2 Heston on the fly.
 // MLP: 0 = one of the closed-form / tabulated policies, 1 = the MLP actor in float32 FFMAs (parity form),
-//      2 = the MLP actor on the tensor cores (bf16 tcgen05.mma, mlp_tc.cuh); compile-time, so the other policies do not
-//      pay for its registers and shared memory.
+//      2 = the MLP actor on the tensor cores (bf16 tcgen05.mma, mlp_tc.cuh), 3 = the recurrent LSTM + MLP actor on the
+//      tensor cores (lstm_tc.cuh); compile-time, so the other policies do not pay for its registers and shared memory.
 template <int SRC, int MLP, bool WRITE>
 __global__ void __launch_bounds__(kRollThreads)
 rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const PolicyConsts pc, long long n_envs,
@@ -135,10 +136,12 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                int obs_tma_ok, int share_quote) {
     extern __shared__ __align__(128) float smem_f[];
     float* w_mlp = smem_f;                                                     // [kMlpFloats] float32 weights (MLP == 1)
-    constexpr int mlp_floats = MLP == 1 ? (kMlpFloats + 3) / 4 * 4 : (MLP == 2 ? mlptc::kSmemBytes / 4 : 0);
+    constexpr int mlp_floats = MLP == 1 ? (kMlpFloats + 3) / 4 * 4 : (MLP == 2 ? mlptc::kSmemBytes / 4 : (MLP == 3 ? lstmtc::kSmemBytes / 4 : 0));
     float* tile = smem_f + mlp_floats;                                         // [kRollThreads * 13] when WRITE
     double* red = reinterpret_cast<double*>(tile + (WRITE ? kRollThreads * CANTOR_OBS_DIM : 0));
     mlptc::Actor actor;
+    lstmtc::Actor lstm;
+    if (MLP == 3) lstm.setup(reinterpret_cast<unsigned char*>(smem_f), reinterpret_cast<const unsigned char*>(pc.mlp));
     if (MLP == 1) {
         for (int j = threadIdx.x; j < kMlpFloats; j += kRollThreads) w_mlp[j] = pc.mlp[j];
     }
@@ -202,7 +205,9 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             if (SRC != 0 && share_quote) make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y, gk);
             else make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y);
             float2 a;
-            if (MLP == 2) {
+            if (MLP == 3) {
+                a = lstm.forward(o);                                           // CTA-collective; carries h, c across steps
+            } else if (MLP == 2) {
                 a = actor.forward(o);                                          // CTA-collective: all 128 threads, every step
             } else if (MLP == 1) {
                 a = policy_mlp(o, w_mlp);
@@ -281,6 +286,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                 }
                 ++episode;
                 begin_episode();
+                if (MLP == 3) lstm.reset_state();                              // SB3 zeroes the LSTM state at an episode start
                 break;                                                         // the new path starts a new Philox call
             }
         }
@@ -291,6 +297,10 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
     if (MLP == 2) {
         if (actor.timed_out && st.sums != nullptr) atomicAdd(st.sums + 15, 1.0);   // an MMA never completed: results are invalid
         actor.teardown();
+    }
+    if (MLP == 3) {
+        if (lstm.timed_out && st.sums != nullptr) atomicAdd(st.sums + 15, 1.0);
+        lstm.teardown();
     }
     // fused all-reduce: the last CTA adds this launch's statistics into every rank's global block (NVLS multimem.red / peer atomics)
     push_statistics_to_all_ranks<kRollThreads>(st);
@@ -307,8 +317,9 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
     CANTOR_REQUIRE(params != nullptr && policy != nullptr, "params/policy is NULL");
     CANTOR_REQUIRE((book != nullptr) != (sim != nullptr), "exactly one of book / sim must be given");
     CANTOR_REQUIRE(n_envs > 0 && n_steps >= 0 && total_envs >= n_envs && env_offset >= 0, "bad sizes");
-    CANTOR_REQUIRE(policy->kind >= CANTOR_POLICY_NO_HEDGE && policy->kind <= CANTOR_POLICY_ACTIONS, "policy kind");
-    CANTOR_REQUIRE(policy->kind != CANTOR_POLICY_MLP || policy->mlp != nullptr, "policy.mlp is NULL");
+    CANTOR_REQUIRE(policy->kind >= CANTOR_POLICY_NO_HEDGE && policy->kind <= CANTOR_POLICY_LSTM, "policy kind");
+    CANTOR_REQUIRE((policy->kind != CANTOR_POLICY_MLP && policy->kind != CANTOR_POLICY_LSTM) || policy->mlp != nullptr, "policy.mlp is NULL");
+    CANTOR_REQUIRE(policy->kind != CANTOR_POLICY_LSTM || aligned16(policy->mlp), "the LSTM weight image must be 16-byte aligned");
     CANTOR_REQUIRE(policy->kind != CANTOR_POLICY_ACTIONS || policy->actions != nullptr, "policy.actions is NULL");
     StepConsts k;
     Book b{nullptr, 0, 1};
@@ -340,18 +351,26 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
     }
     if (n_steps == 0) return CANTOR_OK;
     const unsigned grid = (unsigned)((n_envs + kRollThreads - 1) / kRollThreads);
-    const int mlp_mode = policy->kind != CANTOR_POLICY_MLP ? 0 : (policy->mlp_tensor_cores ? 2 : 1);
-    const size_t smem = (mlp_mode == 1 ? (kMlpFloats + 3) / 4 * 4 * sizeof(float) : (mlp_mode == 2 ? (size_t)mlptc::kSmemBytes : 0)) +
+    const int mlp_mode = policy->kind == CANTOR_POLICY_LSTM ? 3 : (policy->kind != CANTOR_POLICY_MLP ? 0 : (policy->mlp_tensor_cores ? 2 : 1));
+    const size_t smem = (mlp_mode == 1 ? (kMlpFloats + 3) / 4 * 4 * sizeof(float)
+                         : (mlp_mode == 2 ? (size_t)mlptc::kSmemBytes : (mlp_mode == 3 ? (size_t)lstmtc::kSmemBytes : 0))) +
                         (write ? kRollThreads * CANTOR_OBS_DIM * sizeof(float) : 0) + 11 * (kRollThreads / 32) * sizeof(double) + 16;
     const int tma_ok = write && aligned16(out->obs) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     // the observation's greeks can ride on the price evaluation when the env and the simulator agree on (r, tenor)
     const int share = (src != 0 && params->record_metrics && k.g.r_f == sk.r && k.g.T_f == sk.tenor && sk.tenor > 1e-6f) ? 1 : 0;
-#define LAUNCH(SRC, MLP, WRITE) \
-    rollout_kernel<SRC, MLP, WRITE><<<grid, kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok, share)
+#define LAUNCH(SRC, MLP, WRITE)                                                                                                         \
+    do {                                                                                                                             \
+        if (smem > 48 * 1024) {                                                                                                      \
+            cudaError_t e_ = cudaFuncSetAttribute(rollout_kernel<SRC, MLP, WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e_ != cudaSuccess) return cuda_fail(e_, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");                         \
+        }                                                                                                                            \
+        rollout_kernel<SRC, MLP, WRITE><<<grid, kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok, share); \
+    } while (0)
 #define LAUNCH_SRC(SRC)                                                      \
     do {                                                                     \
-        if (mlp_mode == 2) { if (write) LAUNCH(SRC, 2, true); else LAUNCH(SRC, 2, false); }      \
+        if (mlp_mode == 3) { if (write) LAUNCH(SRC, 3, true); else LAUNCH(SRC, 3, false); }      \
+        else if (mlp_mode == 2) { if (write) LAUNCH(SRC, 2, true); else LAUNCH(SRC, 2, false); } \
         else if (mlp_mode == 1) { if (write) LAUNCH(SRC, 1, true); else LAUNCH(SRC, 1, false); } \
         else { if (write) LAUNCH(SRC, 0, true); else LAUNCH(SRC, 0, false); }                    \
     } while (0)

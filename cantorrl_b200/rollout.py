@@ -52,6 +52,63 @@ def pack_mlp(W1, b1, W2, b2, W3, b3, obs_mean=None, obs_var=None, epsilon=1e-8, 
     return flat.to(device)
 
 
+def _bf16_bits(x: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 bit patterns (round to nearest even) as uint16."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
+
+
+def _umma_tile(mat: np.ndarray) -> np.ndarray:
+    """[rows, K] float32 (rows % 8 == 0, K % 8 == 0) -> the bf16 byte image of the canonical K-major no-swizzle UMMA layout:
+    element (r, k) at (r // 8) * (K // 8) * 128 + (k // 8) * 128 + (r % 8) * 16 + (k % 8) * 2 (csrc/mlp_tc.cuh)."""
+    rows, K = mat.shape
+    bits = _bf16_bits(mat).reshape(rows // 8, 8, K // 8, 8)          # [row group, row in group, k chunk, k in chunk]
+    return np.ascontiguousarray(bits.transpose(0, 2, 1, 3)).reshape(-1).view(np.uint8)
+
+
+def pack_lstm(w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b2, W3, b3, obs_mean=None, obs_var=None, epsilon=1e-8, device="cuda") -> torch.Tensor:
+    """Weights of the recurrent actor in ``torch.nn`` layout -> the byte image ``cantor_policy.mlp`` wants for
+    ``CANTOR_POLICY_LSTM`` (csrc/lstm_tc.cuh).
+
+    ``w_ih [512, 13]``, ``w_hh [512, 128]``, ``b_ih``, ``b_hh [512]`` as ``torch.nn.LSTM`` stores them (gate order i, f, g, o);
+    head ``W1 [64, 128]``, ``W2 [64, 64]``, ``W3 [2, 64]`` + biases (``mlp_extractor.policy_net.*`` / ``action_net.*`` of the
+    shipped ``policy_weights.pth``); ``obs_mean`` / ``obs_var``: VecNormalize statistics.  Biases are folded onto a ones column.
+    """
+    f = lambda x, shape: _check(np.asarray(x.detach().cpu() if isinstance(x, torch.Tensor) else x, np.float32), shape)  # noqa: E731
+
+    def _check(a, shape):
+        if a.shape != shape:
+            raise ValueError(f"expected shape {shape}, got {a.shape}")
+        return a
+    w_ih, w_hh = f(w_ih, (512, 13)), f(w_hh, (512, 128))
+    bias = f(b_ih, (512,)) + f(b_hh, (512,))
+    W1, b1, W2, b2, W3, b3 = f(W1, (64, 128)), f(b1, (64,)), f(W2, (64, 64)), f(b2, (64,)), f(W3, (2, 64)), f(b3, (2,))
+    parts = []
+    for p in range(4):                                                # pass p = hidden units 32 p .. 32 p + 31, rows {i, f, g, o} x 32
+        tile = np.zeros((128, 144), np.float32)
+        for g in range(4):
+            rows = slice(g * 128 + 32 * p, g * 128 + 32 * p + 32)
+            tile[g * 32:(g + 1) * 32, 0:13] = w_ih[rows]
+            tile[g * 32:(g + 1) * 32, 13] = bias[rows]
+            tile[g * 32:(g + 1) * 32, 16:144] = w_hh[rows]
+        parts.append(_umma_tile(tile))
+    t1 = np.zeros((64, 144), np.float32)
+    t1[:, 13], t1[:, 16:144] = b1, W1
+    t2 = np.zeros((64, 80), np.float32)
+    t2[:, :64], t2[:, 64] = W2, b2
+    t3 = np.zeros((16, 80), np.float32)
+    t3[:2, :64], t3[:2, 64] = W3, b3
+    parts += [_umma_tile(t1), _umma_tile(t2), _umma_tile(t3)]
+    norm = np.zeros(32, np.float32)
+    norm[16:29] = 1.0
+    if obs_mean is not None:
+        norm[:13] = np.asarray(obs_mean, np.float32)
+        norm[16:29] = (1.0 / np.sqrt(np.asarray(obs_var, np.float64) + epsilon)).astype(np.float32)
+    img = np.concatenate(parts + [norm.view(np.uint8)])
+    assert img.size == _lib.LSTM_IMAGE_BYTES
+    return torch.from_numpy(img).to(device)
+
+
 @dataclass
 class RolloutResult:
     stats: EpisodeStats
@@ -133,6 +190,7 @@ class HedgingRollout:
         policy   "no_hedge" | "random" | "delta_every_step" | "delta_benchmark" | "actions" (open loop, ``actions``
                  float32 ``[n_steps, num_envs, 2]`` on the device) | "mlp" (``mlp=pack_mlp(...)``; float32 FFMA actor,
                  the parity form) | "mlp_bf16" (same weights on the tensor cores: bf16 operands, float32 accumulation)
+                 | "lstm_bf16" (``mlp=pack_lstm(...)``: the recurrent LSTM + MLP actor the reference trained, tensor cores)
         store    also write the rollout (obs the policy saw, actions, reward, done), time-major
         """
         n, dev = self.num_envs, self.device
@@ -144,6 +202,10 @@ class HedgingRollout:
             if mlp is None or mlp.dtype != torch.float32 or mlp.numel() != _lib.MLP_FLOATS or mlp.device != dev:
                 raise ValueError("policy='mlp' needs mlp=pack_mlp(...) on the rollout's device")
             pol.kind, pol.mlp = _lib.POLICY_MLP, mlp.data_ptr()
+        elif policy == "lstm_bf16":
+            if mlp is None or mlp.dtype != torch.uint8 or mlp.numel() != _lib.LSTM_IMAGE_BYTES or mlp.device != dev:
+                raise ValueError("policy='lstm_bf16' needs mlp=pack_lstm(...) on the rollout's device")
+            pol.kind, pol.mlp = _lib.POLICY_LSTM, mlp.data_ptr()
         elif policy == "actions":
             if actions is None or actions.dtype != torch.float32 or tuple(actions.shape) != (n_steps, n, 2) \
                     or not actions.is_contiguous() or actions.device != dev:

@@ -299,8 +299,12 @@ enum {
     CANTOR_POLICY_DELTA_BASELINES = 2,   /* policy_delta_every_step, baselines.py:77-103 */
     CANTOR_POLICY_DELTA_BENCHMARK = 3,   /* delta_hedging_action_selector, delta_and_nothing.py:122-163 */
     CANTOR_POLICY_MLP = 4,               /* ReLU MLP 13-64-64-2 on the normalised obs, output clipped to [-1, 1] */
-    CANTOR_POLICY_ACTIONS = 5            /* open-loop: actions[step, env, 2] */
+    CANTOR_POLICY_ACTIONS = 5,           /* open-loop: actions[step, env, 2] */
+    CANTOR_POLICY_LSTM = 6               /* LSTM(13 -> 128) -> ReLU MLP(128 -> 64 -> 64) -> 2 on the tensor cores (bf16): the policy the
+                                            reference trained (quantconnect/model_wrapper.py:167-204); cantor_policy.mlp = the
+                                            CANTOR_LSTM_IMAGE_BYTES weight image (cantorrl_b200/rollout.py: pack_lstm) */
 };
+#define CANTOR_LSTM_IMAGE_BYTES 178816   /* 4 gate tiles [128 x 144] + W1 [64 x 144] + W2 [64 x 80] + W3 [16 x 80] bf16 + mean / inv_std */
 #define CANTOR_MLP_FLOATS 5212           /* W1[13][64] b1[64] W2[64][64] b2[64] W3[64][2] b3[2] obs_mean[13] obs_inv_std[13] */
 typedef struct cantor_policy {
     int32_t kind;                        /* CANTOR_POLICY_* */

@@ -79,6 +79,45 @@ def mlp_actor_bf16(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-
     return np.clip(out, -1, 1).astype(F32)
 
 
+def lstm_actor_sequence(obs_seq, done_seq, w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8,
+                        bf16=True):
+    """The recurrent actor LSTM(13 -> 128) -> ReLU MLP(128 -> 64 -> 64) -> 2 (quantconnect/model_wrapper.py:167-204) over an
+    observation sequence ``[n_steps, n_envs, 13]``; the state (h, c) of an env is zeroed after a step on which it finished
+    (``done_seq [n_steps, n_envs]``), as SB3 does at episode starts.  ``torch.nn.LSTM`` weight layout, gate order i, f, g, o.
+
+    ``bf16=True`` follows the rounding points of cantorrl_b200/csrc/lstm_tc.cuh (inputs, weights, biases, h and the head's
+    activations in bfloat16; products accumulated wide; c in float32); ``bf16=False`` is the plain float64 network.
+    """
+    q = _bf16 if bf16 else (lambda a: np.asarray(a, np.float64))
+    n_steps, n, _ = obs_seq.shape
+    wi, wh, bb = q(w_ih).astype(np.float64), q(w_hh).astype(np.float64), q(np.asarray(b_ih, F32) + np.asarray(b_hh, F32)).astype(np.float64)
+    A1, c1 = q(W1).astype(np.float64), q(b1).astype(np.float64)
+    A2, c2 = q(W2).astype(np.float64), q(b2).astype(np.float64)
+    A3, c3 = q(W3).astype(np.float64), q(b3).astype(np.float64)
+    h = np.zeros((n, 128))
+    c = np.zeros((n, 128))
+    out = np.zeros((n_steps, n, 2), F32)
+    sig = lambda z: 1.0 / (1.0 + np.exp(-z))  # noqa: E731
+    for t in range(n_steps):
+        x = np.asarray(obs_seq[t], F32)
+        if mean is not None:
+            inv = (1.0 / np.sqrt(np.asarray(var, np.float64) + epsilon)).astype(F32)
+            x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-10), F32(10))
+        g = q(x).astype(np.float64) @ wi.T + q(h.astype(F32)).astype(np.float64) @ wh.T + bb
+        gi, gf, gg, go = g[:, 0:128], g[:, 128:256], g[:, 256:384], g[:, 384:512]
+        c = (sig(gf) * c + sig(gi) * np.tanh(gg)).astype(F32).astype(np.float64) if bf16 else sig(gf) * c + sig(gi) * np.tanh(gg)
+        h = sig(go) * np.tanh(c)
+        hq = q(h.astype(F32)).astype(np.float64)
+        a1 = np.maximum(hq @ A1.T + c1, 0)
+        a2 = np.maximum(q(a1.astype(F32)).astype(np.float64) @ A2.T + c2, 0)
+        o = q(a2.astype(F32)).astype(np.float64) @ A3.T + c3
+        out[t] = np.clip(o, -1, 1)
+        fin = np.asarray(done_seq[t], bool)
+        h[fin] = 0
+        c[fin] = 0
+    return out
+
+
 def run_rollout(paths, vols, calls, puts, params: EnvParams, policy, n_envs, n_steps, env_offset=0, total_envs=None,
                 forced_actions=None, one_call_only=False, seed=0, mlp=None):
     """Free-running (or, with ``forced_actions`` [n_steps, n_envs, 2], teacher-forced) rollout of the oracle env.

@@ -165,3 +165,42 @@ def test_rollout_argument_errors():
     with pytest.raises(FileNotFoundError):
         HedgingRollout(num_envs=4)
     assert issubclass(CantorError, RuntimeError)
+
+
+def _lstm_weights(seed=3):
+    g = np.random.default_rng(seed)
+    k = 1 / np.sqrt(128)
+    return dict(w_ih=g.uniform(-k, k, (512, 13)).astype(np.float32) * 3, w_hh=g.uniform(-k, k, (512, 128)).astype(np.float32) * 2,
+                b_ih=g.uniform(-k, k, 512).astype(np.float32), b_hh=g.uniform(-k, k, 512).astype(np.float32),
+                W1=g.normal(0, 0.15, (64, 128)).astype(np.float32), b1=g.normal(0, 0.1, 64).astype(np.float32),
+                W2=g.normal(0, 0.2, (64, 64)).astype(np.float32), b2=g.normal(0, 0.1, 64).astype(np.float32),
+                W3=g.normal(0, 0.3, (2, 64)).astype(np.float32), b3=g.normal(0, 0.1, 2).astype(np.float32))
+
+
+def test_recurrent_lstm_actor_matches_oracle_over_episodes():
+    """The tensor-core LSTM + MLP actor inside the rollout: env parity teacher-forced on its own actions, and the actions
+    themselves against the oracle network run over the kernel's observation sequence (state reset at episode ends)."""
+    from cantorrl_b200.rollout import HedgingRollout, pack_lstm
+    n_paths, T, n_envs, n_steps = 61, 12, 203, 41
+    S, V, C, P = _book(n_paths, T, heston=True)
+    w = _lstm_weights()
+    g = np.random.default_rng(1)
+    mean, var = g.normal(0, 0.2, 13).astype(np.float32), g.uniform(0.05, 2.0, 13).astype(np.float32)
+    ro = HedgingRollout(data=dict(paths=S, volatilities=V, call_prices_atm=C, put_prices_atm=P), num_envs=n_envs, **KW)
+    stats = ro.new_stats()
+    res = ro.run(n_steps, "lstm_bf16", mlp=pack_lstm(**w, obs_mean=mean, obs_var=var), stats=stats, store=True)
+    torch.cuda.synchronize()
+    assert float(stats.sums[15]) == 0.0, "a tcgen05 MMA timed out"
+    got = {k: getattr(res, k).cpu().numpy() for k in ("obs", "actions", "reward", "done")}
+    ref = rollout_oracle.run_rollout(S, V, C, P, EnvParams(**KW), "actions", n_envs, n_steps, forced_actions=got["actions"])
+    assert np.array_equal(got["done"], ref["done"])
+    np.testing.assert_allclose(got["obs"], ref["obs"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(got["reward"], ref["reward"], rtol=1e-4, atol=1e-7)
+    want = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=mean, var=var, bf16=True)
+    err = np.abs(got["actions"] - want)
+    # bf16 operands + tanh.approx (2^-11 relative) through a 12-step recurrence
+    assert err.max() < 3e-2 and err.mean() < 2e-3, (err.max(), err.mean())
+    full = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=mean, var=var, bf16=False)
+    assert np.abs(got["actions"] - full).max() < 0.15 and np.abs(got["actions"] - full).mean() < 1e-2
+    assert np.abs(want).mean() > 0.05                     # the network is not saturated / trivially zero
+    assert stats.sums[0] == n_envs * (n_steps // T)
