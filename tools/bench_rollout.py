@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cantorrl_b200 import sim  # noqa: E402
-from cantorrl_b200.rollout import HedgingRollout, pack_mlp  # noqa: E402
+from cantorrl_b200.rollout import HedgingRollout, pack_lstm, pack_mlp  # noqa: E402
 
 KW = dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3, lambda_cost=1e-4)
 
@@ -27,6 +27,10 @@ def main():
     g = np.random.default_rng(0)
     w = pack_mlp(g.normal(0, .5, (64, 13)), g.normal(0, .1, 64), g.normal(0, .2, (64, 64)), g.normal(0, .1, 64),
                  g.normal(0, .3, (2, 64)), g.normal(0, .1, 2), g.normal(0, .2, 13), g.uniform(.05, 2, 13))
+    kk = 1 / np.sqrt(128)
+    wl = pack_lstm(g.uniform(-kk, kk, (512, 13)) * 3, g.uniform(-kk, kk, (512, 128)) * 2, g.uniform(-kk, kk, 512), g.uniform(-kk, kk, 512),
+                   g.normal(0, .15, (64, 128)), g.normal(0, .1, 64), g.normal(0, .2, (64, 64)), g.normal(0, .1, 64),
+                   g.normal(0, .3, (2, 64)), g.normal(0, .1, 2), g.normal(0, .2, 13), g.uniform(.05, 2, 13))
     out = {}
     for src in a.sources.split(","):
         if src == "replay":
@@ -36,12 +40,12 @@ def main():
             ro = HedgingRollout(simulate=dict(model=src, n_steps=252), num_envs=a.envs, **KW)
         for pol in a.policies.split(","):
             st = ro.new_stats()
-            ro.run(a.steps, pol, mlp=w, stats=st, store=a.store)
+            ro.run(a.steps, pol, mlp=wl if pol == "lstm_bf16" else w, stats=st, store=a.store)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(a.reps):
-                ro.run(a.steps, pol, mlp=w, stats=st, store=a.store)
+                ro.run(a.steps, pol, mlp=wl if pol == "lstm_bf16" else w, stats=st, store=a.store)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.reps
