@@ -215,7 +215,7 @@ __device__ __forceinline__ void block_accumulate(double (&v)[NS], double* __rest
         for (int off = 16; off > 0; off >>= 1) v[s] += __shfl_down_sync(0xffffffffu, v[s], off);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) {
+    if (lane == 0 && warp < THREADS / 32) {                    // a CTA may carry extra warps that hold no values
 #pragma unroll
         for (int s = 0; s < NS; ++s) smem[s * (THREADS / 32) + warp] = v[s];
     }

@@ -129,8 +129,9 @@ __device__ __noinline__ float2 policy_mlp(const float* o, const float* __restric
 // MLP: 0 = one of the closed-form / tabulated policies, 1 = the MLP actor in float32 FFMAs (parity form),
 //      2 = the MLP actor on the tensor cores (bf16 tcgen05.mma, mlp_tc.cuh), 3 = the recurrent LSTM + MLP actor on the
 //      tensor cores (lstm_tc.cuh); compile-time, so the other policies do not pay for its registers and shared memory.
+//      The recurrent form runs with a fifth warp that only issues MMAs / TMA copies (lstmtc::Actor::issuer_loop).
 template <int SRC, int MLP, bool WRITE>
-__global__ void __launch_bounds__(kRollThreads)
+__global__ void __launch_bounds__(MLP == 3 ? lstmtc::kThreads : kRollThreads)
 rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const PolicyConsts pc, long long n_envs,
                long long env_offset, long long total_envs, int n_steps, const StatsOut st, const RolloutOut out,
                int obs_tma_ok, int share_quote) {
@@ -148,9 +149,15 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
     if (MLP == 2) actor.setup(reinterpret_cast<unsigned char*>(smem_f), pc.mlp);
     __syncthreads();
 
+    constexpr int kThreads = MLP == 3 ? lstmtc::kThreads : kRollThreads;
+    const bool env_thread = MLP != 3 || threadIdx.x < kRollThreads;            // the others: the recurrent actor's issuer warp
+    auto env_sync = [&]() {                                                    // barrier of the env threads only
+        if (MLP == 3) lstmtc::env_sync();
+        else __syncthreads();
+    };
     const long long first_env = (long long)blockIdx.x * kRollThreads;
     const long long i = first_env + threadIdx.x;
-    const bool live = i < n_envs;
+    const bool live = env_thread && i < n_envs;
     const int rows = (int)min((long long)kRollThreads, n_envs - first_env);
     const unsigned long long genv = (unsigned long long)(env_offset + (live ? i : 0));
     constexpr int MODEL = SRC == 2 ? 1 : 0;
@@ -190,13 +197,14 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
         t = 0;
         acc_pps = acc_abs = acc_cost = acc_reward = 0.f;
     };
-    begin_episode();
+    if (env_thread) begin_episode();
+    if (MLP == 3 && !env_thread) lstm.issuer_loop(n_steps, k.T);
 
-    int g = 0;                                                                 // global step of the rollout
+    int g = env_thread ? 0 : n_steps;                                          // global step of the rollout
     while (g < n_steps) {
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (SRC != 0) path_normals(sk, gp, (unsigned)((t * NPS) >> 2), z);
-#pragma unroll
+#pragma unroll(MLP == 3 ? 1 : STEPS_PER_CALL)            // the recurrent actor is instruction-cache bound: one copy of the step
         for (int j = 0; j < STEPS_PER_CALL; ++j) {
             if (g >= n_steps) break;
             // ---- observation of the current state and the policy's action --------------------------------
@@ -249,17 +257,17 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                 const bool tma = obs_tma_ok && (rows % 4 == 0) && ((((long long)g * n_envs) & 3) == 0);
                 if (tma) {
                     fence_proxy_async_smem();
-                    __syncthreads();
+                    env_sync();
                     if (threadIdx.x == 0) {
                         tma_store_1d_evict_first(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
                         tma_store_commit();
                         tma_store_wait_read();
                     }
-                    __syncthreads();
+                    env_sync();
                 } else {
-                    __syncthreads();
+                    env_sync();
                     for (int q = threadIdx.x; q < rows * CANTOR_OBS_DIM; q += kRollThreads) dst[q] = tile[q];
-                    __syncthreads();
+                    env_sync();
                 }
                 if (live) {
                     const long long at = (long long)g * n_envs + i;
@@ -292,7 +300,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
         }
     }
     // ---- one reduction at the end: warp shuffle -> shared -> one atomic per statistic per block ---------------
-    if (st.sums != nullptr) block_accumulate<11, kRollThreads>(stat, st.sums, red);
+    if (st.sums != nullptr) block_accumulate<11, kRollThreads>(stat, st.sums, red);   // warps beyond the env warps only join its barriers
     if (st.sums != nullptr && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(st.sums + 11, (double)n_envs * (double)n_steps);
     if (MLP == 2) {
         if (actor.timed_out && st.sums != nullptr) atomicAdd(st.sums + 15, 1.0);   // an MMA never completed: results are invalid
@@ -303,7 +311,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
         lstm.teardown();
     }
     // fused all-reduce: the last CTA adds this launch's statistics into every rank's global block (NVLS multimem.red / peer atomics)
-    push_statistics_to_all_ranks<kRollThreads>(st);
+    push_statistics_to_all_ranks<kThreads>(st);
 }
 
 }  // namespace cantor
@@ -365,7 +373,7 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
             cudaError_t e_ = cudaFuncSetAttribute(rollout_kernel<SRC, MLP, WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e_ != cudaSuccess) return cuda_fail(e_, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");                         \
         }                                                                                                                            \
-        rollout_kernel<SRC, MLP, WRITE><<<grid, kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok, share); \
+        rollout_kernel<SRC, MLP, WRITE><<<grid, MLP == 3 ? lstmtc::kThreads : kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok, share); \
     } while (0)
 #define LAUNCH_SRC(SRC)                                                      \
     do {                                                                     \

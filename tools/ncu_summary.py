@@ -52,3 +52,8 @@ for o, c in op.most_common(24):
     print(f"  {o:10s} {c:12d} {100.0 * c / max(tot, 1):5.1f}%  samples {samp[o]}")
 st = {k: sum(int(r[ci[k]] or 0) for r in body) for k in hdr if k.startswith("stall_") and "Not Issued" not in k}
 print("stall samples:", sorted(st.items(), key=lambda kv: -kv[1])[:8])
+
+# hottest SASS instructions by stall samples (with the CUDA source line when the build has -lineinfo)
+top = sorted(body, key=lambda r: -int(r[ci["# Samples"]] or 0))[:int(sys.argv[3]) if len(sys.argv) > 3 else 0]
+for r in top:
+    print(f"  {int(r[ci['# Samples']] or 0):7d}  {r[ci['Address']][-6:]}  {r[ci['Source']].strip()[:90]}")
