@@ -10,9 +10,11 @@
 //                 reward <- clip(reward / sqrt(ret_var + eps), +-clip_reward);  returns[done] <- 0
 //   RunningMeanStd.update(x): batch mean / population variance / count folded in with the parallel (Chan) formula,
 //                 initial mean 0, var 1, count 1e-4.
-// Three small kernels chained with programmatic dependent launch: batch moments (16-byte vector loads of 128-env chunks,
-// per-CTA partial sums, no atomics), the fold (fixed-order sum of the partials -> bitwise reproducible statistics, then
-// the Chan update), the in-place apply.  HBM-bound: 52 B read for the moments, 104 + ~18 B for the apply, per env-step.
+// Two kernels chained with programmatic dependent launch: batch moments (16-byte vector loads of 128-env chunks, per-CTA
+// partial sums, no atomics on the data) whose LAST CTA (atomic ticket) folds the partials in a fixed order -- bitwise
+// reproducible statistics whichever CTA that is -- and does the Chan update; then the in-place apply, which derives
+// 1 / sqrt(var + eps) itself and normalises in float32 against a two-float mean (no float64 conversions per element).
+// Memory-bound: 52 B read for the moments, 104 + ~18 B for the apply, per env-step (L2 hits right behind the step kernel).
 #include "common.cuh"
 
 namespace cantor {
@@ -21,7 +23,8 @@ constexpr int kVnCols = CANTOR_OBS_DIM;            // 13
 constexpr int kVnThreads = kVnCols * 32;           // 416: a thread's flat index keeps (index % 13) fixed across the stride
 // rms[] layout (doubles)
 constexpr int kObsMean = 0, kObsVar = 13, kObsCount = 26, kRetMean = 27, kRetVar = 28, kRetCount = 29;
-constexpr int kDerived = 32;                       // [32..46): derived values for the apply kernel: 1 / sqrt(var + eps) [13], return 1 / std
+constexpr int kDerived = 32;                       // [32..46): 1 / sqrt(var + eps) [13], return 1 / std (informational; the apply kernel derives its own)
+constexpr int kTicket = 56;                        // [56]: arrival counter of the moments kernel's CTAs (unsigned, zero between launches)
 constexpr int kPartial = 64;                       // [64, 64 + 28 * 592): per-CTA partial sums of the moments kernel, [statistic][CTA]
 
 constexpr int kVnRows = 128;                       // envs per chunk: 128 x 13 floats = 416 float4 = one float4 per thread
@@ -43,10 +46,11 @@ struct ChunkMap {
     }
 };
 
-__global__ void __launch_bounds__(kVnThreads, 3)
-vecnorm_moments_kernel(double* __restrict__ partial /* [kVnSums, gridDim.x] */, double* __restrict__ returns, long long n,
+__global__ void __launch_bounds__(kVnThreads, 2)
+vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, long long n,
                        const float* __restrict__ obs, const void* __restrict__ reward, int reward_f64, double gamma,
-                       int norm_obs, int norm_reward, int vec_ok) {
+                       int norm_obs, int norm_reward, int vec_ok, double epsilon) {
+    double* __restrict__ partial = rms + kPartial;                                   // [kVnSums, gridDim.x]
     __shared__ double part[8][kVnThreads];
     __shared__ double cols[kVnSums];
     const ChunkMap cm;
@@ -55,7 +59,7 @@ vecnorm_moments_kernel(double* __restrict__ partial /* [kVnSums, gridDim.x] */, 
     double rsum = 0.0, rsq = 0.0;
     const long long n_chunks = (n + kVnRows - 1) / kVnRows;
     const long long n_full = vec_ok ? n / kVnRows : 0;                               // chunks that move as whole float4 vectors
-    constexpr int U = 4;                                                             // independent 16-byte loads in flight per thread
+    constexpr int U = 8;                                                             // independent 16-byte loads in flight per thread
     long long c = blockIdx.x;
     if (norm_obs) {
         for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {
@@ -90,16 +94,33 @@ vecnorm_moments_kernel(double* __restrict__ partial /* [kVnSums, gridDim.x] */, 
             }
         }
     }
-    if (norm_reward && threadIdx.x < kVnRows) {                                      // discounted returns, one thread per env
-        for (long long cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
-            const long long i = cc * kVnRows + threadIdx.x;
-            if (i < n) {
-                const double r = reward_f64 ? reinterpret_cast<const double*>(reward)[i] : (double)reinterpret_cast<const float*>(reward)[i];
-                const double ret = fma(returns[i], gamma, r);
-                returns[i] = ret;
-                rsum += ret;
-                rsq = fma(ret, ret, rsq);
+    if (norm_reward) {                                                               // discounted returns: envs strided over the whole grid,
+        const long long stride = (long long)gridDim.x * kVnThreads;                 // R independent load pairs in flight per thread
+        long long i = (long long)blockIdx.x * kVnThreads + threadIdx.x;
+        constexpr int R = 4;
+        auto load_reward = [&](long long e) {
+            return reward_f64 ? __ldg(reinterpret_cast<const double*>(reward) + e) : (double)__ldg(reinterpret_cast<const float*>(reward) + e);
+        };
+        for (; i + (R - 1) * stride < n; i += R * stride) {
+            double ret[R], r[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                ret[u] = returns[i + u * stride];
+                r[u] = load_reward(i + u * stride);
             }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                ret[u] = fma(ret[u], gamma, r[u]);
+                returns[i + u * stride] = ret[u];
+                rsum += ret[u];
+                rsq = fma(ret[u], ret[u], rsq);
+            }
+        }
+        for (; i < n; i += stride) {
+            const double ret = fma(returns[i], gamma, load_reward(i));
+            returns[i] = ret;
+            rsum += ret;
+            rsq = fma(ret, ret, rsq);
         }
     }
     pdl_launch_dependents();
@@ -135,39 +156,42 @@ vecnorm_moments_kernel(double* __restrict__ partial /* [kVnSums, gridDim.x] */, 
         rsq += __shfl_down_sync(0xffffffffu, rsq, off);
     }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0 && threadIdx.x < kVnRows) part[0][threadIdx.x >> 5] = rsum, part[1][threadIdx.x >> 5] = rsq;
+    if ((threadIdx.x & 31) == 0) part[0][threadIdx.x >> 5] = rsum, part[1][threadIdx.x >> 5] = rsq;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        cols[2 * kVnCols] = part[0][0] + part[0][1] + part[0][2] + part[0][3];
-        cols[2 * kVnCols + 1] = part[1][0] + part[1][1] + part[1][2] + part[1][3];
+    if (threadIdx.x < 2) {                                                           // fixed order over the 13 warps
+        double a = 0.0;
+#pragma unroll
+        for (int q = 0; q < kVnThreads / 32; ++q) a += part[threadIdx.x][q];
+        cols[2 * kVnCols + threadIdx.x] = a;
     }
     __syncthreads();
     if (threadIdx.x < kVnSums) partial[(long long)threadIdx.x * gridDim.x + blockIdx.x] = cols[threadIdx.x];
-}
-
-// Sums the per-CTA partials in a fixed order (one warp per statistic), then RunningMeanStd.update_from_moments for each
-// observation column and for the returns.  One CTA of kVnSums warps.
-__global__ void __launch_bounds__(kVnSums * 32)
-vecnorm_fold_kernel(double* __restrict__ rms, const double* __restrict__ partial, int n_partial, long long n, double epsilon,
-                    int training, int norm_obs, int norm_reward) {
-    __shared__ double tot[kVnSums];
-    pdl_wait_prior_grid();
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double a = 0.0;
-    if (training)
-        for (int j = lane; j < n_partial; j += 32) a += partial[(long long)w * n_partial + j];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
-    if (lane == 0) tot[w] = a;
+    // ---- the last CTA to get here folds everybody's partials (fixed order) and updates the running statistics ----------
+    __shared__ int is_last;
+    __threadfence();
     __syncthreads();
-    pdl_launch_dependents();
+    unsigned* ticket = reinterpret_cast<unsigned*>(rms + kTicket);
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_partial = (int)gridDim.x;
+    for (int s = w; s < kVnSums; s += kVnThreads / 32) {                             // 13 warps, 28 statistics
+        double a = 0.0;
+        for (int j = lane; j < n_partial; j += 32) a += __ldcg(partial + (long long)s * n_partial + j);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_down_sync(0xffffffffu, a, off);
+        if (lane == 0) cols[s] = a;
+    }
+    __syncthreads();
     const int j = threadIdx.x;
     const double bc = (double)n;
     const double count = rms[kObsCount];
-    if (j < kVnCols) {
-        if (training && norm_obs) {
-            const double bmean = tot[j] / bc;
-            const double bvar = fmax(tot[kVnCols + j] / bc - bmean * bmean, 0.0);
+    if (j < kVnCols) {                                                               // RunningMeanStd.update_from_moments, per column
+        if (norm_obs) {
+            const double bmean = cols[j] / bc;
+            const double bvar = fmax(cols[kVnCols + j] / bc - bmean * bmean, 0.0);
             const double mean = rms[kObsMean + j], var = rms[kObsVar + j];
             const double t = count + bc, delta = bmean - mean;
             rms[kObsMean + j] = mean + delta * bc / t;
@@ -175,9 +199,9 @@ vecnorm_fold_kernel(double* __restrict__ rms, const double* __restrict__ partial
         }
         rms[kDerived + j] = 1.0 / sqrt(rms[kObsVar + j] + epsilon);
     } else if (j == kVnCols) {
-        if (training && norm_reward) {
-            const double bmean = tot[2 * kVnCols] / bc;
-            const double bvar = fmax(tot[2 * kVnCols + 1] / bc - bmean * bmean, 0.0);
+        if (norm_reward) {
+            const double bmean = cols[2 * kVnCols] / bc;
+            const double bvar = fmax(cols[2 * kVnCols + 1] / bc - bmean * bmean, 0.0);
             const double rc = rms[kRetCount], mean = rms[kRetMean], var = rms[kRetVar];
             const double t = rc + bc, delta = bmean - mean;
             rms[kRetMean] = mean + delta * bc / t;
@@ -187,30 +211,34 @@ vecnorm_fold_kernel(double* __restrict__ rms, const double* __restrict__ partial
         rms[kDerived + kVnCols] = 1.0 / sqrt(rms[kRetVar] + epsilon);
     }
     __syncthreads();
-    if (j == 0 && training && norm_obs) rms[kObsCount] = count + bc;            // after every column used the old count
+    if (j == 0) {
+        if (norm_obs) rms[kObsCount] = count + bc;                                   // after every column used the old count
+        *ticket = 0u;                                                                // ready for the next launch
+    }
 }
 
-__global__ void __launch_bounds__(kVnThreads, 3)
+__global__ void __launch_bounds__(kVnThreads, 2)
 vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ returns, long long n, float* __restrict__ obs,
                      void* __restrict__ reward, int reward_f64, const unsigned char* __restrict__ done,
                      float* __restrict__ terminal_obs, double clip_obs, double clip_reward, int norm_obs, int norm_reward,
-                     int vec_ok) {
+                     int vec_ok, double epsilon) {
     const ChunkMap cm;
     pdl_wait_prior_grid();
-    double mean[4];
-    float inv[4];
+    float mh[4], ml[4], inv[4];                                                      // mean = mh + ml to ~2^-48: (x - mh) - ml loses nothing
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        mean[j] = rms[kObsMean + cm.col[j]];
-        inv[j] = (float)rms[kDerived + cm.col[j]];
+        const double m = rms[kObsMean + cm.col[j]];
+        mh[j] = (float)m;
+        ml[j] = (float)(m - (double)mh[j]);
+        inv[j] = (float)(1.0 / sqrt(rms[kObsVar + cm.col[j]] + epsilon));
     }
     const float lo = (float)-clip_obs, hi = (float)clip_obs;
-    const double rinv = rms[kDerived + kVnCols];
-    // (x - mean) in float64 (no cancellation error), scale and clip in float32 -- the result is a float32 anyway
-    auto norm1 = [&](float x, int j) { return fminf(fmaxf((float)((double)x - mean[j]) * inv[j], lo), hi); };
+    const double rinv = 1.0 / sqrt(rms[kRetVar] + epsilon);
+    // the subtraction against a two-float mean has no cancellation error; scale and clip in float32 -- the result is a float32 anyway
+    auto norm1 = [&](float x, int j) { return fminf(fmaxf(((x - mh[j]) - ml[j]) * inv[j], lo), hi); };
     const long long n_chunks = (n + kVnRows - 1) / kVnRows;
     const long long n_full = vec_ok ? n / kVnRows : 0;
-    constexpr int U = 4;
+    constexpr int U = 8;
     long long c = blockIdx.x;
     if (norm_obs) {
         for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {
@@ -244,10 +272,39 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
             }
         }
     }
-    if (threadIdx.x < kVnRows) {
-        for (long long cc = blockIdx.x; cc < n_chunks; cc += gridDim.x) {
-            const long long i = cc * kVnRows + threadIdx.x;
-            if (i >= n) continue;
+    // rewards, returns and the finished envs' terminal observations: envs strided over the whole grid, R loads in flight
+    {
+        const long long stride = (long long)gridDim.x * kVnThreads;
+        constexpr int R = 4;
+        auto finish = [&](long long i) {
+            returns[i] = 0.0;
+            if (norm_obs && terminal_obs != nullptr) {                               // the finished env's pre-reset observation (rare: whole row here)
+                float* row = terminal_obs + i * kVnCols;
+#pragma unroll
+                for (int j = 0; j < kVnCols; ++j)
+                    row[j] = fminf(fmaxf((float)((double)row[j] - rms[kObsMean + j]) * (float)(1.0 / sqrt(rms[kObsVar + j] + epsilon)), lo), hi);
+            }
+        };
+        long long i = (long long)blockIdx.x * kVnThreads + threadIdx.x;
+        for (; i + (R - 1) * stride < n; i += R * stride) {
+            unsigned char d[R];
+            double r[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                d[u] = __ldg(done + i + u * stride);
+                if (norm_reward) r[u] = reward_f64 ? reinterpret_cast<double*>(reward)[i + u * stride] : (double)reinterpret_cast<float*>(reward)[i + u * stride];
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                if (norm_reward) {
+                    const double y = fmin(fmax(r[u] * rinv, -clip_reward), clip_reward);
+                    if (reward_f64) reinterpret_cast<double*>(reward)[i + u * stride] = y;
+                    else reinterpret_cast<float*>(reward)[i + u * stride] = (float)y;
+                }
+                if (d[u]) finish(i + u * stride);
+            }
+        }
+        for (; i < n; i += stride) {
             if (norm_reward) {
                 if (reward_f64) {
                     double* r = reinterpret_cast<double*>(reward) + i;
@@ -257,15 +314,7 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
                     *r = (float)fmin(fmax((double)*r * rinv, -clip_reward), clip_reward);
                 }
             }
-            if (done[i]) {
-                returns[i] = 0.0;
-                if (norm_obs && terminal_obs != nullptr) {                       // the finished env's pre-reset observation (rare: whole row here)
-                    float* row = terminal_obs + i * kVnCols;
-#pragma unroll
-                    for (int j = 0; j < kVnCols; ++j)
-                        row[j] = fminf(fmaxf((float)((double)row[j] - rms[kObsMean + j]) * (float)rms[kDerived + j], lo), hi);
-                }
-            }
+            if (done[i]) finish(i);
         }
     }
 }
@@ -320,23 +369,17 @@ extern "C" int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs,
     const long long cap_m = (long long)n_sm * (occ_moments > 0 ? occ_moments : 1), cap_a = (long long)n_sm * (occ_apply > 0 ? occ_apply : 1);
     const unsigned grid = (unsigned)(n_chunks < cap_m ? n_chunks : (cap_m < kVnMaxGrid ? cap_m : kVnMaxGrid));
     const unsigned grid_apply = (unsigned)(n_chunks < cap_a ? n_chunks : cap_a);
-    int n_partial = (int)grid;
     int vec_ok = aligned16(obs) && (terminal_obs == nullptr || aligned16(terminal_obs)) ? 1 : 0;
-    double* partial = rms + kPartial;
     int rc;
     const float* obs_c = obs;
     const void* rew_c = reward;
     if (training) {
-        void* a1[] = {&partial, &returns, &n, &obs_c, &rew_c, (void*)&f64, &gamma, &norm_obs, &norm_reward, &vec_ok};
+        void* a1[] = {&rms, &returns, &n, &obs_c, &rew_c, (void*)&f64, &gamma, &norm_obs, &norm_reward, &vec_ok, &epsilon};
         rc = launch_pdl((const void*)vecnorm_moments_kernel, dim3(grid), dim3(kVnThreads), s, a1);
         if (rc) return rc;
     }
-    const double* partial_c = partial;
-    void* a2[] = {&rms, &partial_c, &n_partial, &n, &epsilon, &training, &norm_obs, &norm_reward};
-    rc = launch_pdl((const void*)vecnorm_fold_kernel, dim3(1), dim3(kVnSums * 32), s, a2);
-    if (rc) return rc;
     const double* rms_c = rms;
     void* a3[] = {&rms_c, &returns, &n, &obs, &reward, (void*)&f64, &done, &terminal_obs, &clip_obs, &clip_reward, &norm_obs,
-                  &norm_reward, &vec_ok};
+                  &norm_reward, &vec_ok, &epsilon};
     return launch_pdl((const void*)vecnorm_apply_kernel, dim3(grid_apply), dim3(kVnThreads), s, a3);
 }
