@@ -62,8 +62,8 @@ vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, l
     constexpr int U = 8;                                                             // independent 16-byte loads in flight per thread
     long long c = blockIdx.x;
     if (norm_obs) {
-        for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {
-            float4 v[U];
+        for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {   // full batches of U chunks:
+            float4 v[U];                                                             // every load of a batch is in flight before the first add
 #pragma unroll
             for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(obs) + (c + u * (long long)gridDim.x) * kVnThreads + threadIdx.x);
 #pragma unroll
@@ -75,23 +75,33 @@ vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, l
                 sum[3] += d3; sq[3] = fma(d3, d3, sq[3]);
             }
         }
-        for (; c < n_chunks; c += gridDim.x) {                                       // leftovers and the ragged last chunk
+        constexpr int UL = 4;
+        for (; c < n_full; c += UL * (long long)gridDim.x) {                        // the leftovers, in partly empty batches of UL
+            float4 v[UL];
+#pragma unroll
+            for (int u = 0; u < UL; ++u) {
+                const long long cu = c + u * (long long)gridDim.x;
+                v[u] = cu < n_full ? __ldg(reinterpret_cast<const float4*>(obs) + cu * kVnThreads + threadIdx.x) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UL; ++u) {
+                const double d0 = v[u].x, d1 = v[u].y, d2 = v[u].z, d3 = v[u].w;
+                sum[0] += d0; sq[0] = fma(d0, d0, sq[0]);
+                sum[1] += d1; sq[1] = fma(d1, d1, sq[1]);
+                sum[2] += d2; sq[2] = fma(d2, d2, sq[2]);
+                sum[3] += d3; sq[3] = fma(d3, d3, sq[3]);
+            }
+        }
+        // the chunks that cannot move as whole vectors: the ragged last one, or all of them when obs is not 16-byte aligned
+        for (c = n_full + blockIdx.x; c < n_chunks; c += gridDim.x) {
             const long long base = c * kVnRows;
-            float x[4] = {0.f, 0.f, 0.f, 0.f};
-            if (c < n_full) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(obs) + c * kVnThreads + threadIdx.x);
-                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-            } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (base + cm.row[j] < n) x[j] = __ldg(obs + base * kVnCols + 4 * threadIdx.x + j);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double d = (double)x[j];
-                sum[j] += d;
-                sq[j] = fma(d, d, sq[j]);
-            }
+            for (int j = 0; j < 4; ++j)
+                if (base + cm.row[j] < n) {
+                    const double d = (double)__ldg(obs + base * kVnCols + 4 * threadIdx.x + j);
+                    sum[j] += d;
+                    sq[j] = fma(d, d, sq[j]);
+                }
         }
     }
     if (norm_reward) {                                                               // discounted returns: envs strided over the whole grid,
@@ -101,26 +111,22 @@ vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, l
         auto load_reward = [&](long long e) {
             return reward_f64 ? __ldg(reinterpret_cast<const double*>(reward) + e) : (double)__ldg(reinterpret_cast<const float*>(reward) + e);
         };
-        for (; i + (R - 1) * stride < n; i += R * stride) {
+        for (; i < n; i += R * stride) {
             double ret[R], r[R];
 #pragma unroll
-            for (int u = 0; u < R; ++u) {
-                ret[u] = returns[i + u * stride];
-                r[u] = load_reward(i + u * stride);
-            }
+            for (int u = 0; u < R; ++u)
+                if (i + u * stride < n) {
+                    ret[u] = returns[i + u * stride];
+                    r[u] = load_reward(i + u * stride);
+                }
 #pragma unroll
-            for (int u = 0; u < R; ++u) {
-                ret[u] = fma(ret[u], gamma, r[u]);
-                returns[i + u * stride] = ret[u];
-                rsum += ret[u];
-                rsq = fma(ret[u], ret[u], rsq);
-            }
-        }
-        for (; i < n; i += stride) {
-            const double ret = fma(returns[i], gamma, load_reward(i));
-            returns[i] = ret;
-            rsum += ret;
-            rsq = fma(ret, ret, rsq);
+            for (int u = 0; u < R; ++u)
+                if (i + u * stride < n) {
+                    ret[u] = fma(ret[u], gamma, r[u]);
+                    returns[i + u * stride] = ret[u];
+                    rsum += ret[u];
+                    rsq = fma(ret[u], ret[u], rsq);
+                }
         }
     }
     pdl_launch_dependents();
@@ -241,7 +247,7 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
     constexpr int U = 8;
     long long c = blockIdx.x;
     if (norm_obs) {
-        for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {
+        for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {   // full batches of U chunks
             float4* p[U];
             float4 v[U];
 #pragma unroll
@@ -255,21 +261,31 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
                 *p[u] = v[u];
             }
         }
-        for (; c < n_chunks; c += gridDim.x) {
-            const long long base = c * kVnRows;
-            if (c < n_full) {
-                float4* p = reinterpret_cast<float4*>(obs) + c * kVnThreads + threadIdx.x;
-                float4 v = *p;
-                v.x = norm1(v.x, 0); v.y = norm1(v.y, 1); v.z = norm1(v.z, 2); v.w = norm1(v.w, 3);
-                *p = v;
-            } else {
+        constexpr int UL = 4;
+        for (; c < n_full; c += UL * (long long)gridDim.x) {                        // the leftovers, in partly empty batches of UL
+            float4 v[UL];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (base + cm.row[j] < n) {
-                        float* p = obs + base * kVnCols + 4 * threadIdx.x + j;
-                        *p = norm1(*p, j);
-                    }
+            for (int u = 0; u < UL; ++u) {
+                const long long cu = c + u * (long long)gridDim.x;
+                if (cu < n_full) v[u] = *(reinterpret_cast<float4*>(obs) + cu * kVnThreads + threadIdx.x);
             }
+#pragma unroll
+            for (int u = 0; u < UL; ++u) {
+                const long long cu = c + u * (long long)gridDim.x;
+                if (cu < n_full) {
+                    v[u].x = norm1(v[u].x, 0); v[u].y = norm1(v[u].y, 1); v[u].z = norm1(v[u].z, 2); v[u].w = norm1(v[u].w, 3);
+                    *(reinterpret_cast<float4*>(obs) + cu * kVnThreads + threadIdx.x) = v[u];
+                }
+            }
+        }
+        for (c = n_full + blockIdx.x; c < n_chunks; c += gridDim.x) {               // ragged last chunk / unaligned obs
+            const long long base = c * kVnRows;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (base + cm.row[j] < n) {
+                    float* p = obs + base * kVnCols + 4 * threadIdx.x + j;
+                    *p = norm1(*p, j);
+                }
         }
     }
     // rewards, returns and the finished envs' terminal observations: envs strided over the whole grid, R loads in flight
@@ -286,16 +302,21 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
             }
         };
         long long i = (long long)blockIdx.x * kVnThreads + threadIdx.x;
-        for (; i + (R - 1) * stride < n; i += R * stride) {
+        for (; i < n; i += R * stride) {
             unsigned char d[R];
             double r[R];
 #pragma unroll
             for (int u = 0; u < R; ++u) {
-                d[u] = __ldg(done + i + u * stride);
-                if (norm_reward) r[u] = reward_f64 ? reinterpret_cast<double*>(reward)[i + u * stride] : (double)reinterpret_cast<float*>(reward)[i + u * stride];
+                d[u] = 0;
+                r[u] = 0.0;
+                if (i + u * stride < n) {
+                    d[u] = __ldg(done + i + u * stride);
+                    if (norm_reward) r[u] = reward_f64 ? reinterpret_cast<double*>(reward)[i + u * stride] : (double)reinterpret_cast<float*>(reward)[i + u * stride];
+                }
             }
 #pragma unroll
             for (int u = 0; u < R; ++u) {
+                if (i + u * stride >= n) continue;
                 if (norm_reward) {
                     const double y = fmin(fmax(r[u] * rinv, -clip_reward), clip_reward);
                     if (reward_f64) reinterpret_cast<double*>(reward)[i + u * stride] = y;
@@ -303,18 +324,6 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
                 }
                 if (d[u]) finish(i + u * stride);
             }
-        }
-        for (; i < n; i += stride) {
-            if (norm_reward) {
-                if (reward_f64) {
-                    double* r = reinterpret_cast<double*>(reward) + i;
-                    *r = fmin(fmax(*r * rinv, -clip_reward), clip_reward);
-                } else {
-                    float* r = reinterpret_cast<float*>(reward) + i;
-                    *r = (float)fmin(fmax((double)*r * rinv, -clip_reward), clip_reward);
-                }
-            }
-            if (done[i]) finish(i);
         }
     }
 }
