@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2, help="episode sweeps timed through the host-buffer API")
     ap.add_argument("--rollout-steps", type=int, default=3, help="episode sweeps of the on-the-fly rollout kernel (extra)")
     ap.add_argument("--mlp-rollout-steps", type=int, default=1000, help="steps of the MLP-policy rollout (configs[4] shape; 0 = skip)")
+    ap.add_argument("--lstm-rollout-steps", type=int, default=252, help="steps of the recurrent (LSTM + MLP) policy rollout (0 = skip)")
     ap.add_argument("--book-strikes", type=int, default=8, help="strikes of the multi-strike book extra (configs[2] shape; 0 = skip)")
     ap.add_argument("--rbergomi-paths", type=int, default=512, help="paths of the rough-Bergomi nested-MC extra (x 32 days; 0 = skip)")
     ap.add_argument("--no-fused-allreduce", action="store_true", help="all-reduce the statistics with NCCL instead of in-kernel")
@@ -369,6 +370,31 @@ def main():
         assert float(st5.sums[15]) == 0.0, "a tcgen05 MMA timed out"
         mlp_roll = (m0.elapsed_time(m1), n5, st5.result())
 
+    # ---- the policy the reference actually trained: LSTM(13-128) + MLP(128-64-64-2), recurrent state carried in TMEM --------
+    lstm_roll = None
+    if args.lstm_rollout_steps > 0:
+        from cantorrl_b200.rollout import HedgingRollout, pack_lstm
+        n6 = min(n, 1 << 19)
+        gw = np.random.default_rng(6)
+        kk = 1 / np.sqrt(128)
+        wl = pack_lstm(gw.uniform(-kk, kk, (512, 13)) * 3, gw.uniform(-kk, kk, (512, 128)) * 2, gw.uniform(-kk, kk, 512), gw.uniform(-kk, kk, 512),
+                       gw.normal(0, .15, (64, 128)), gw.normal(0, .1, 64), gw.normal(0, .2, (64, 64)), gw.normal(0, .1, 64),
+                       gw.normal(0, .3, (2, 64)), gw.normal(0, .1, 2), gw.normal(0, .2, 13), gw.uniform(.05, 2, 13), device=dev)
+        ro6 = HedgingRollout(simulate=dict(model="gbm", seed=42, s0=S0, v0=XI, n_steps=T), num_envs=n6, device=dev,
+                             env_offset=rank * n6, total_envs=world * n6, **ENV_KW)
+        st6 = ro6.new_stats()
+        ro6.run(min(args.lstm_rollout_steps, 16), "lstm_bf16", mlp=wl, stats=st6)
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st6.zero_()
+        l0.record(stream)
+        ro6.run(args.lstm_rollout_steps, "lstm_bf16", mlp=wl, stats=st6)
+        st6.all_reduce()
+        l1.record(stream)
+        barrier()
+        assert float(st6.sums[15]) == 0.0, "a tcgen05 MMA timed out"
+        lstm_roll = (l0.elapsed_time(l1), n6, st6.result())
+
     # ---- configs[2] shape: Heston paths + multi-strike float32 Black-Scholes book (8 strikes, maturities to episode end) ---
     book_ms = None
     if args.book_strikes > 0 and rank == 0:
@@ -401,10 +427,11 @@ def main():
         rb_res = (q0.elapsed_time(q1), args.rbergomi_paths * 32 * 2)
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------
-    tt = torch.tensor([ms, e2e_s, roll[0] if roll else 0.0, mlp_roll[0] if mlp_roll else 0.0], dtype=torch.float64, device=dev)
+    tt = torch.tensor([ms, e2e_s, roll[0] if roll else 0.0, mlp_roll[0] if mlp_roll else 0.0, lstm_roll[0] if lstm_roll else 0.0],
+                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms, e2e_s, roll_ms, mlp_ms = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
+    ms, e2e_s, roll_ms, mlp_ms, lstm_ms = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3]), float(tt[4])
     if rank == 0:
         env_steps = float(n) * world * T * K
         value = env_steps / (ms * 1e-3)
@@ -462,6 +489,16 @@ def main():
                 env_steps_per_s=float(mlp_roll[1]) * world * args.mlp_rollout_steps / (mlp_ms * 1e-3),
                 actor_tflops=float(mlp_roll[1]) * world * args.mlp_rollout_steps * 2 * (16 * 64 + 80 * 64 + 80 * 16) / (mlp_ms * 1e-3) / 1e12,
                 n_episodes=mlp_roll[2]["n_episodes"])
+        if lstm_roll is not None:
+            flop = 2 * (4 * 128 * 144 + 64 * 144 + 64 * 80 + 16 * 80)                  # per env-step, as issued (padded K / N)
+            line["extra"]["rollout_lstm_policy"] = dict(
+                kernel="rollout_kernel<GBM on the fly, LSTM(13-128) + MLP(128-64-64-2) actor as bf16 tcgen05.mma (warp-specialised "
+                       "issuer, TMA-streamed gate weights, cell state in TMEM), env step, episode statistics> + all-reduce of the statistics",
+                envs_per_gpu=lstm_roll[1], steps=args.lstm_rollout_steps, ms=lstm_ms,
+                env_steps_per_s=float(lstm_roll[1]) * world * args.lstm_rollout_steps / (lstm_ms * 1e-3),
+                actor_tflops=float(lstm_roll[1]) * world * args.lstm_rollout_steps * flop / (lstm_ms * 1e-3) / 1e12,
+                mufu_bound_frac=float(lstm_roll[1]) * args.lstm_rollout_steps * 640 / (lstm_ms * 1e-3) / (148 * 16 * 1.965e9),
+                n_episodes=lstm_roll[2]["n_episodes"])
         if book_ms is not None:
             cells = float(n) * (T + 1)
             line["extra"]["multi_strike_book"] = dict(

@@ -99,9 +99,13 @@ def test_vecnormalize_matches_oracle_over_many_steps_and_checkpoints():
         vn2 = VecNormalize.load(f, env)
     assert torch.equal(vn2._rms[:30], vn._rms[:30]) and vn2.gamma == 0.95
     vn2.training = False
+    vn2.keep_original = True
     before = vn2._rms[:30].clone()
-    vn2.step(torch.zeros((n, 2), device="cuda"))
+    o_eval, r_eval, _, _ = vn2.step(torch.zeros((n, 2), device="cuda"))
     assert torch.equal(vn2._rms[:30], before)
+    # evaluation mode = the apply kernel alone, deriving 1 / sqrt(var + eps) itself (quantconnect/model_wrapper.py:131)
+    torch.testing.assert_close(o_eval, vn2.normalize_obs(vn2.get_original_obs()), rtol=1e-5, atol=5e-6)
+    torch.testing.assert_close(r_eval, vn2.normalize_reward(vn2.get_original_reward()), rtol=1e-6, atol=1e-9)
     st = vn.export_stats()
     assert st["obs_mean"].shape == (13,) and st["obs_var"].dtype == np.float32
 
@@ -121,3 +125,23 @@ def test_vecnormalize_fp32_rewards_and_full_size():
     raw_like = obs[:, [0, 1, 2, 5, 7]]                  # columns with real cross-sectional spread
     assert float(raw_like.mean(0).abs().max()) < 0.5 and 0.3 < float(raw_like.std(0).mean()) < 3.0
     assert abs(vn.obs_rms.count - (7 * n + 1e-4)) < 1e-3
+
+
+def test_vecnormalize_statistics_are_bitwise_reproducible():
+    """The moments are reduced without atomics on the data and folded in a fixed order by whichever CTA finishes last:
+    two identical runs give bit-identical running statistics (70 000 envs = 547 chunks over one wave of CTAs, ragged tail)."""
+    from cantorrl_b200 import HedgingVecEnv, sim
+    from cantorrl_b200.vecnorm import VecNormalize
+    n = 70000
+    book = sim.generate_paths_and_options(n, n_steps=8, model="gbm")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = [torch.rand((n, 2), device="cuda", generator=g) * 2 - 1 for _ in range(10)]
+    runs = []
+    for _ in range(2):
+        vn = VecNormalize(HedgingVecEnv(data=book, num_envs=n, episode_sampler="same_path", **KW))
+        vn.reset()
+        for a in acts:
+            obs, r, _, _ = vn.step(a)
+        runs.append((vn._rms[:30].clone(), obs.clone(), r.clone(), vn.returns.clone()))
+    for x, y in zip(*runs):
+        assert torch.equal(x, y)
