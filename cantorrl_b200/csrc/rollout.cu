@@ -129,7 +129,8 @@ __device__ __noinline__ float2 policy_mlp(const float* o, const float* __restric
 // MLP: 0 = one of the closed-form / tabulated policies, 1 = the MLP actor in float32 FFMAs (parity form),
 //      2 = the MLP actor on the tensor cores (bf16 tcgen05.mma, mlp_tc.cuh), 3 = the recurrent LSTM + MLP actor on the
 //      tensor cores (lstm_tc.cuh); compile-time, so the other policies do not pay for its registers and shared memory.
-//      The recurrent form runs with a fifth warp that only issues MMAs / TMA copies (lstmtc::Actor::issuer_loop).
+//      The recurrent form runs 256 envs per CTA (two groups of 128 that ping-pong) plus a ninth warp that only issues MMAs /
+//      TMA copies (lstmtc::Actor::issuer_loop).
 template <int SRC, int MLP, bool WRITE>
 __global__ void __launch_bounds__(MLP == 3 ? lstmtc::kThreads : kRollThreads)
 rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const PolicyConsts pc, long long n_envs,
@@ -138,27 +139,29 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
     extern __shared__ __align__(128) float smem_f[];
     float* w_mlp = smem_f;                                                     // [kMlpFloats] float32 weights (MLP == 1)
     constexpr int mlp_floats = MLP == 1 ? (kMlpFloats + 3) / 4 * 4 : (MLP == 2 ? mlptc::kSmemBytes / 4 : (MLP == 3 ? lstmtc::kSmemBytes / 4 : 0));
-    float* tile = smem_f + mlp_floats;                                         // [kRollThreads * 13] when WRITE
-    double* red = reinterpret_cast<double*>(tile + (WRITE ? kRollThreads * CANTOR_OBS_DIM : 0));
+    constexpr int kEnv = MLP == 3 ? lstmtc::kEnvs : kRollThreads;             // envs (= env threads) per CTA
+    constexpr int kThreads = MLP == 3 ? lstmtc::kThreads : kRollThreads;
     mlptc::Actor actor;
     lstmtc::Actor lstm;
     if (MLP == 3) lstm.setup(reinterpret_cast<unsigned char*>(smem_f), reinterpret_cast<const unsigned char*>(pc.mlp));
+    // [kEnv * 13] observation staging tile when WRITE; the recurrent actor lends its A2 tiles for it (no shared memory left)
+    float* tile = MLP == 3 ? lstm.obs_staging() : smem_f + mlp_floats;
+    double* red = reinterpret_cast<double*>(smem_f + mlp_floats + ((WRITE && MLP != 3) ? kEnv * CANTOR_OBS_DIM : 0));
     if (MLP == 1) {
         for (int j = threadIdx.x; j < kMlpFloats; j += kRollThreads) w_mlp[j] = pc.mlp[j];
     }
     if (MLP == 2) actor.setup(reinterpret_cast<unsigned char*>(smem_f), pc.mlp);
     __syncthreads();
 
-    constexpr int kThreads = MLP == 3 ? lstmtc::kThreads : kRollThreads;
-    const bool env_thread = MLP != 3 || threadIdx.x < kRollThreads;            // the others: the recurrent actor's issuer warp
+    const bool env_thread = threadIdx.x < kEnv;                                // the others: the recurrent actor's issuer warp
     auto env_sync = [&]() {                                                    // barrier of the env threads only
         if (MLP == 3) lstmtc::env_sync();
         else __syncthreads();
     };
-    const long long first_env = (long long)blockIdx.x * kRollThreads;
+    const long long first_env = (long long)blockIdx.x * kEnv;
     const long long i = first_env + threadIdx.x;
     const bool live = env_thread && i < n_envs;
-    const int rows = (int)min((long long)kRollThreads, n_envs - first_env);
+    const int rows = (int)min((long long)kEnv, n_envs - first_env);
     const unsigned long long genv = (unsigned long long)(env_offset + (live ? i : 0));
     constexpr int MODEL = SRC == 2 ? 1 : 0;
     constexpr int NPS = SRC == 2 ? 2 : 1;
@@ -266,7 +269,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                     env_sync();
                 } else {
                     env_sync();
-                    for (int q = threadIdx.x; q < rows * CANTOR_OBS_DIM; q += kRollThreads) dst[q] = tile[q];
+                    for (int q = threadIdx.x; q < rows * CANTOR_OBS_DIM; q += kEnv) dst[q] = tile[q];
                     env_sync();
                 }
                 if (live) {
@@ -300,7 +303,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
         }
     }
     // ---- one reduction at the end: warp shuffle -> shared -> one atomic per statistic per block ---------------
-    if (st.sums != nullptr) block_accumulate<11, kRollThreads>(stat, st.sums, red);   // warps beyond the env warps only join its barriers
+    if (st.sums != nullptr) block_accumulate<11, kEnv>(stat, st.sums, red);          // warps beyond the env warps only join its barriers
     if (st.sums != nullptr && threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(st.sums + 11, (double)n_envs * (double)n_steps);
     if (MLP == 2) {
         if (actor.timed_out && st.sums != nullptr) atomicAdd(st.sums + 15, 1.0);   // an MMA never completed: results are invalid
@@ -358,11 +361,12 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
         ro = RolloutOut{out->obs, (float2*)out->actions, out->reward, out->done};
     }
     if (n_steps == 0) return CANTOR_OK;
-    const unsigned grid = (unsigned)((n_envs + kRollThreads - 1) / kRollThreads);
     const int mlp_mode = policy->kind == CANTOR_POLICY_LSTM ? 3 : (policy->kind != CANTOR_POLICY_MLP ? 0 : (policy->mlp_tensor_cores ? 2 : 1));
+    const int env_per_cta = mlp_mode == 3 ? lstmtc::kEnvs : kRollThreads;
+    const unsigned grid = (unsigned)((n_envs + env_per_cta - 1) / env_per_cta);
     const size_t smem = (mlp_mode == 1 ? (kMlpFloats + 3) / 4 * 4 * sizeof(float)
                          : (mlp_mode == 2 ? (size_t)mlptc::kSmemBytes : (mlp_mode == 3 ? (size_t)lstmtc::kSmemBytes : 0))) +
-                        (write ? kRollThreads * CANTOR_OBS_DIM * sizeof(float) : 0) + 11 * (kRollThreads / 32) * sizeof(double) + 16;
+                        ((write && mlp_mode != 3) ? kRollThreads * CANTOR_OBS_DIM * sizeof(float) : 0) + 11 * (env_per_cta / 32) * sizeof(double) + 16;
     const int tma_ok = write && aligned16(out->obs) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     // the observation's greeks can ride on the price evaluation when the env and the simulator agree on (r, tenor)
