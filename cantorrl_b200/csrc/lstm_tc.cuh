@@ -114,9 +114,10 @@ struct Actor {
     __device__ __forceinline__ uint32_t bar_a2(int g) const { return bars + 8 * (12 + g); }
     __device__ __forceinline__ unsigned char* a_tile(int g) const { return smem + kOffA + g * kABytes; }
     __device__ __forceinline__ unsigned char* a2_tile(int g) const { return smem + kOffA2 + g * kA2Bytes; }
-    // [kEnvs x 13] float staging tile for the rollout's observation store: aliases the A2 tiles, which are idle between
-    // a group's last head layer and its next one (head_epilogue rewrites the constant tail of its rows every time)
-    __device__ __forceinline__ float* obs_staging() const { return reinterpret_cast<float*>(smem + kOffA2); }
+    // [128 x 13] float staging tile of group g for the rollout's observation store: aliases the group's OWN A2 tile, which is
+    // idle between the group's last head layer and its next one (head_epilogue rewrites the constant tail of its rows every
+    // time).  Per group, because the groups are not in lockstep: one may still be in its head while the other stores.
+    __device__ __forceinline__ float* obs_staging(int g) const { return reinterpret_cast<float*>(a2_tile(g)); }
 
     // CTA-collective (all kThreads threads).
     __device__ __forceinline__ void setup(unsigned char* smem_base, const unsigned char* image) {

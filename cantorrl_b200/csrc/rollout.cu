@@ -144,8 +144,10 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
     mlptc::Actor actor;
     lstmtc::Actor lstm;
     if (MLP == 3) lstm.setup(reinterpret_cast<unsigned char*>(smem_f), reinterpret_cast<const unsigned char*>(pc.mlp));
-    // [kEnv * 13] observation staging tile when WRITE; the recurrent actor lends its A2 tiles for it (no shared memory left)
-    float* tile = MLP == 3 ? lstm.obs_staging() : smem_f + mlp_floats;
+    // [kEnv * 13] observation staging tile when WRITE; the recurrent actor lends its A2 tiles for it (no shared memory left):
+    // one [128 x 13] piece per group
+    float* tile = MLP == 3 ? lstm.obs_staging(0) : smem_f + mlp_floats;
+    auto tile_row = [&](int r) { return MLP == 3 ? lstm.obs_staging(r >> 7) + (r & 127) * CANTOR_OBS_DIM : tile + r * CANTOR_OBS_DIM; };
     double* red = reinterpret_cast<double*>(smem_f + mlp_floats + ((WRITE && MLP != 3) ? kEnv * CANTOR_OBS_DIM : 0));
     if (MLP == 1) {
         for (int j = threadIdx.x; j < kMlpFloats; j += kRollThreads) w_mlp[j] = pc.mlp[j];
@@ -253,7 +255,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             const LedgerF32 L = ledger_f32(k, a.x, a.y, pos_c, pos_p, t, inv_s0, cur, nxt, false);
             const bool terminated = t + 1 >= k.T;
             if (WRITE) {
-                float* orow = tile + threadIdx.x * CANTOR_OBS_DIM;
+                float* orow = tile_row(threadIdx.x);
 #pragma unroll
                 for (int q = 0; q < CANTOR_OBS_DIM; ++q) orow[q] = o[q];
                 float* dst = out.obs + ((long long)g * n_envs + first_env) * CANTOR_OBS_DIM;
@@ -262,14 +264,16 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                     fence_proxy_async_smem();
                     env_sync();
                     if (threadIdx.x == 0) {
-                        tma_store_1d_evict_first(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
+                        for (int r0 = 0; r0 < rows; r0 += kRollThreads)                        // one piece (MLP == 3: one per group)
+                            tma_store_1d_evict_first(dst + r0 * CANTOR_OBS_DIM, tile_row(r0),
+                                                     (uint32_t)((MLP == 3 ? min(rows - r0, kRollThreads) : rows) * CANTOR_OBS_DIM * sizeof(float)));
                         tma_store_commit();
                         tma_store_wait_read();
                     }
                     env_sync();
                 } else {
                     env_sync();
-                    for (int q = threadIdx.x; q < rows * CANTOR_OBS_DIM; q += kEnv) dst[q] = tile[q];
+                    for (int q = threadIdx.x; q < rows * CANTOR_OBS_DIM; q += kEnv) dst[q] = tile_row(q / CANTOR_OBS_DIM)[q % CANTOR_OBS_DIM];
                     env_sync();
                 }
                 if (live) {
