@@ -200,8 +200,9 @@ def test_recurrent_lstm_actor_matches_oracle_over_episodes(n_envs):
     np.testing.assert_allclose(got["reward"], ref["reward"], rtol=1e-4, atol=1e-7)
     want = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=mean, var=var, bf16=True)
     err = np.abs(got["actions"] - want)
-    # bf16 operands + tanh.approx (2^-11 relative) through a 12-step recurrence
-    assert err.max() < 3e-2 and err.mean() < 2e-3, (err.max(), err.mean())
+    # bf16 operands + tanh.approx (2^-11 relative) through a 12-step recurrence: measured max 3e-3, mean 1.5e-4 (a wrong
+    # hidden unit out of 128 already shows as max 3e-2, mean 1.5e-2)
+    assert err.max() < 8e-3 and err.mean() < 5e-4, (err.max(), err.mean())
     full = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=mean, var=var, bf16=False)
     assert np.abs(got["actions"] - full).max() < 0.15 and np.abs(got["actions"] - full).mean() < 1e-2
     assert np.abs(want).mean() > 0.05                     # the network is not saturated / trivially zero
