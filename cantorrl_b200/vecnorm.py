@@ -4,7 +4,7 @@ Reference use: ``VecNormalize(env, norm_obs=True, norm_reward=True, clip_obs=10.
 (``src/agents/train_ppo_v2.py:204-208, 305-309``), saved / loaded with the model (``:315-317, 449-455``), its statistics
 exported for deployment (``quantconnect/extract_model.py:62-79``; applied as ``(obs - mean) / sqrt(var + 1e-8)``,
 ``quantconnect/model_wrapper.py:131``).  Stable-Baselines3 is an un-vendored dependency, so this mirrors its public
-behaviour (attribute and method names included); all arithmetic runs in ``cantor_vecnorm_step`` (three chained kernels).
+behaviour (attribute and method names included); all arithmetic runs in ``cantor_vecnorm_step`` (two chained kernels).
 """
 from __future__ import annotations
 
@@ -42,6 +42,8 @@ class VecNormalize:
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().cantor_vecnorm_init(self._rms.data_ptr(), self.returns.data_ptr(), self.num_envs,
                                                       _lib.current_stream_ptr(self.device)), "cantor_vecnorm_init")
+        self._rms_ptr, self._returns_ptr, self._fn = self._rms.data_ptr(), self.returns.data_ptr(), _lib.lib().cantor_vecnorm_step
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.obs_rms = RunningMeanStdView(self._rms[0:13], self._rms[13:26], self._rms[26])
         self.ret_rms = RunningMeanStdView(self._rms[27], self._rms[28], self._rms[29])
         self.keep_original = bool(keep_original)
@@ -51,12 +53,16 @@ class VecNormalize:
 
     # ------------------------------------------------------------------------------------------------ core
     def _apply(self, obs, reward, done_u8, terminal_obs, norm_reward):
-        with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().cantor_vecnorm_step(
-                self._rms.data_ptr(), self.returns.data_ptr(), self.num_envs, obs.data_ptr(), reward.data_ptr(),
-                _lib.F64 if reward.dtype == torch.float64 else _lib.F32, done_u8.data_ptr(), _lib.ptr(terminal_obs),
-                self.gamma, self.clip_obs, self.clip_reward, self.epsilon, int(self.training), int(self.norm_obs),
-                int(norm_reward), _lib.current_stream_ptr(self.device)), "cantor_vecnorm_step")
+        args = (self._rms_ptr, self._returns_ptr, self.num_envs, obs.data_ptr(), reward.data_ptr(),
+                _lib.F64 if reward.dtype is torch.float64 else _lib.F32, done_u8.data_ptr(), _lib.ptr(terminal_obs),
+                self.gamma, self.clip_obs, self.clip_reward, self.epsilon, int(self.training), int(self.norm_obs), int(norm_reward))
+        if torch.cuda.current_device() == self._dev_index:      # no context switch on the hot path (two launches per env-step)
+            status = self._fn(*args, torch.cuda.current_stream().cuda_stream)
+        else:
+            with torch.cuda.device(self.device):
+                status = self._fn(*args, _lib.current_stream_ptr(self.device))
+        if status != 0:
+            _lib.check(status, "cantor_vecnorm_step")
 
     def reset(self, *args, **kwargs):
         obs = self.venv.reset(*args, **kwargs)
@@ -72,7 +78,8 @@ class VecNormalize:
         if self.keep_original:
             self.old_obs, self.old_reward = obs.clone(), reward.clone()
         term = infos["terminal_observation"] if hasattr(infos, "__getitem__") else None
-        self._apply(obs, reward, done.view(torch.uint8), term, self.norm_reward)
+        done_u8 = self.venv._done if getattr(self.venv, "_done_bool", None) is done else done.view(torch.uint8)
+        self._apply(obs, reward, done_u8, term, self.norm_reward)
         return obs, reward, done, infos
 
     def step_async(self, actions):

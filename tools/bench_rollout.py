@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--envs", type=int, default=1 << 20)
     ap.add_argument("--steps", type=int, default=252)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--policies", default="no_hedge,random,delta_every_step,mlp,mlp_bf16")
+    ap.add_argument("--policies", default="no_hedge,random,delta_every_step,mlp,mlp_bf16,lstm_bf16")
     ap.add_argument("--sources", default="gbm,heston,replay")
     ap.add_argument("--store", action="store_true")
     a = ap.parse_args()
