@@ -80,6 +80,7 @@ class RbergomiParams(C.Structure):
 
 POLICY_NO_HEDGE, POLICY_RANDOM, POLICY_DELTA_BASELINES, POLICY_DELTA_BENCHMARK, POLICY_MLP, POLICY_ACTIONS, POLICY_LSTM = range(7)
 LSTM_IMAGE_BYTES = 178816
+SQUASH_CLIP, SQUASH_TANH = 0, 1
 MLP_FLOATS = 5212
 STATS_LEN = 16
 VECNORM_DOUBLES = 16704
@@ -87,7 +88,7 @@ VECNORM_DOUBLES = 16704
 
 class Policy(C.Structure):
     _fields_ = [("kind", C.c_int32), ("put_leg_disabled", C.c_int32), ("mlp", C.c_void_p), ("actions", C.c_void_p),
-                ("seed", C.c_uint64), ("mlp_tensor_cores", C.c_int32), ("reserved", C.c_int32)]
+                ("seed", C.c_uint64), ("mlp_tensor_cores", C.c_int32), ("action_squash", C.c_int32)]
 
 
 class StatsOut(C.Structure):

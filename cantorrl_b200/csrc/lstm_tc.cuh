@@ -391,7 +391,7 @@ struct Actor {
         uint32_t r0, r1;
         mlptc::tmem_ld2(lane_base() + kColGates + kPassN * grp + kColHeadOut, r0, r1);
         mlptc::tmem_ld_wait();
-        return make_float2(fminf(fmaxf(__uint_as_float(r0), -1.f), 1.f), fminf(fmaxf(__uint_as_float(r1), -1.f), 1.f));
+        return make_float2(__uint_as_float(r0), __uint_as_float(r1));         // action means; the caller squashes them
     }
 };
 

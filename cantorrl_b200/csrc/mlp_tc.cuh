@@ -235,7 +235,7 @@ struct Actor {
         uint32_t r0, r1;
         tmem_ld2(tmem + ((uint32_t)(m & ~31) << 16), r0, r1);
         tmem_ld_wait();
-        return make_float2(fminf(fmaxf(__uint_as_float(r0), -1.f), 1.f), fminf(fmaxf(__uint_as_float(r1), -1.f), 1.f));
+        return make_float2(__uint_as_float(r0), __uint_as_float(r1));         // action means; the caller squashes them
     }
 };
 

@@ -26,7 +26,7 @@ constexpr int kMlpFloats = kMlpIn * kMlpHidden + kMlpHidden + kMlpHidden * kMlpH
                            kMlpHidden * kMlpOut + kMlpOut + 2 * kMlpIn;          // 5212
 
 struct PolicyConsts {
-    int kind, put_disabled;
+    int kind, put_disabled, squash;
     const float* mlp;
     const float2* actions;      // CANTOR_POLICY_ACTIONS: [n_steps, n_envs] open-loop actions
     unsigned seed_lo, seed_hi;
@@ -122,7 +122,7 @@ __device__ __noinline__ float2 policy_mlp(const float* o, const float* __restric
         out0 = fmaf(a2, W3[(j + 2) * 2], out0); out1 = fmaf(a2, W3[(j + 2) * 2 + 1], out1);
         out0 = fmaf(a3, W3[(j + 3) * 2], out0); out1 = fmaf(a3, W3[(j + 3) * 2 + 1], out1);
     }
-    return make_float2(fminf(fmaxf(out0, -1.f), 1.f), fminf(fmaxf(out1, -1.f), 1.f));
+    return make_float2(out0, out1);                     // action means; the caller squashes them
 }
 
 // SRC: 0 replay (packed book), 1 GBM on the fly, 2 Heston on the fly.
@@ -232,6 +232,10 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                     case CANTOR_POLICY_ACTIONS: a = live ? __ldcs(pc.actions + (long long)g * n_envs + i) : make_float2(0.f, 0.f); break;
                     default: a = make_float2(0.f, 0.f);
                 }
+            }
+            if (MLP != 0) {                                                    // network policies return action means
+                if (pc.squash == CANTOR_SQUASH_TANH) a = make_float2(tanhf(a.x), tanhf(a.y));         // quantconnect/model_wrapper.py:202
+                else a = make_float2(fminf(fmaxf(a.x, -1.f), 1.f), fminf(fmaxf(a.y, -1.f), 1.f));   // SB3: clip to the Box
             }
             if (pc.put_disabled) a.y = 0.f;
             // ---- next path record -------------------------------------------------------------------------
@@ -353,7 +357,8 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
     }
     int rc = make_step_consts(params, T, &k);
     if (rc) return rc;
-    PolicyConsts pc{policy->kind, policy->put_leg_disabled, policy->mlp, (const float2*)policy->actions,
+    CANTOR_REQUIRE(policy->action_squash == CANTOR_SQUASH_CLIP || policy->action_squash == CANTOR_SQUASH_TANH, "policy.action_squash");
+    PolicyConsts pc{policy->kind, policy->put_leg_disabled, policy->action_squash, policy->mlp, (const float2*)policy->actions,
                     (unsigned)(policy->seed & 0xffffffffull), (unsigned)(policy->seed >> 32)};
     StatsOut so;
     rc = make_stats_out(stats, &so);

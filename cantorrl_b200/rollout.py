@@ -184,7 +184,7 @@ class HedgingRollout:
 
     def run(self, n_steps: int, policy: Union[str, torch.Tensor] = "delta_every_step", *, mlp: Optional[torch.Tensor] = None,
             actions: Optional[torch.Tensor] = None, seed: int = 0, stats: Optional[EpisodeStats] = None,
-            store: bool = False) -> RolloutResult:
+            store: bool = False, squash: str = "clip") -> RolloutResult:
         """``n_steps`` env-steps of every env (auto-reset at episode ends), statistics accumulated into ``stats``.
 
         policy   "no_hedge" | "random" | "delta_every_step" | "delta_benchmark" | "actions" (open loop, ``actions``
@@ -192,10 +192,15 @@ class HedgingRollout:
                  the parity form) | "mlp_bf16" (same weights on the tensor cores: bf16 operands, float32 accumulation)
                  | "lstm_bf16" (``mlp=pack_lstm(...)``: the recurrent LSTM + MLP actor the reference trained, tensor cores)
         store    also write the rollout (obs the policy saw, actions, reward, done), time-major
+        squash   network policies: "clip" the action means to [-1, 1] (SB3 stepping the env) or "tanh" (the reference's
+                 deployment wrapper, quantconnect/model_wrapper.py:202)
         """
         n, dev = self.num_envs, self.device
         pol = _lib.Policy()
         pol.put_leg_disabled = int(self.one_call_only)
+        if squash not in ("clip", "tanh"):
+            raise ValueError("squash must be 'clip' or 'tanh'")
+        pol.action_squash = _lib.SQUASH_TANH if squash == "tanh" else _lib.SQUASH_CLIP
         pol.seed = int(seed) & (2 ** 64 - 1)
         if policy in ("mlp", "mlp_bf16"):
             pol.mlp_tensor_cores = int(policy == "mlp_bf16")

@@ -313,8 +313,10 @@ typedef struct cantor_policy {
     const float* actions;                /* [n_steps, n_envs, 2] for CANTOR_POLICY_ACTIONS */
     uint64_t seed;                       /* CANTOR_POLICY_RANDOM */
     int32_t mlp_tensor_cores;            /* CANTOR_POLICY_MLP: 0 = float32 FFMA (parity form), 1 = bf16 tcgen05.mma (throughput form) */
-    int32_t reserved;
+    int32_t action_squash;               /* network policies: CANTOR_SQUASH_CLIP = clip the action means to [-1, 1] (what SB3 does with the
+                                            Box bounds when it steps the env), CANTOR_SQUASH_TANH = tanh (quantconnect/model_wrapper.py:202) */
 } cantor_policy;
+enum { CANTOR_SQUASH_CLIP = 0, CANTOR_SQUASH_TANH = 1 };
 
 /* sums[] layout; every entry is a plain sum over finished episodes, so shards combine by addition (all-reduce):
  *  0 n_episodes

@@ -80,11 +80,14 @@ def mlp_actor_bf16(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-
 
 
 def lstm_actor_sequence(obs_seq, done_seq, w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8,
-                        bf16=True):
+                        bf16=True, squash="clip"):
     """The recurrent actor LSTM(13 -> 128) -> ReLU MLP(128 -> 64 -> 64) -> 2 (quantconnect/model_wrapper.py:167-204) over an
     observation sequence ``[n_steps, n_envs, 13]``; the state (h, c) of an env is zeroed after a step on which it finished
     (``done_seq [n_steps, n_envs]``), as SB3 does at episode starts.  ``torch.nn.LSTM`` weight layout, gate order i, f, g, o.
 
+    ``squash``: "clip" (SB3 clips the action means to the Box when it steps the env) or "tanh" (the reference's deployment
+    wrapper, quantconnect/model_wrapper.py:202).  Pinned: with ``bf16=False, squash="tanh"`` this reproduces the reference's
+    own ``RecurrentPPOModel`` run on the shipped ``policy_weights.pth`` (tests/golden/lstm_golden.npz, tests/test_oracle_policy.py).
     ``bf16=True`` follows the rounding points of cantorrl_b200/csrc/lstm_tc.cuh (inputs, weights, biases, h and the head's
     activations in bfloat16; products accumulated wide; c in float32); ``bf16=False`` is the plain float64 network.
     """
@@ -111,7 +114,7 @@ def lstm_actor_sequence(obs_seq, done_seq, w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b
         a1 = np.maximum(hq @ A1.T + c1, 0)
         a2 = np.maximum(q(a1.astype(F32)).astype(np.float64) @ A2.T + c2, 0)
         o = q(a2.astype(F32)).astype(np.float64) @ A3.T + c3
-        out[t] = np.clip(o, -1, 1)
+        out[t] = np.tanh(o) if squash == "tanh" else np.clip(o, -1, 1)
         fin = np.asarray(done_seq[t], bool)
         h[fin] = 0
         c[fin] = 0

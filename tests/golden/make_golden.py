@@ -288,6 +288,64 @@ def make_rbergomi_golden():
     print(f"rbergomi_golden: pricer batch of {B} x {n_mc} inner paths (call, put) + generator 24 paths x 12 days")
 
 
+def make_lstm_golden():
+    """The shipped recurrent policy run by the reference's OWN network class on observations of the reference env.
+
+    ``quantconnect/model_wrapper.py: RecurrentPPOModel`` (LSTM(13, 128) -> Linear(128, 64) ReLU Linear(64, 64) ReLU ->
+    Linear(64, 2) -> tanh) with ``quantconnect/model_files/policy_weights.pth`` loaded through the key mapping of
+    ``ModelWrapper.LoadModel`` (:84-103) and the normalisation of ``ModelWrapper.predict`` (:131) with
+    ``normalization_stats.pkl``.  The hidden state is carried from step to step and zeroed after a terminated step (the
+    wrapper's ``reset_hidden_states``).  Inputs: steps 220-299 of the 4 reference envs of env_v2_train.npz (an episode boundary
+    inside), brought inside +-9.5 sigma of the shipped statistics.  The weights travel in the fixture: /root/reference does not exist on the GPU box."""
+    import pickle
+    import types
+
+    import torch
+    sys.modules.setdefault("AlgorithmImports", types.ModuleType("AlgorithmImports"))          # LEAN's star-import module
+    mw = _load("ref_model_wrapper", os.path.join(REF, "quantconnect", "model_wrapper.py"))
+    sd = torch.load(os.path.join(REF, "quantconnect", "model_files", "policy_weights.pth"), map_location="cpu", weights_only=False)
+    stats = pickle.load(open(os.path.join(REF, "quantconnect", "model_files", "normalization_stats.pkl"), "rb"))
+    model = mw.RecurrentPPOModel()
+    ours = {"lstm_actor." + k: sd["lstm_actor." + k] for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")}
+    for j in (0, 2):
+        for kind in ("weight", "bias"):
+            ours[f"mlp_extractor_policy_net.{j}.{kind}"] = sd[f"mlp_extractor.policy_net.{j}.{kind}"]
+    ours["action_net.weight"], ours["action_net.bias"], ours["log_std"] = sd["action_net.weight"], sd["action_net.bias"], sd["log_std"]
+    model.load_state_dict(ours)
+    model.eval()
+    env = np.load(os.path.join(HERE, "env_v2_train.npz"))
+    obs = np.concatenate([env["reset_obs"][:1], env["obs"][:300]], axis=0)[220:300].astype(np.float32)   # [80, 4, 13], crosses t = 252
+    done = np.concatenate([np.zeros((1, 4), bool), env["terminated"][:300].astype(bool)], axis=0)[220:300]
+    mean, var = np.asarray(stats["obs_mean"], np.float64), np.asarray(stats["obs_var"], np.float64)
+    # these envs run on paths.npy-derived data, not on the training set: the deltas reach 12 sigma and the variance change 35.
+    # The wrapper never clips (SB3's VecNormalize did, at 10, in training), so bring the inputs inside +-9.5 sigma: then the
+    # reference network, the oracle and the kernel (which clips at 10) all see the same thing.
+    obs = (mean + np.sqrt(var + 1e-8) * np.clip((obs - mean) / np.sqrt(var + 1e-8), -9.5, 9.5)).astype(np.float32)
+    n_steps, n = obs.shape[:2]
+    hid = (torch.zeros(1, n, 128), torch.zeros(1, n, 128))
+    acts = np.zeros((n_steps, n, 2), np.float32)
+    worst = 0.0
+    with torch.no_grad():
+        for t in range(n_steps):
+            x = (obs[t] - mean) / np.sqrt(var + 1e-8)                                          # model_wrapper.py:131
+            worst = max(worst, float(np.abs(x).max()))
+            xt = torch.as_tensor(x, dtype=torch.float32).unsqueeze(1)                          # [n, 1, 13], batch_first
+            a, hid = model(xt, hid)
+            acts[t] = a[:, 0].numpy()
+            fin = torch.as_tensor(done[t])
+            hid = (hid[0] * (~fin).float()[None, :, None], hid[1] * (~fin).float()[None, :, None])
+    assert worst < 10.0, worst            # VecNormalize's clip_obs = 10 never bites on these inputs
+    np.savez_compressed(os.path.join(HERE, "lstm_golden.npz"), obs=obs, done=done, actions=acts, obs_mean=mean.astype(np.float32),
+                        obs_var=var.astype(np.float32), max_abs_normalised_obs=worst,
+                        w_ih=sd["lstm_actor.weight_ih_l0"].numpy(), w_hh=sd["lstm_actor.weight_hh_l0"].numpy(),
+                        b_ih=sd["lstm_actor.bias_ih_l0"].numpy(), b_hh=sd["lstm_actor.bias_hh_l0"].numpy(),
+                        W1=sd["mlp_extractor.policy_net.0.weight"].numpy(), b1=sd["mlp_extractor.policy_net.0.bias"].numpy(),
+                        W2=sd["mlp_extractor.policy_net.2.weight"].numpy(), b2=sd["mlp_extractor.policy_net.2.bias"].numpy(),
+                        W3=sd["action_net.weight"].numpy(), b3=sd["action_net.bias"].numpy())
+    print(f"lstm_golden: {n_steps} steps x {n} envs through the reference's RecurrentPPOModel with the shipped weights; "
+          f"max |normalised obs| = {worst:.2f}, actions in [{acts.min():.3f}, {acts.max():.3f}]")
+
+
 def make_calibration_golden():
     """estimate_base_params (rbergomi_sim.py:171-193) of the unmodified reference on the shipped price history and on
     synthetic histories of several lengths (short ones exercise the default / guard branches)."""
@@ -330,6 +388,9 @@ if __name__ == "__main__":
     if "--rbergomi-only" in sys.argv:
         make_rbergomi_golden()
         sys.exit(0)
+    if "--lstm-only" in sys.argv:
+        make_lstm_golden()
+        sys.exit(0)
     if "--policy-only" in sys.argv:
         make_policy_golden()
         sys.exit(0)
@@ -339,3 +400,4 @@ if __name__ == "__main__":
     make_outer_euler_golden()
     make_rbergomi_golden()
     make_calibration_golden()
+    make_lstm_golden()

@@ -84,3 +84,19 @@ def test_episode_statistics_definitions():
     # baselines.py:49-65
     assert np.isclose(s["mean_abs_pnl_baseline"], np.mean([np.abs(r).sum() / 30 for r in pps]))
     assert np.isclose(s["mean_cost"], np.mean([r.sum() / 30 for r in cost]))
+
+
+def test_recurrent_policy_oracle_reproduces_the_reference_network_on_the_shipped_weights():
+    """oracle/rollout_oracle.lstm_actor_sequence against tests/golden/lstm_golden.npz: the reference's own RecurrentPPOModel
+    (quantconnect/model_wrapper.py:167-204) with the shipped policy_weights.pth and normalization_stats.pkl, hidden state
+    carried over 80 steps of 4 envs with an episode boundary inside (generator: tests/golden/make_golden.py --lstm-only)."""
+    from oracle import rollout_oracle
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lstm_golden.npz"))
+    w = {k: g[k] for k in ("w_ih", "w_hh", "b_ih", "b_hh", "W1", "b1", "W2", "b2", "W3", "b3")}
+    assert g["done"].any() and float(g["max_abs_normalised_obs"]) < 10.0
+    got = rollout_oracle.lstm_actor_sequence(g["obs"], g["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=False, squash="tanh")
+    np.testing.assert_allclose(got, g["actions"], rtol=0, atol=2e-6)           # float32 torch vs float64 NumPy
+    assert np.abs(g["actions"]).max() <= 1.0 and np.abs(g["actions"]).std() > 0.05
+    # the bf16 rounding points of the tensor-core kernel stay close to the float32 network on the real weights
+    q = rollout_oracle.lstm_actor_sequence(g["obs"], g["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=True, squash="tanh")
+    assert np.abs(q - g["actions"]).max() < 0.1 and np.abs(q - g["actions"]).mean() < 1e-2

@@ -4,6 +4,7 @@ Parity is checked TEACHER-FORCED: the kernel's stored actions drive the oracle e
 in the last float32 bit cannot fork the two trajectories; the policy itself is compared on the kernel's own
 observations.  fp32 tolerance of the north star: 1e-4 relative; done flags and episode counts exact.
 """
+import os
 import numpy as np
 import pytest
 import torch
@@ -207,3 +208,31 @@ def test_recurrent_lstm_actor_matches_oracle_over_episodes(n_envs):
     assert np.abs(got["actions"] - full).max() < 0.15 and np.abs(got["actions"] - full).mean() < 1e-2
     assert np.abs(want).mean() > 0.05                     # the network is not saturated / trivially zero
     assert stats.sums[0] == n_envs * (n_steps // T)
+
+
+def test_recurrent_policy_with_the_shipped_weights_and_tanh_squash():
+    """The policy the reference ships (quantconnect/model_files/policy_weights.pth + normalization_stats.pkl, carried in
+    tests/golden/lstm_golden.npz) inside the rollout kernel, squashed with tanh like the reference's deployment wrapper
+    (quantconnect/model_wrapper.py:202), against the oracle network -- which tests/test_oracle_policy.py pins on the
+    reference's own RecurrentPPOModel -- run over the kernel's observation sequence."""
+    from cantorrl_b200.rollout import HedgingRollout, pack_lstm
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lstm_golden.npz"))
+    w = {k: g[k] for k in ("w_ih", "w_hh", "b_ih", "b_hh", "W1", "b1", "W2", "b2", "W3", "b3")}
+    n_paths, T, n_envs, n_steps = 61, 16, 300, 40
+    S, V, C, P = _book(n_paths, T, heston=True)
+    ro = HedgingRollout(data=dict(paths=S, volatilities=V, call_prices_atm=C, put_prices_atm=P), num_envs=n_envs, **KW)
+    stats = ro.new_stats()
+    res = ro.run(n_steps, "lstm_bf16", mlp=pack_lstm(**w, obs_mean=g["obs_mean"], obs_var=g["obs_var"]), stats=stats, store=True,
+                 squash="tanh")
+    torch.cuda.synchronize()
+    assert float(stats.sums[15]) == 0.0, "a tcgen05 MMA timed out"
+    got = {k: getattr(res, k).cpu().numpy() for k in ("obs", "actions", "reward", "done")}
+    ref = rollout_oracle.run_rollout(S, V, C, P, EnvParams(**KW), "actions", n_envs, n_steps, forced_actions=got["actions"])
+    assert np.array_equal(got["done"], ref["done"])
+    np.testing.assert_allclose(got["obs"], ref["obs"], rtol=1e-4, atol=2e-6)
+    want = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=True, squash="tanh")
+    err = np.abs(got["actions"] - want)
+    assert err.max() < 2e-2 and err.mean() < 1e-3, (err.max(), err.mean())
+    full = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=False, squash="tanh")
+    assert np.abs(got["actions"] - full).mean() < 2e-2
+    assert np.abs(got["actions"]).max() <= 1.0 and got["actions"].std() > 0.05
