@@ -109,6 +109,28 @@ def pack_lstm(w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b2, W3, b3, obs_mean=None, obs
     return torch.from_numpy(img).to(device)
 
 
+def load_reference_policy(policy_weights_path, normalization_stats_path=None, device="cuda") -> torch.Tensor:
+    """The policy files the reference ships -> the ``pack_lstm`` image for ``run(..., "lstm_bf16", mlp=...)``.
+
+    ``policy_weights_path``: ``quantconnect/model_files/policy_weights.pth`` (keys ``lstm_actor.*``, ``mlp_extractor.policy_net.*``,
+    ``action_net.*``, mapped like ``ModelWrapper.LoadModel``, quantconnect/model_wrapper.py:84-103); ``normalization_stats_path``:
+    ``normalization_stats.pkl`` (``obs_mean`` / ``obs_var``, applied as :131).  The critic tensors are ignored."""
+    import pickle
+    sd = torch.load(policy_weights_path, map_location="cpu", weights_only=True)
+    need = ["lstm_actor.weight_ih_l0", "lstm_actor.weight_hh_l0", "lstm_actor.bias_ih_l0", "lstm_actor.bias_hh_l0",
+            "mlp_extractor.policy_net.0.weight", "mlp_extractor.policy_net.0.bias", "mlp_extractor.policy_net.2.weight",
+            "mlp_extractor.policy_net.2.bias", "action_net.weight", "action_net.bias"]
+    missing = [k for k in need if k not in sd]
+    if missing:
+        raise KeyError(f"{policy_weights_path}: missing {missing}")
+    mean = var = None
+    if normalization_stats_path is not None:
+        with open(normalization_stats_path, "rb") as f:
+            st = pickle.load(f)
+        mean, var = np.asarray(st["obs_mean"], np.float32), np.asarray(st["obs_var"], np.float32)
+    return pack_lstm(*[sd[k] for k in need], obs_mean=mean, obs_var=var, device=device)
+
+
 @dataclass
 class RolloutResult:
     stats: EpisodeStats

@@ -100,3 +100,15 @@ def test_recurrent_policy_oracle_reproduces_the_reference_network_on_the_shipped
     # the bf16 rounding points of the tensor-core kernel stay close to the float32 network on the real weights
     q = rollout_oracle.lstm_actor_sequence(g["obs"], g["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=True, squash="tanh")
     assert np.abs(q - g["actions"]).max() < 0.1 and np.abs(q - g["actions"]).mean() < 1e-2
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="needs /root/reference (build container only)")
+def test_load_reference_policy_packs_the_shipped_files_like_the_golden_weights():
+    """Host-side packing only (no GPU): the shipped files and the weights carried in the golden fixture give the same image."""
+    from cantorrl_b200.rollout import load_reference_policy, pack_lstm
+    mf = os.path.join(REFERENCE, "quantconnect", "model_files")
+    img = load_reference_policy(os.path.join(mf, "policy_weights.pth"), os.path.join(mf, "normalization_stats.pkl"), device="cpu")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lstm_golden.npz"))
+    w = {k: g[k] for k in ("w_ih", "w_hh", "b_ih", "b_hh", "W1", "b1", "W2", "b2", "W3", "b3")}
+    want = pack_lstm(**w, obs_mean=g["obs_mean"], obs_var=g["obs_var"], device="cpu")
+    assert img.dtype == want.dtype and img.shape == want.shape and bool((img == want).all())
