@@ -14,6 +14,46 @@ import torch
 from . import _lib
 
 
+def read_sb3_vecnormalize(path) -> dict:
+    """Statistics and hyper-parameters out of a pickle written by Stable-Baselines3's ``VecNormalize.save`` -- the file the
+    reference keeps next to its model (``train_ppo_v2.py:315-317``, loaded at ``:449-455``; shipped as
+    ``quantconnect/model_files/final_vecnormalize.pkl``) -- WITHOUT SB3 / gymnasium installed: their classes are replaced by
+    attribute bags while unpickling, everything outside NumPy / builtins / collections is refused."""
+    import pickle
+
+    class _Bag:
+        def __init__(self, *a, **k):
+            pass
+
+        def __setstate__(self, state):
+            self.__dict__.update(state if isinstance(state, dict) else {"_state": state})
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            root = module.split(".")[0]
+            if root in ("stable_baselines3", "sb3_contrib", "gymnasium", "gym"):
+                return type(name, (_Bag,), {"__module__": module})
+            if root in ("numpy", "collections", "builtins", "copyreg", "_codecs"):
+                return super().find_class(module, name)
+            raise pickle.UnpicklingError(f"refusing to unpickle {module}.{name}")
+
+    with open(path, "rb") as f:
+        o = _Unpickler(f).load()
+    try:
+        out = {"obs_mean": np.asarray(o.obs_rms.mean, np.float64), "obs_var": np.asarray(o.obs_rms.var, np.float64),
+               "obs_count": float(o.obs_rms.count), "ret_mean": float(o.ret_rms.mean), "ret_var": float(o.ret_rms.var),
+               "ret_count": float(o.ret_rms.count)}
+    except AttributeError as e:
+        raise ValueError(f"{path}: not a VecNormalize pickle ({e})") from None
+    if out["obs_mean"].shape != (13,):
+        raise ValueError(f"{path}: observation statistics of shape {out['obs_mean'].shape}, expected (13,)")
+    for k, default in (("clip_obs", 10.0), ("clip_reward", 10.0), ("gamma", 0.99), ("epsilon", 1e-8)):
+        out[k] = float(getattr(o, k, default))
+    for k in ("norm_obs", "norm_reward", "training"):
+        out[k] = bool(getattr(o, k, True))
+    return out
+
+
 class RunningMeanStdView:
     """``mean`` / ``var`` / ``count`` of one running statistic (views of the device buffer, float64)."""
 
@@ -138,6 +178,19 @@ class VecNormalize:
 
     @classmethod
     def load(cls, path, venv):
+        """``VecNormalize.load(path, venv)`` as the reference calls it (train_ppo_v2.py:449-455).  Accepts this class's own
+        ``save`` files and the pickles SB3's ``VecNormalize.save`` wrote (``read_sb3_vecnormalize``)."""
+        with open(path, "rb") as f:
+            magic = f.read(2)
+        if magic != b"PK":                                    # not a torch.save archive: an SB3 pickle
+            st = read_sb3_vecnormalize(path)
+            self = cls(venv, training=st["training"], norm_obs=st["norm_obs"], norm_reward=st["norm_reward"], clip_obs=st["clip_obs"],
+                       clip_reward=st["clip_reward"], gamma=st["gamma"], epsilon=st["epsilon"])
+            rms = torch.zeros(32, dtype=torch.float64)
+            rms[0:13], rms[13:26], rms[26] = torch.from_numpy(st["obs_mean"]), torch.from_numpy(st["obs_var"]), st["obs_count"]
+            rms[27], rms[28], rms[29] = st["ret_mean"], st["ret_var"], st["ret_count"]
+            self._rms[:32].copy_(rms)
+            return self
         sd = torch.load(path, weights_only=False)
         self = cls(venv, norm_obs=sd["norm_obs"], norm_reward=sd["norm_reward"], clip_obs=sd["clip_obs"], clip_reward=sd["clip_reward"],
                    gamma=sd["gamma"], epsilon=sd["epsilon"])

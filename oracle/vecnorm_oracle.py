@@ -13,8 +13,11 @@ this restates its published algorithm (``common/running_mean_std.py``, ``common/
   VecNormalize.reset: returns = 0; obs_rms.update(obs) [training]; normalise
   Monitor: info["episode"] = {"r": sum of rewards, "l": number of steps} at the end of an episode.
 
-Parity status: UNPINNED by any reference vector (no SB3 here, no stored statistics trajectory in the reference); the only
-reference anchor is the application formula quantconnect/model_wrapper.py:131, which ``normalize_obs`` follows.
+Parity status: the update TRAJECTORY is unpinned (no SB3 here, no stored statistics trajectory in the reference).  Two
+reference anchors exist and are checked: the application formula quantconnect/model_wrapper.py:131, which ``normalize_obs``
+follows, and the shipped SB3 pickle quantconnect/model_files/final_vecnormalize.pkl, readable without SB3
+(cantorrl_b200/vecnorm.py: read_sb3_vecnormalize), which confirms count0 = 1e-4, the reset batch going to the observation
+statistics only, clip_obs = clip_reward = 10 and epsilon = 1e-8 (tests/test_oracle_policy.py).
 """
 from __future__ import annotations
 

@@ -112,3 +112,29 @@ def test_load_reference_policy_packs_the_shipped_files_like_the_golden_weights()
     w = {k: g[k] for k in ("w_ih", "w_hh", "b_ih", "b_hh", "W1", "b1", "W2", "b2", "W3", "b3")}
     want = pack_lstm(**w, obs_mean=g["obs_mean"], obs_var=g["obs_var"], device="cpu")
     assert img.dtype == want.dtype and img.shape == want.shape and bool((img == want).all())
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="needs /root/reference (build container only)")
+def test_shipped_sb3_vecnormalize_pickle_is_readable_without_sb3_and_confirms_the_restated_conventions():
+    """quantconnect/model_files/final_vecnormalize.pkl (SB3 2.6.0's VecNormalize.save) read with SB3 absent.  It is the one
+    artefact of SB3's VecNormalize the reference ships, and it pins the conventions oracle/vecnorm_oracle.py restates from
+    documentation: count starts at 1e-4, the observation statistics see one extra batch (the reset) that the return
+    statistics do not, clip_obs = clip_reward = 10, epsilon = 1e-8; its mean / var are the shipped normalization_stats.pkl."""
+    import pickle
+    from cantorrl_b200.vecnorm import read_sb3_vecnormalize
+    mf = os.path.join(REFERENCE, "quantconnect", "model_files")
+    st = read_sb3_vecnormalize(os.path.join(mf, "final_vecnormalize.pkl"))
+    with open(os.path.join(mf, "normalization_stats.pkl"), "rb") as f:
+        shipped = pickle.load(f)
+    assert np.array_equal(st["obs_mean"], np.asarray(shipped["obs_mean"])) and np.array_equal(st["obs_var"], np.asarray(shipped["obs_var"]))
+    assert st["clip_obs"] == 10.0 and st["clip_reward"] == 10.0 and st["epsilon"] == 1e-8 and st["norm_obs"] and st["norm_reward"]
+    steps = st["ret_count"] - 1e-4
+    assert abs(steps - round(steps)) < 1e-6 and steps > 1e5                                   # RunningMeanStd(epsilon=1e-4).count
+    n_envs = st["obs_count"] - st["ret_count"]
+    assert abs(n_envs - round(n_envs)) < 1e-6 and 1 <= round(n_envs) <= 8                     # the reset batch: obs only
+    with pytest.raises(Exception):
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".pkl") as f:                                 # anything but numpy / builtins is refused
+            pickle.dump(os.path.join, f)
+            f.flush()
+            read_sb3_vecnormalize(f.name)

@@ -145,3 +145,50 @@ def test_vecnormalize_statistics_are_bitwise_reproducible():
         runs.append((vn._rms[:30].clone(), obs.clone(), r.clone(), vn.returns.clone()))
     for x, y in zip(*runs):
         assert torch.equal(x, y)
+
+
+def test_vecnormalize_load_accepts_an_sb3_pickle():
+    """``VecNormalize.load(path, venv)`` on a file in the format SB3's ``VecNormalize.save`` writes (the reference:
+    train_ppo_v2.py:315-317, 449-455).  SB3 is not installed, so the pickle is produced from stand-in classes registered under
+    SB3's module paths, which are removed again before loading."""
+    import pickle
+    import sys
+    import types
+    from cantorrl_b200 import HedgingVecEnv
+    from cantorrl_b200.vecnorm import VecNormalize
+    names = ["stable_baselines3", "stable_baselines3.common", "stable_baselines3.common.running_mean_std",
+             "stable_baselines3.common.vec_env", "stable_baselines3.common.vec_env.vec_normalize"]
+    mods = {n: types.ModuleType(n) for n in names}
+    rms_cls = type("RunningMeanStd", (), {"__module__": names[2]})
+    vn_cls = type("VecNormalize", (), {"__module__": names[4]})
+    mods[names[2]].RunningMeanStd, mods[names[4]].VecNormalize = rms_cls, vn_cls
+    sys.modules.update(mods)
+    try:
+        rng = np.random.default_rng(4)
+        o, r, v = rms_cls(), rms_cls(), vn_cls()
+        o.mean, o.var, o.count = rng.normal(0, 1, 13), rng.uniform(0.1, 2, 13), 5000.0001
+        r.mean, r.var, r.count = np.float64(-0.05), np.float64(0.0025), 4996.0001
+        v.obs_rms, v.ret_rms, v.clip_obs, v.clip_reward, v.gamma, v.epsilon = o, r, 10.0, 10.0, 0.98, 1e-8
+        v.norm_obs, v.norm_reward, v.training, v.venv = True, True, True, None
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "final_vecnormalize.pkl")
+            with open(path, "wb") as f:
+                pickle.dump(v, f)
+            for n in names:
+                del sys.modules[n]
+            S, V, C, P = _data(n_paths=16, T=5)
+            env = HedgingVecEnv(data=dict(paths=S, volatilities=V, call_prices_atm=C, put_prices_atm=P), num_envs=64,
+                                episode_sampler="same_path", **KW)
+            vn = VecNormalize.load(path, env)
+    finally:
+        for n in names:
+            sys.modules.pop(n, None)
+    np.testing.assert_array_equal(vn.obs_rms.mean.cpu().numpy(), o.mean)
+    np.testing.assert_array_equal(vn.obs_rms.var.cpu().numpy(), o.var)
+    assert vn.obs_rms.count == 5000.0001 and vn.ret_rms.count == 4996.0001 and vn.gamma == 0.98 and float(vn.ret_rms.var) == 0.0025
+    vn.training, vn.keep_original = False, True
+    vn.reset()
+    obs, rew, _, _ = vn.step(torch.zeros((64, 2), device="cuda"))
+    raw = vn.get_original_obs().double().cpu().numpy()
+    want = np.clip((raw - o.mean) / np.sqrt(o.var + 1e-8), -10, 10)
+    np.testing.assert_allclose(obs.cpu().numpy(), want, rtol=1e-5, atol=5e-6)
