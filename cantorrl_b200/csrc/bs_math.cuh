@@ -92,11 +92,17 @@ __device__ __forceinline__ AtmCore atm_core_f32(float S, float K, float vv, floa
     AtmCore c;
     const float Kc = fmaxf(K, 1e-6f);
     c.rs = mufu_rsqrt(vv);                                                     // 1 / sigma
-    // log(S / K) with K = rint(S).  The reference rounds the quotient to float32 before the log (:99); with a
-    // floored sigma that rounding is amplified by 1 / (sigma sqrt(T)) ~ 3e4 in d1, so it is reproduced (IEEE
-    // division), and log(q) is taken through the log1p series of u = q - 1 (exact subtraction; |u| <= 1/16:
-    // error < u^7/7) because lg2.approx only bounds the ABSOLUTE error near 1.
-    const float u = __fdiv_rn(S, Kc) - 1.0f;
+    c.inv_sst = c.rs * inv_sqrtT;                                              // 1 / (sigma sqrt(T))
+    // log(S / K) with K = rint(S), through u = S / K - 1.  The reference rounds the quotient to float32 before the log
+    // (:99); that rounding (<= 6e-8 in u) is amplified by 1 / (sigma sqrt(T)) in d1 -- 3e4 with a floored sigma -- so
+    // there it is reproduced bit for bit with an IEEE division.  At ordinary volatilities (amplification <= 64: a d1
+    // difference < 5e-6, far inside the 1e-4 tolerance) u = (S - K) / K, with the subtraction exact (|S - K| <= 1/2,
+    // Sterbenz) and one MUFU reciprocal, is both cheaper (3 instructions instead of ~15) and closer to the exact value.
+    float u;
+    if (c.inv_sst <= 64.0f) u = (S - Kc) * mufu_rcp(Kc);
+    else u = __fdiv_rn(S, Kc) - 1.0f;
+    // log(1 + u) through the log1p series (|u| <= 1/16: error < u^7 / 7) because lg2.approx only bounds the ABSOLUTE
+    // error near 1.
     float lg;
     if (fabsf(u) <= 0.0625f) {
         float s = fmaf(u, -1.0f / 6.0f, 0.2f);
@@ -108,7 +114,6 @@ __device__ __forceinline__ AtmCore atm_core_f32(float S, float K, float vv, floa
         lg = mufu_lg2(1.0f + u) * kLn2f;
     }
     const float num = fmaf(fmaf(0.5f, vv, r), T, lg);
-    c.inv_sst = c.rs * inv_sqrtT;                                              // 1 / (sigma sqrt(T))
     c.d1 = num * c.inv_sst;
     c.pdf = normal_pdf_cdf(c.d1, &c.cdf, &c.cdf_m1);
     return c;
