@@ -24,7 +24,8 @@ sim_paths_kernel(const SimConsts k, int n_paths, float4* __restrict__ rec, long 
     float S = k.s0, v = k.v0;
     float4 out = make_float4(S, fmaxf(v, 0.0f), 0.f, 0.f);
     if (k.reprice) { const AtmQuote q = atm_quote_f32(out.x, out.y, k); out.z = q.call; out.w = q.put; }
-    __stcs(rec + p, out);                                                    // row 0
+    float4* dst = rec + p;                                                   // stepped by one row per day (no 64-bit index arithmetic in the loop)
+    __stcs(dst, out);                                                        // row 0
     constexpr int NPS = MODEL == 0 ? 1 : 2;                                  // normals per step
     int t = 0;
     for (unsigned call = 0; t < k.T; ++call) {                               // one Philox call = 4 normals
@@ -39,7 +40,8 @@ sim_paths_kernel(const SimConsts k, int n_paths, float4* __restrict__ rec, long 
                 out.y = fmaxf(v, 0.0f);
                 // row T has no option columns in the reference schema: it repeats the marks of row T-1
                 if (k.reprice && t < k.T) { const AtmQuote q = atm_quote_f32(out.x, out.y, k); out.z = q.call; out.w = q.put; }
-                __stcs(rec + (long long)t * ld + p, out);
+                dst += ld;
+                __stcs(dst, out);
             }
         }
     }
