@@ -236,3 +236,31 @@ def test_recurrent_policy_with_the_shipped_weights_and_tanh_squash():
     full = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=False, squash="tanh")
     assert np.abs(got["actions"] - full).mean() < 2e-2
     assert np.abs(got["actions"]).max() <= 1.0 and got["actions"].std() > 0.05
+
+
+def test_config2_size_heston_16m_paths_replay_equals_on_the_fly():
+    """BASELINE configs[2] at its full size: 2^24 Heston paths x 252 days generated into a 68 GB packed book (K1), a whole
+    episode of every env replayed from it, and the same episode simulated on the fly inside the rollout kernel: the
+    statistics of the two are identical (same device functions, same Philox counters), every env finishes exactly one
+    episode, the martingale holds.  Needs ~75 GB of HBM."""
+    from cantorrl_b200 import sim
+    from cantorrl_b200.rollout import HedgingRollout
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a 180 GB B200")
+    n, T = 1 << 24, 252
+    book = sim.generate_paths_and_options(n, model="heston", n_steps=T)
+    assert book.tensor.shape[0] == T + 1 and bool(torch.isfinite(book.tensor[-1]).all())
+    assert abs(float(book.tensor[T, :n, 0].double().mean()) / (100 * np.exp(0.04)) - 1) < 2e-3      # E[S_T] = S_0 e^{rT}
+    ro = HedgingRollout(data=book, num_envs=n, **KW)
+    st = ro.new_stats()
+    ro.run(T, "delta_every_step", stats=st)
+    torch.cuda.synchronize()
+    replayed = st.sums[:12].clone()
+    del ro, book, st
+    torch.cuda.empty_cache()
+    ro = HedgingRollout(simulate=dict(model="heston", n_steps=T), num_envs=n, **KW)
+    st = ro.new_stats()
+    ro.run(T, "delta_every_step", stats=st)
+    torch.cuda.synchronize()
+    assert float(st.sums[0]) == n and float(st.sums[11]) == float(n) * T
+    assert torch.allclose(st.sums[:12], replayed, rtol=1e-9, atol=0)
