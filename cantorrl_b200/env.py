@@ -371,10 +371,20 @@ class HedgingVecEnv:
         n = self.num_envs if indices is None else len(np.atleast_1d(indices))
         return [getattr(self, name)] * n
 
+    def set_attr(self, attr_name, value, indices=None):
+        raise AttributeError(f"{attr_name}: the envs of a HedgingVecEnv share one configuration; construct a new one")
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        raise AttributeError(f"{method_name}: there are no per-env Python objects behind a HedgingVecEnv")
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [False] * n
+
     def close(self):
         pass
 
-    def render(self):
+    def render(self, mode=None):
         pass
 
     # per-env views of the state the reference exposes as attributes (delta_and_nothing.py:71-78)

@@ -17,6 +17,26 @@ from . import _lib
 _KEYS = ("paths", "volatilities", "call_prices_atm", "put_prices_atm")
 
 
+class _EmptyInfos:
+    """``infos`` of a step as SB3 indexes it (``infos[i].get(...)``, ``len(infos)``) without building N dicts per step."""
+
+    def __init__(self, n):
+        self._n = n
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [{} for _ in range(*i.indices(self._n))]
+        if not -self._n <= int(i) < self._n:
+            raise IndexError(i)
+        return {}
+
+    def __iter__(self):
+        return ({} for _ in range(self._n))
+
+
 class HostVecEnv:
     def __init__(self, data_file_path=None, transaction_cost_per_contract=0.65, lambda_cost=1.0, pnl_penalty_weight=0.01,
                  theta_weight=0.0, slippage_bps=0.0, loss_type="abs", initial_cash=0.0, shares_to_hedge=10000,
@@ -71,6 +91,7 @@ class HostVecEnv:
         self.episode_length = L.cantor_vecenv_episode_length(self._h)
         self.num_episodes = L.cantor_vecenv_num_paths(self._h)
         mode = {"same_path": _lib.RESET_SAME_PATH, "philox": _lib.RESET_PHILOX, "array": _lib.RESET_FROM_ARRAY}[episode_sampler]
+        self._reset_mode, self._env_offset = mode, int(env_offset)
         if mode != _lib.RESET_FROM_ARRAY:
             _lib.check(L.cantor_vecenv_set_reset_rule(self._h, mode, int(seed) & (2 ** 64 - 1), int(env_offset)))
         n = self.num_envs
@@ -104,7 +125,46 @@ class HostVecEnv:
         _lib.check(_lib.lib().cantor_vecenv_step_host(self._h, a.ctypes.data, self._obs.ctypes.data, self._reward.ctypes.data,
                                                       self._done.ctypes.data, None if nxt is None else nxt.ctypes.data),
                    "cantor_vecenv_step_host")
-        return self._obs, self._reward, self._done.view(np.bool_), {}
+        return self._obs, self._reward, self._done.view(np.bool_), _EmptyInfos(self.num_envs)
+
+    # -- the rest of SB3's VecEnv protocol (stable_baselines3.common.vec_env.base_vec_env.VecEnv) ---------------
+    @property
+    def observation_space(self):
+        from .env import OBS_HIGH, OBS_LOW, Box                # hedging_env_v2.py:62-68 (needs torch, like every device class)
+        return Box(OBS_LOW, OBS_HIGH, (13,), np.float32)
+
+    @property
+    def action_space(self):
+        from .env import Box
+        return Box(-1.0, 1.0, (2,), np.float32)
+
+    def step_async(self, actions):
+        self._pending_actions = actions
+
+    def step_wait(self):
+        return self.step(self._pending_actions)
+
+    def get_attr(self, attr_name, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [getattr(self, attr_name)] * n
+
+    def set_attr(self, attr_name, value, indices=None):
+        raise AttributeError(f"{attr_name}: the envs of a HostVecEnv share one configuration; construct a new one")
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        raise AttributeError(f"{method_name}: there are no per-env Python objects behind a HostVecEnv")
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = self.num_envs if indices is None else len(np.atleast_1d(indices))
+        return [False] * n
+
+    def seed(self, seed=None):
+        if seed is not None:
+            _lib.check(_lib.lib().cantor_vecenv_set_reset_rule(self._h, self._reset_mode, int(seed) & (2 ** 64 - 1), self._env_offset))
+        return [seed] * self.num_envs
+
+    def render(self, mode=None):
+        return None
 
     def close(self):
         if getattr(self, "_h", None):

@@ -70,3 +70,23 @@ def test_simulated_book_on_the_host_path():
         tot += int(d.sum())
         assert np.isfinite(r).all() and np.isfinite(obs).all()
     assert tot == 4096 and d.all()
+
+
+def test_host_env_speaks_the_sb3_vecenv_protocol():
+    """The duck-typed surface SB3's algorithms use on a VecEnv (base_vec_env.VecEnv): spaces, step_async / step_wait,
+    get_attr("episode_length") (train_ppo_v2.py:463), env_is_wrapped, seed, indexable infos."""
+    from cantorrl_b200.host_env import HostVecEnv
+    env = HostVecEnv(num_envs=6, simulate=dict(num_paths=6, n_steps=5), slippage_bps=1.0, episode_sampler="philox", seed=3)
+    assert env.observation_space.shape == (13,) and env.action_space.shape == (2,) and env.action_space.dtype == np.float32
+    assert env.get_attr("episode_length") == [5] * 6 and env.get_attr("episode_length", [0, 2]) == [5, 5]
+    assert env.env_is_wrapped(object) == [False] * 6 and env.seed(11) == [11] * 6
+    obs = env.reset()
+    assert obs.shape == (6, 13) and obs.dtype == np.float32
+    for t in range(5):
+        env.step_async(np.stack([env.action_space.sample() for _ in range(6)]))
+        obs, rew, done, infos = env.step_wait()
+        assert len(infos) == 6 and infos[3].get("terminal_observation") is None and infos[-1] == {}
+    assert done.all() and done.dtype == np.bool_
+    with pytest.raises(AttributeError):
+        env.set_attr("lambda_cost", 2.0)
+    env.close()
