@@ -50,8 +50,8 @@ struct RunningVolF32 {
 
 template <bool GREEKS>
 __global__ void __launch_bounds__(kBookThreads)
-book_f32_kernel(const float4* __restrict__ rec, long long ld, int n_paths, int T, float r, const float* __restrict__ strike_mult,
-                int M, int sigma_from_book, float fixed_tenor, const BookOut out) {
+book_f32_kernel(const float4* __restrict__ rec, long long ld, long long out_ld, int n_paths, int T, float r,
+                const float* __restrict__ strike_mult, int M, int sigma_from_book, float fixed_tenor, const BookOut out) {
     __shared__ float s_mult[kBookMaxStrikes], s_lnm[kBookMaxStrikes], s_invm[kBookMaxStrikes];
     extern __shared__ float s_grid[];                 // [5][T+1]: T_t, sqrt, 1/sqrt, disc, 1/disc
     float* g_T = s_grid;
@@ -83,7 +83,7 @@ book_f32_kernel(const float4* __restrict__ rec, long long ld, int n_paths, int T
     const float K0 = rintf(S0);                                               // np.round: half to even (:36)
     RunningVolF32 rv;
     float prev = S0;
-    const long long plane = (long long)(T + 1) * ld;
+    const long long plane = (long long)(T + 1) * out_ld;
     for (int t = 0; t <= T; ++t) {
         const float4 rc = __ldcs(rec + (long long)t * ld + p);
         const float S = rc.x;
@@ -107,10 +107,10 @@ book_f32_kernel(const float4* __restrict__ rec, long long ld, int n_paths, int T
         const float k0d = K0 * disc;                                          // K_0 e^{-rT}
         const float s_over_k0d = S * mufu_rcp(K0) * g_idisc[t];               // S / (K_0 e^{-rT})
         const float gamma_scale = GREEKS ? inv_sst * mufu_rcp(S) : 0.f;
-        float* pc = out.calls + (long long)t * ld + p;                        // strike m lives `m * plane` further on
-        float* pp = out.puts + (long long)t * ld + p;
-        float* pd = (GREEKS && out.deltas != nullptr) ? out.deltas + (long long)t * ld + p : nullptr;
-        float* pg = (GREEKS && out.gammas != nullptr) ? out.gammas + (long long)t * ld + p : nullptr;
+        float* pc = out.calls + (long long)t * out_ld + p;                        // strike m lives `m * plane` further on
+        float* pp = out.puts + (long long)t * out_ld + p;
+        float* pd = (GREEKS && out.deltas != nullptr) ? out.deltas + (long long)t * out_ld + p : nullptr;
+        float* pg = (GREEKS && out.gammas != nullptr) ? out.gammas + (long long)t * out_ld + p : nullptr;
         if (Tt <= 0.f) {                                                      // :17-20 intrinsic value at expiry (uniform in t)
             for (int m = 0; m < M; ++m) {
                 const float K = K0 * s_mult[m], kd = k0d * s_mult[m];
@@ -162,12 +162,12 @@ book_f32_kernel(const float4* __restrict__ rec, long long ld, int n_paths, int T
 
 using namespace cantor;
 
-extern "C" int cantor_reprice_book(const float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length, double r,
-                                   const float* strike_mult, int32_t n_strikes, int32_t sigma_source, double fixed_tenor,
-                                   float* calls, float* puts, float* deltas, float* gammas, void* stream) {
+extern "C" int cantor_reprice_book_strided(const float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length, double r,
+                                           const float* strike_mult, int32_t n_strikes, int32_t sigma_source, double fixed_tenor,
+                                           int64_t out_ld, float* calls, float* puts, float* deltas, float* gammas, void* stream) {
     CANTOR_REQUIRE(svcp && strike_mult && calls && puts, "array is NULL");
     CANTOR_REQUIRE(aligned16(svcp), "svcp must be 16-byte aligned");
-    CANTOR_REQUIRE(n_paths > 0 && episode_length > 0 && ld >= n_paths, "bad shape");
+    CANTOR_REQUIRE(n_paths > 0 && episode_length > 0 && ld >= n_paths && out_ld >= n_paths, "bad shape");
     CANTOR_REQUIRE(n_strikes >= 1 && n_strikes <= kBookMaxStrikes, "n_strikes must be in [1, 32]");
     CANTOR_REQUIRE(episode_length + 1 <= kBookMaxGrid, "episode_length too large for the shared-memory maturity grid");
     CANTOR_REQUIRE(sigma_source == CANTOR_SIGMA_REALISED || sigma_source == CANTOR_SIGMA_BOOK_VARIANCE, "sigma_source");
@@ -177,10 +177,17 @@ extern "C" int cantor_reprice_book(const float* svcp, int64_t ld, int32_t n_path
     const size_t smem = 5 * (size_t)(episode_length + 1) * sizeof(float);
     cudaStream_t s = (cudaStream_t)stream;
     if (deltas != nullptr || gammas != nullptr)
-        book_f32_kernel<true><<<grid, kBookThreads, smem, s>>>((const float4*)svcp, ld, n_paths, episode_length, (float)r,
+        book_f32_kernel<true><<<grid, kBookThreads, smem, s>>>((const float4*)svcp, ld, out_ld, n_paths, episode_length, (float)r,
                                                                strike_mult, n_strikes, sigma_source, (float)fixed_tenor, out);
     else
-        book_f32_kernel<false><<<grid, kBookThreads, smem, s>>>((const float4*)svcp, ld, n_paths, episode_length, (float)r,
+        book_f32_kernel<false><<<grid, kBookThreads, smem, s>>>((const float4*)svcp, ld, out_ld, n_paths, episode_length, (float)r,
                                                                 strike_mult, n_strikes, sigma_source, (float)fixed_tenor, out);
     return check_launch("book_f32_kernel");
+}
+
+extern "C" int cantor_reprice_book(const float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length, double r,
+                                   const float* strike_mult, int32_t n_strikes, int32_t sigma_source, double fixed_tenor,
+                                   float* calls, float* puts, float* deltas, float* gammas, void* stream) {
+    return cantor_reprice_book_strided(svcp, ld, n_paths, episode_length, r, strike_mult, n_strikes, sigma_source, fixed_tenor, ld,
+                                       calls, puts, deltas, gammas, stream);
 }

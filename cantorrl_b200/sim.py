@@ -130,7 +130,8 @@ def process_price_paths(paths, r=R, strike_multipliers=(1.0,), device="cuda", re
     return (calls, puts, vols.T) if return_vols else (calls, puts)
 
 
-def reprice_book(book: ReplayData, strike_multipliers=(1.0,), r=R, sigma="realised", tenor=None, greeks=False):
+def reprice_book(book: ReplayData, strike_multipliers=(1.0,), r=R, sigma="realised", tenor=None, greeks=False, path_range=None,
+                 out=None):
     """Float32 multi-strike Black-Scholes book along every path of a packed book (BASELINE configs[2]).
 
     ``process_price_paths`` (option_price_assignment.py:33-52) in throughput form: K_m = round(S_0) * mult_m, maturity to
@@ -138,20 +139,48 @@ def reprice_book(book: ReplayData, strike_multipliers=(1.0,), r=R, sigma="realis
     ``sigma="book"`` uses the book's instantaneous variance (Heston).  Returns time-major device tensors
     ``calls, puts`` of shape ``[M, T+1, n_paths]`` (+ ``deltas, gammas`` with ``greeks=True``); ``.permute(0, 2, 1)``
     gives the reference's path-major ``(n, T+1)`` planes.
+
+    ``path_range=(first, last)`` prices that slice of the paths only, into arrays of the slice's width (``out``: a tuple of
+    such tensors to reuse): the way through a book whose full output does not fit (``reprice_book_slices``).
     """
     if sigma not in ("realised", "book"):
         raise ValueError("sigma must be 'realised' or 'book'")
     dev = book.device
     mult = torch.as_tensor(np.asarray(list(strike_multipliers), np.float32)).to(dev)
     M, T1, ld = int(mult.numel()), book.episode_length + 1, book.ld
-    outs = [torch.empty((M, T1, ld), dtype=torch.float32, device=dev) for _ in range(4 if greeks else 2)]
+    first, last = (0, book.n_paths) if path_range is None else (int(path_range[0]), int(path_range[1]))
+    if not 0 <= first < last <= book.n_paths:
+        raise ValueError(f"path_range {path_range} outside [0, {book.n_paths}]")
+    width = last - first
+    out_ld = ld if path_range is None else (width + 3) // 4 * 4
+    n_out = 4 if greeks else 2
+    if out is None:
+        outs = [torch.empty((M, T1, out_ld), dtype=torch.float32, device=dev) for _ in range(n_out)]
+    else:
+        outs = list(out)
+        if len(outs) != n_out or any(o.shape != (M, T1, out_ld) or o.dtype != torch.float32 or not o.is_contiguous() for o in outs):
+            raise ValueError(f"out must be {n_out} contiguous float32 tensors of shape {(M, T1, out_ld)}")
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().cantor_reprice_book(
-            book.tensor.data_ptr(), ld, book.n_paths, book.episode_length, float(r), mult.data_ptr(), M,
-            _lib.SIGMA_REALISED if sigma == "realised" else _lib.SIGMA_BOOK_VARIANCE, float(tenor or 0.0),
+        _lib.check(_lib.lib().cantor_reprice_book_strided(
+            book.tensor.data_ptr() + 16 * first, ld, width, book.episode_length, float(r), mult.data_ptr(), M,
+            _lib.SIGMA_REALISED if sigma == "realised" else _lib.SIGMA_BOOK_VARIANCE, float(tenor or 0.0), out_ld,
             outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr() if greeks else None,
-            outs[3].data_ptr() if greeks else None, _stream(dev)), "cantor_reprice_book")
-    return tuple(o[:, :, :book.n_paths] for o in outs)
+            outs[3].data_ptr() if greeks else None, _stream(dev)), "cantor_reprice_book_strided")
+    return tuple(o[:, :, :width] for o in outs)
+
+
+def reprice_book_slices(book: ReplayData, strike_multipliers=(1.0,), paths_per_slice=1 << 21, **kw):
+    """``reprice_book`` over consecutive path slices, yielding ``(first, last, outputs)``; the output tensors are REUSED from
+    slice to slice (copy or consume them before advancing).  BASELINE configs[2]: 2^24 Heston paths x 8 strikes."""
+    bufs = None
+    for first in range(0, book.n_paths, int(paths_per_slice)):
+        last = min(first + int(paths_per_slice), book.n_paths)
+        if bufs is not None and bufs[0].shape[2] != (last - first + 3) // 4 * 4:
+            bufs = None
+        res = reprice_book(book, strike_multipliers, path_range=(first, last), out=bufs, **kw)
+        if bufs is None:
+            bufs = tuple(r._base if r._base is not None else r for r in res)
+        yield first, last, res
 
 
 def calculate_annualized_vol_matrix(paths, device="cuda"):

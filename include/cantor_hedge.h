@@ -236,6 +236,12 @@ enum { CANTOR_SIGMA_REALISED = 0, CANTOR_SIGMA_BOOK_VARIANCE = 1 };
 int cantor_reprice_book(const float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length, double r,
                         const float* strike_mult, int32_t n_strikes, int32_t sigma_source, double fixed_tenor,
                         float* calls, float* puts, float* deltas, float* gammas, void* stream);
+/* The same with its own leading dimension for the outputs ([n_strikes * (T+1) * out_ld], out_ld >= n_paths): a slice of the
+ * paths of a large book (svcp + 4 * first_path, n_paths = slice width, ld = the book's) is priced into slice-sized arrays --
+ * BASELINE configs[2]'s 2^24-path book x 8 strikes would need 259 GB of outputs in one piece. */
+int cantor_reprice_book_strided(const float* svcp, int64_t ld, int32_t n_paths, int32_t episode_length, double r,
+                                const float* strike_mult, int32_t n_strikes, int32_t sigma_source, double fixed_tenor,
+                                int64_t out_ld, float* calls, float* puts, float* deltas, float* gammas, void* stream);
 /* bs_delta_hedge (src/tools/bs_delta.py:36-55): per-path delta-hedge P&L, time-major paths -> pnl [(T+1) * ld]. */
 int cantor_bs_delta_hedge(const double* paths, int32_t n_paths, int32_t episode_length, int64_t ld, double r,
                           double dt, double* pnl, void* stream);

@@ -84,6 +84,46 @@ def test_book_on_simulated_heston_paths_full_width_properties():
         assert float(((calls[m] - puts[m]) - rhs).abs().max()) < 5e-4
 
 
+def test_book_in_path_slices_equals_the_book_in_one_piece():
+    """``reprice_book_slices`` / ``cantor_reprice_book_strided``: ragged slices of the paths priced into slice-sized arrays are
+    bit-equal to the corresponding columns of the one-piece book (realised sigma: a per-path running statistic; with greeks)."""
+    from cantorrl_b200 import sim
+    n, T = 1000, 20
+    book = sim.generate_paths_and_options(n, n_steps=T, model="heston", reprice=False)
+    mult = np.array([0.95, 1.0, 1.07], np.float32)
+    for kw in (dict(sigma="realised"), dict(sigma="book", greeks=True, tenor=30 / 252)):
+        whole = sim.reprice_book(book, mult, **kw)
+        seen = 0
+        for first, last, part in sim.reprice_book_slices(book, mult, paths_per_slice=301, **kw):
+            assert first == seen and len(part) == len(whole)
+            for w, q in zip(whole, part):
+                a, b = w[:, :, first:last], q
+                assert a.shape == b.shape and bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+            seen = last
+        assert seen == n
+    with pytest.raises(ValueError):
+        sim.reprice_book(book, mult, path_range=(10, 5))
+
+
+def test_config2_size_multi_strike_book_in_slices():
+    """BASELINE configs[2] at full size: 2^24 Heston paths x 253 days x 8 strikes priced in 2^21-path slices (the one-piece
+    output would be 259 GB); put-call parity and monotonicity in the strike on every slice.  Needs ~100 GB of HBM."""
+    from cantorrl_b200 import sim
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs a 180 GB B200")
+    n, T = 1 << 24, 252
+    book = sim.generate_paths_and_options(n, n_steps=T, model="heston", reprice=False)
+    mult = np.linspace(0.9, 1.1, 8).astype(np.float32)
+    Tt = torch.clamp(1 - torch.arange(T + 1, device="cuda") / 252, min=0)[:, None]
+    n_slices = 0
+    for first, last, (calls, puts) in sim.reprice_book_slices(book, mult, paths_per_slice=1 << 21, sigma="book"):
+        n_slices += 1
+        assert bool((calls[:-1] >= calls[1:] - 1e-4).all()) and bool((puts[0] >= 0).all()) and bool(torch.isfinite(puts[7]).all())
+        rhs = book.S[:, first:last] - float(mult[3]) * 100.0 * torch.exp(-0.04 * Tt)
+        assert float(((calls[3] - puts[3]) - rhs).abs().max()) < 1e-3
+    assert n_slices == 8
+
+
 def test_reprice_book_argument_errors():
     from cantorrl_b200 import CantorError, sim
     book = sim.generate_paths_and_options(64, n_steps=8, reprice=False)
