@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--e2e-steps", type=int, default=2, help="episode sweeps timed through the host-buffer API")
     ap.add_argument("--rollout-steps", type=int, default=3, help="episode sweeps of the on-the-fly rollout kernel (extra)")
+    ap.add_argument("--rollout-envs", type=int, default=1 << 23, help="envs per GPU of that extra (configs[3]: 64 M envs over 8 GPUs)")
     ap.add_argument("--mlp-rollout-steps", type=int, default=1000, help="steps of the MLP-policy rollout (configs[4] shape; 0 = skip)")
     ap.add_argument("--lstm-rollout-steps", type=int, default=252, help="steps of the recurrent (LSTM + MLP) policy rollout (0 = skip)")
     ap.add_argument("--book-strikes", type=int, default=8, help="strikes of the multi-strike book extra (configs[2] shape; 0 = skip)")
@@ -320,8 +321,9 @@ def main():
     roll = None
     if args.rollout_steps > 0:
         from cantorrl_b200.rollout import HedgingRollout
-        ro = HedgingRollout(simulate=dict(model="gbm", seed=42, s0=S0, v0=XI, n_steps=T), num_envs=n, device=dev,
-                            env_offset=rank * n, total_envs=world * n, one_call_only=True, **ENV_KW)
+        nr = args.rollout_envs
+        ro = HedgingRollout(simulate=dict(model="gbm", seed=42, s0=S0, v0=XI, n_steps=T), num_envs=nr, device=dev,
+                            env_offset=rank * nr, total_envs=world * nr, one_call_only=True, **ENV_KW)
         rstats = ro.new_stats()
         stats_transport = "nccl all_reduce" if world > 1 else "single GPU"
         if world > 1 and not args.no_fused_allreduce:
@@ -478,8 +480,9 @@ def main():
             rs = roll[1]
             line["extra"]["rollout_on_the_fly"] = dict(
                 kernel="rollout_kernel<GBM on the fly, delta_every_step policy, episode statistics> + all-reduce of the "
-                       "statistics buffers once per sweep", stats_all_reduce=roll[2], sweeps=args.rollout_steps, ms_per_sweep=roll_ms / args.rollout_steps,
-                env_steps_per_s=float(n) * world * T * args.rollout_steps / (roll_ms * 1e-3),
+                       "statistics buffers once per sweep (configs[3] shape: 2^23 envs per GPU, 64 M on 8)", stats_all_reduce=roll[2], sweeps=args.rollout_steps, ms_per_sweep=roll_ms / args.rollout_steps,
+                envs_per_gpu=args.rollout_envs,
+                env_steps_per_s=float(args.rollout_envs) * world * T * args.rollout_steps / (roll_ms * 1e-3),
                 stats={k: rs[k] for k in ("n_episodes", "mean_abs_pnl", "std_abs_pnl", "mean_cost", "mean_reward", "cvar95_abs_pnl")})
         if mlp_roll is not None:
             line["extra"]["rollout_mlp_policy"] = dict(
