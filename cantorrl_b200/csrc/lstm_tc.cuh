@@ -92,6 +92,15 @@ __device__ __forceinline__ bool elect_one() {
 // the env warps' own barrier (the issuer warp never joins it)
 __device__ __forceinline__ void env_sync() { asm volatile("bar.sync 1, %0;" :: "n"(kEnvs) : "memory"); }
 
+#ifdef LSTM_TRACE
+// debugging aid (variant builds only): clock64 timestamps of CTA 0's three actors during steps [LSTM_TRACE, LSTM_TRACE + 2)
+__device__ long long g_lstm_trace[3][256][2];
+__device__ int g_lstm_trace_n[3];
+#define LSTM_TR(actor, tag) do { if (blockIdx.x == 0 && trace_on) { int i_ = g_lstm_trace_n[actor]; if (i_ < 256) { g_lstm_trace[actor][i_][0] = (tag); g_lstm_trace[actor][i_][1] = clock64(); g_lstm_trace_n[actor] = i_ + 1; } } } while (0)
+#else
+#define LSTM_TR(actor, tag) do { } while (0)
+#endif
+
 struct Actor {
     unsigned char* smem;        // base of the actor's shared memory (offsets above)
     const unsigned char* img;   // global weight image
@@ -103,6 +112,9 @@ struct Actor {
     uint32_t ph_g, ph_h;        // phase parities of the barriers this env thread waits on (its own group's)
     uint32_t tmem;
     int grp;                    // this thread's group (env threads)
+#ifdef LSTM_TRACE
+    int n_forward;
+#endif
     bool timed_out;
 
     __device__ __forceinline__ uint32_t bar_g(int g) const { return bars + 8 * g; }
@@ -129,6 +141,9 @@ struct Actor {
         bars = mlptc::smem_u32(bar_mem);
         ph_g = ph_h = 0;
         timed_out = false;
+#ifdef LSTM_TRACE
+        n_forward = 0;
+#endif
         const int tid = threadIdx.x;
         grp = tid >> 7;
         if (tid == 0) {
@@ -198,13 +213,30 @@ struct Actor {
     }
 
     // ---- issuer warp ---------------------------------------------------------------------------------------------------
-    // K-steps [k0, k1) of D[128 x n] = A * B^T into TMEM column `dcol` (the first one overwrites).
-    // a_desc / b_desc: descriptors of K-step 0; one K-step = two 128-byte core-matrix columns = 16 in the address field.
-    __device__ __forceinline__ void mma(uint64_t a_desc, uint64_t b_desc, int k0, int k1, uint32_t idesc, int dcol) {
-#pragma unroll 1
-        for (int k = k0; k < k1; ++k)
-            mlptc::umma_bf16(tmem + dcol, a_desc + (uint64_t)(k * (2 * kLbo / 16)), b_desc + (uint64_t)(k * (2 * kLbo / 16)), idesc, k > k0 ? 1u : 0u);
+    // NK consecutive K-steps of D[128 x n] = A * B^T into TMEM column `dcol` (the first one overwrites), as ONE straight-line
+    // block: the descriptors of K-step k are those of K-step 0 plus 16 k in the address field (two 128-byte core-matrix
+    // columns), formed by chained 64-bit adds that ptxas keeps on the uniform datapath (one R2UR per operand, then
+    // UIADD3.64 / UTCHMMA pairs).  The rolled loop it replaces re-derived both descriptors from vector registers for every
+    // MMA -- ~100 clocks each on a warp that shares its scheduler with two epilogue warps, i.e. ~1 000 clocks between "the
+    // epilogue released the gate columns" and "the next pass is in the tensor pipe", on the critical path of every pass.
+#define CANTOR_UMMA_STEP(ACC) "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, " ACC ";\n\tadd.s64 da, da, 16;\n\tadd.s64 db, db, 16;\n\t"
+#define CANTOR_UMMA_HEAD "{\n\t.reg .pred pt, pf;\n\t.reg .b64 da, db;\n\tsetp.eq.u32 pt, 0, 0;\n\tsetp.ne.u32 pf, 0, 0;\n\tmov.b64 da, %1;\n\tmov.b64 db, %2;\n\t"
+    template <int NK>
+    __device__ __forceinline__ void mma(uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int dcol) {
+        static_assert(NK == 1 || NK == 5 || NK == 9, "K-step counts of this actor: x-part, head layers 2 / 3, full A tile");
+        const uint32_t d = tmem + dcol;
+        if (NK == 1)
+            asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+        else if (NK == 5)
+            asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
+                         CANTOR_UMMA_STEP("pt") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+        else
+            asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
+                         CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
+                         "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
     }
+#undef CANTOR_UMMA_STEP
+#undef CANTOR_UMMA_HEAD
 
     // The whole rollout from the tensor core's side: `n_steps` policy steps, episodes of `T` steps in lockstep.
     __device__ __noinline__ void issuer_loop(int n_steps, int T) {
@@ -226,6 +258,9 @@ struct Actor {
         int t = 0;                                                             // step within the episode
 #pragma unroll 1
         for (int s = 0; s < n_steps; ++s) {
+#ifdef LSTM_TRACE
+            const bool trace_on = threadIdx.x == kEnvs && s >= LSTM_TRACE && s < LSTM_TRACE + 2;
+#endif
             const int kend = t == 0 ? 1 : kKA / 16;                            // h_{t-1} = 0 at an episode start: x-part only
 #pragma unroll 1
             for (int p = 0; p < kPasses; ++p) {
@@ -237,15 +272,20 @@ struct Actor {
                     // later passes need the group's epilogue of the previous pass to have read the gate columns
                     if (p == 0) wait_tc(bar_x(g), ph_x[g]);
                     else wait_tc(bar_gfree(g), ph_gfree[g]);
+                    LSTM_TR(2, 100 + 10 * p + g);
                     if (elect_one()) {
-                        mma(d_a[g], d_wg[b], 0, kend, idesc_g, kColGates + kPassN * g);
+                        if (kend == 1) mma<1>(d_a[g], d_wg[b], idesc_g, kColGates + kPassN * g);
+                        else mma<kKA / 16>(d_a[g], d_wg[b], idesc_g, kColGates + kPassN * g);
                         mlptc::umma_commit(bar_g(g));
                     }
                     __syncwarp();
+                    LSTM_TR(2, 105 + 10 * p + g);
                 }
                 // both groups' pass p done (in-order pipe: the second commit covers the first): weight buffer b is free
                 wait(bar_g(0), ph_gi[0]);
+                LSTM_TR(2, 140 + p);
                 wait(bar_g(1), ph_gi[1]);
+                LSTM_TR(2, 150 + p);
                 if (elect_one()) tma_load_1d(wg_s[b], img + kImgGate + ((p + 2) % kPasses) * kWgBytes, kWgBytes, bar_w(b));
                 __syncwarp();
             }
@@ -253,8 +293,9 @@ struct Actor {
 #pragma unroll 1
             for (int g = 0; g < kGroups; ++g) {
                 wait_tc(bar_hready(g), ph_hready[g]);                          // h_t rows are in the A tile; gate columns read
+                LSTM_TR(2, 160 + g);
                 if (elect_one()) {
-                    mma(d_a[g], d_w1, 0, kKA / 16, idesc_h, kColGates + kPassN * g);
+                    mma<kKA / 16>(d_a[g], d_w1, idesc_h, kColGates + kPassN * g);
                     mlptc::umma_commit(bar_h(g));
                 }
                 __syncwarp();
@@ -263,7 +304,7 @@ struct Actor {
             for (int g = 0; g < kGroups; ++g) {
                 wait_tc(bar_a2(g), ph_a2[g]);
                 if (elect_one()) {
-                    mma(d_a2[g], d_w2, 0, kK2 / 16, idesc_h, kColGates + kPassN * g);
+                    mma<kK2 / 16>(d_a2[g], d_w2, idesc_h, kColGates + kPassN * g);
                     mlptc::umma_commit(bar_h(g));
                 }
                 __syncwarp();
@@ -272,7 +313,7 @@ struct Actor {
             for (int g = 0; g < kGroups; ++g) {
                 wait_tc(bar_a2(g), ph_a2[g]);
                 if (elect_one()) {
-                    mma(d_a2[g], d_w3, 0, kK2 / 16, idesc_o, kColGates + kPassN * g + kColHeadOut);
+                    mma<kK2 / 16>(d_a2[g], d_w3, idesc_o, kColGates + kPassN * g + kColHeadOut);
                     mlptc::umma_commit(bar_h(g));
                 }
                 __syncwarp();
@@ -353,6 +394,11 @@ struct Actor {
     // 4x-unrolled form (19 k SASS instructions, 300 KB) spent 40 % of its stall samples in `no_instruction`.
     __device__ __noinline__ float2 forward(const float* o) {
         const int m = threadIdx.x & (kRows - 1);
+#ifdef LSTM_TRACE
+        const bool trace_on = m == 0 && n_forward >= LSTM_TRACE && n_forward < LSTM_TRACE + 2;
+        ++n_forward;
+#endif
+        LSTM_TR(grp, 1);
         float x[16];
 #pragma unroll
         for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - norm[i]) * norm[16 + i], -10.f), 10.f);
@@ -363,11 +409,14 @@ struct Actor {
         *reinterpret_cast<uint4*>(row) = make_uint4(mlptc::pack_bf16(x[0], x[1]), mlptc::pack_bf16(x[2], x[3]), mlptc::pack_bf16(x[4], x[5]), mlptc::pack_bf16(x[6], x[7]));
         *reinterpret_cast<uint4*>(row + kLbo) = make_uint4(mlptc::pack_bf16(x[8], x[9]), mlptc::pack_bf16(x[10], x[11]), mlptc::pack_bf16(x[12], x[13]), mlptc::pack_bf16(x[14], x[15]));
         publish(bar_x(grp));
+        LSTM_TR(grp, 2);
         uint32_t hp[kPasses][16];                                              // h_t as bf16 pairs, held until every pass has read h_{t-1}
 #pragma unroll
         for (int p = 0; p < kPasses; ++p) {
             wait_tc(bar_g(grp), ph_g);                                         // pass p is in the group's gate columns
+            LSTM_TR(grp, 10 + p);
             gate_epilogue(p, hp[p]);
+            LSTM_TR(grp, 20 + p);
             if (p + 1 < kPasses) {                                             // pass p + 1 reuses them
                 mlptc::fence_before_sync();
                 mbar_arrive(bar_gfree(grp));
@@ -381,13 +430,19 @@ struct Actor {
                 *reinterpret_cast<uint4*>(row + (2 + 4 * p + q) * kLbo) = make_uint4(hp[p][4 * q], hp[p][4 * q + 1], hp[p][4 * q + 2], hp[p][4 * q + 3]);
         }
         publish(bar_hready(grp));
+        LSTM_TR(grp, 30);
         wait_tc(bar_h(grp), ph_h);
+        LSTM_TR(grp, 31);
         head_epilogue();
         publish(bar_a2(grp));
+        LSTM_TR(grp, 32);
         wait_tc(bar_h(grp), ph_h);
+        LSTM_TR(grp, 33);
         head_epilogue();
         publish(bar_a2(grp));
+        LSTM_TR(grp, 34);
         wait_tc(bar_h(grp), ph_h);
+        LSTM_TR(grp, 35);
         uint32_t r0, r1;
         mlptc::tmem_ld2(lane_base() + kColGates + kPassN * grp + kColHeadOut, r0, r1);
         mlptc::tmem_ld_wait();

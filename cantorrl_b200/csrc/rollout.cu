@@ -407,3 +407,13 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
 #undef LAUNCH
     return check_launch("rollout_kernel");
 }
+
+#ifdef LSTM_TRACE
+// debugging aid of variant builds: copies the recurrent actor's timestamp trace to the host (3 actors x 256 x {tag, clock})
+extern "C" int cantor_debug_lstm_trace(long long* out, int* counts) {
+    CANTOR_CUDA(cudaDeviceSynchronize());
+    CANTOR_CUDA(cudaMemcpyFromSymbol(out, cantor::lstmtc::g_lstm_trace, sizeof(long long) * 3 * 256 * 2));
+    CANTOR_CUDA(cudaMemcpyFromSymbol(counts, cantor::lstmtc::g_lstm_trace_n, sizeof(int) * 3));
+    return CANTOR_OK;
+}
+#endif
