@@ -96,7 +96,7 @@ __device__ __forceinline__ void env_sync() { asm volatile("bar.sync 1, %0;" :: "
 // debugging aid (variant builds only): clock64 timestamps of CTA 0's three actors during steps [LSTM_TRACE, LSTM_TRACE + 2)
 __device__ long long g_lstm_trace[3][256][2];
 __device__ int g_lstm_trace_n[3];
-#define LSTM_TR(actor, tag) do { if (blockIdx.x == 0 && trace_on) { int i_ = g_lstm_trace_n[actor]; if (i_ < 256) { g_lstm_trace[actor][i_][0] = (tag); g_lstm_trace[actor][i_][1] = clock64(); g_lstm_trace_n[actor] = i_ + 1; } } } while (0)
+#define LSTM_TR(actor, tag) do { if (blockIdx.x == 0 && trace_on && tr_n < 256) { g_lstm_trace[actor][tr_n][0] = (tag); g_lstm_trace[actor][tr_n][1] = clock64(); ++tr_n; g_lstm_trace_n[actor] = tr_n; } } while (0)
 #else
 #define LSTM_TR(actor, tag) do { } while (0)
 #endif
@@ -113,7 +113,7 @@ struct Actor {
     uint32_t tmem;
     int grp;                    // this thread's group (env threads)
 #ifdef LSTM_TRACE
-    int n_forward;
+    int n_forward, tr_n;        // fire-and-forget stores only: the trace must not stall the actor it watches
 #endif
     bool timed_out;
 
@@ -143,6 +143,7 @@ struct Actor {
         timed_out = false;
 #ifdef LSTM_TRACE
         n_forward = 0;
+        tr_n = 0;
 #endif
         const int tid = threadIdx.x;
         grp = tid >> 7;
