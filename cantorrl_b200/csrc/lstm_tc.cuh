@@ -240,6 +240,9 @@ struct Actor {
 #undef CANTOR_UMMA_HEAD
 
     // The whole rollout from the tensor core's side: `n_steps` policy steps, episodes of `T` steps in lockstep.
+    // The pass / group loops are unrolled so that every phase bit and descriptor has a static index and lives in a register:
+    // this warp shares its scheduler with two epilogue warps, and what it executes between two MMA batches is latency the
+    // second group of a pass waits for.
     __device__ __noinline__ void issuer_loop(int n_steps, int T) {
         uint32_t ph_gi[kGroups] = {0, 0}, ph_w[2] = {0, 0}, ph_x[kGroups] = {0, 0}, ph_gfree[kGroups] = {0, 0};
         uint32_t ph_hready[kGroups] = {0, 0}, ph_a2[kGroups] = {0, 0};
@@ -263,11 +266,11 @@ struct Actor {
             const bool trace_on = threadIdx.x == kEnvs && s >= LSTM_TRACE && s < LSTM_TRACE + 2;
 #endif
             const int kend = t == 0 ? 1 : kKA / 16;                            // h_{t-1} = 0 at an episode start: x-part only
-#pragma unroll 1
+#pragma unroll
             for (int p = 0; p < kPasses; ++p) {
                 const int b = p & 1;
                 wait(bar_w(b), ph_w[b]);                                       // tile p is in weight buffer b
-#pragma unroll 1
+#pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
                     // pass 0 needs the group's x rows (which also says: its head accumulators of the last step are read);
                     // later passes need the group's epilogue of the previous pass to have read the gate columns
@@ -291,7 +294,7 @@ struct Actor {
                 __syncwarp();
             }
             // head: three small layers per group, interleaved
-#pragma unroll 1
+#pragma unroll
             for (int g = 0; g < kGroups; ++g) {
                 wait_tc(bar_hready(g), ph_hready[g]);                          // h_t rows are in the A tile; gate columns read
                 LSTM_TR(2, 160 + g);
@@ -301,7 +304,7 @@ struct Actor {
                 }
                 __syncwarp();
             }
-#pragma unroll 1
+#pragma unroll
             for (int g = 0; g < kGroups; ++g) {
                 wait_tc(bar_a2(g), ph_a2[g]);
                 if (elect_one()) {
@@ -310,7 +313,7 @@ struct Actor {
                 }
                 __syncwarp();
             }
-#pragma unroll 1
+#pragma unroll
             for (int g = 0; g < kGroups; ++g) {
                 wait_tc(bar_a2(g), ph_a2[g]);
                 if (elect_one()) {
