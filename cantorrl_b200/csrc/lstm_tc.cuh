@@ -197,16 +197,18 @@ struct Actor {
         tmem_st_wait();
     }
 
-    __device__ __forceinline__ void wait(uint32_t bar, uint32_t& phase) {
+    // `flag`: the caller's timed-out flag (a register copy on the hot paths; the member lives in local memory)
+    static __device__ __forceinline__ void wait_on(uint32_t bar, uint32_t& phase, bool& flag) {
         uint32_t done = 0;
         unsigned spins = 0;
-        while (!done && !timed_out) {
+        while (!done && !flag) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(done) : "r"(bar), "r"(phase) : "memory");
-            if (!done && ++spins > mlptc::kSpinLimit) timed_out = true;       // never hang the GPU: bail out, the caller reports it
+            if (!done && ++spins > mlptc::kSpinLimit) flag = true;            // never hang the GPU: bail out, the caller reports it
         }
         phase ^= 1;
     }
+    __device__ __forceinline__ void wait(uint32_t bar, uint32_t& phase) { wait_on(bar, phase, timed_out); }
     // wait, then order the tcgen05 operations that follow behind what the barrier stands for
     __device__ __forceinline__ void wait_tc(uint32_t bar, uint32_t& phase) {
         wait(bar, phase);
@@ -330,9 +332,7 @@ struct Actor {
 
     // ---- env warps ----------------------------------------------------------------------------------------------------
     // gates of hidden units 32 p .. 32 p + 31 are in the group's gate columns as {i | f | g | o} x 32: update c, return h as bf16 pairs
-    __device__ __forceinline__ void gate_epilogue(int p, uint32_t (&hp)[16]) {
-        const uint32_t gates = lane_base() + kColGates + kPassN * grp;
-        const uint32_t cell = lane_base() + kColCell + kH * grp + kUnitsPerPass * p;
+    __device__ __forceinline__ void gate_epilogue(uint32_t gates, uint32_t cell, uint32_t (&hp)[16]) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             uint32_t gi[16], gf[16], gg[16], go[16], cc[16];
@@ -363,10 +363,7 @@ struct Actor {
 
     // 64 head accumulators -> ReLU -> bf16 -> this thread's A2 row (constant tail included: the rollout's observation
     // staging tile aliases the A2 tiles between steps)
-    __device__ __forceinline__ void head_epilogue() {
-        const int m = threadIdx.x & (kRows - 1);
-        const uint32_t acc = lane_base() + kColGates + kPassN * grp;
-        unsigned char* row = a2_tile(grp) + (m >> 3) * kSbo2 + (m & 7) * 16;
+    __device__ __forceinline__ void head_epilogue(uint32_t acc, unsigned char* row) {
         uint32_t r[4][16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) mlptc::tmem_ld16(acc + c * 16, r[c]);
@@ -398,6 +395,15 @@ struct Actor {
     // 4x-unrolled form (19 k SASS instructions, 300 KB) spent 40 % of its stall samples in `no_instruction`.
     __device__ __noinline__ float2 forward(const float* o) {
         const int m = threadIdx.x & (kRows - 1);
+        // this object lives in local memory (its address is taken by this call) and every asm below clobbers memory: read
+        // what the step needs into registers once instead of once per use
+        const int g = grp;
+        const uint32_t b_g = bar_g(g), b_h = bar_h(g), b_x = bar_x(g), b_gfree = bar_gfree(g), b_hready = bar_hready(g), b_a2 = bar_a2(g);
+        const uint32_t gates = lane_base() + kColGates + kPassN * g, cell0 = lane_base() + kColCell + kH * g;
+        unsigned char* const row2 = a2_tile(g) + (m >> 3) * kSbo2 + (m & 7) * 16;
+        uint32_t phg = ph_g, phh = ph_h;
+        bool to = timed_out;
+        const float* const nrm = norm;
 #ifdef LSTM_TRACE
         const bool trace_on = m == 0 && n_forward >= LSTM_TRACE && n_forward < LSTM_TRACE + 2;
         ++n_forward;
@@ -405,25 +411,26 @@ struct Actor {
         LSTM_TR(grp, 1);
         float x[16];
 #pragma unroll
-        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - norm[i]) * norm[16 + i], -10.f), 10.f);
+        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - nrm[i]) * nrm[16 + i], -10.f), 10.f);
         x[13] = 1.0f;
         x[14] = 0.f;
         x[15] = 0.f;
-        unsigned char* row = a_tile(grp) + (m >> 3) * kSboA + (m & 7) * 16;
+        unsigned char* const row = a_tile(g) + (m >> 3) * kSboA + (m & 7) * 16;
         *reinterpret_cast<uint4*>(row) = make_uint4(mlptc::pack_bf16(x[0], x[1]), mlptc::pack_bf16(x[2], x[3]), mlptc::pack_bf16(x[4], x[5]), mlptc::pack_bf16(x[6], x[7]));
         *reinterpret_cast<uint4*>(row + kLbo) = make_uint4(mlptc::pack_bf16(x[8], x[9]), mlptc::pack_bf16(x[10], x[11]), mlptc::pack_bf16(x[12], x[13]), mlptc::pack_bf16(x[14], x[15]));
-        publish(bar_x(grp));
+        publish(b_x);
         LSTM_TR(grp, 2);
         uint32_t hp[kPasses][16];                                              // h_t as bf16 pairs, held until every pass has read h_{t-1}
 #pragma unroll
         for (int p = 0; p < kPasses; ++p) {
-            wait_tc(bar_g(grp), ph_g);                                         // pass p is in the group's gate columns
+            wait_on(b_g, phg, to);                                             // pass p is in the group's gate columns
+            mlptc::fence_after_sync();
             LSTM_TR(grp, 10 + p);
-            gate_epilogue(p, hp[p]);
+            gate_epilogue(gates, cell0 + kUnitsPerPass * p, hp[p]);
             LSTM_TR(grp, 20 + p);
             if (p + 1 < kPasses) {                                             // pass p + 1 reuses them
                 mlptc::fence_before_sync();
-                mbar_arrive(bar_gfree(grp));
+                mbar_arrive(b_gfree);
             }
         }
         // the last pass's MMAs are done (its accumulator was just read): h_t may overwrite h_{t-1} in the A tile
@@ -433,23 +440,29 @@ struct Actor {
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<uint4*>(row + (2 + 4 * p + q) * kLbo) = make_uint4(hp[p][4 * q], hp[p][4 * q + 1], hp[p][4 * q + 2], hp[p][4 * q + 3]);
         }
-        publish(bar_hready(grp));
+        publish(b_hready);
         LSTM_TR(grp, 30);
-        wait_tc(bar_h(grp), ph_h);
+        wait_on(b_h, phh, to);
+        mlptc::fence_after_sync();
         LSTM_TR(grp, 31);
-        head_epilogue();
-        publish(bar_a2(grp));
+        head_epilogue(gates, row2);
+        publish(b_a2);
         LSTM_TR(grp, 32);
-        wait_tc(bar_h(grp), ph_h);
+        wait_on(b_h, phh, to);
+        mlptc::fence_after_sync();
         LSTM_TR(grp, 33);
-        head_epilogue();
-        publish(bar_a2(grp));
+        head_epilogue(gates, row2);
+        publish(b_a2);
         LSTM_TR(grp, 34);
-        wait_tc(bar_h(grp), ph_h);
+        wait_on(b_h, phh, to);
+        mlptc::fence_after_sync();
         LSTM_TR(grp, 35);
         uint32_t r0, r1;
-        mlptc::tmem_ld2(lane_base() + kColGates + kPassN * grp + kColHeadOut, r0, r1);
+        mlptc::tmem_ld2(gates + kColHeadOut, r0, r1);
         mlptc::tmem_ld_wait();
+        ph_g = phg;
+        ph_h = phh;
+        timed_out = to;
         return make_float2(__uint_as_float(r0), __uint_as_float(r1));         // action means; the caller squashes them
     }
 };
