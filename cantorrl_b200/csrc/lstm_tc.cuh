@@ -225,9 +225,8 @@ struct Actor {
 #define CANTOR_UMMA_STEP(ACC) "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, " ACC ";\n\tadd.s64 da, da, 16;\n\tadd.s64 db, db, 16;\n\t"
 #define CANTOR_UMMA_HEAD "{\n\t.reg .pred pt, pf;\n\t.reg .b64 da, db;\n\tsetp.eq.u32 pt, 0, 0;\n\tsetp.ne.u32 pf, 0, 0;\n\tmov.b64 da, %1;\n\tmov.b64 db, %2;\n\t"
     template <int NK>
-    __device__ __forceinline__ void mma(uint64_t a_desc, uint64_t b_desc, uint32_t idesc, int dcol) {
+    static __device__ __forceinline__ void mma(uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t d) {
         static_assert(NK == 1 || NK == 5 || NK == 9, "K-step counts of this actor: x-part, head layers 2 / 3, full A tile");
-        const uint32_t d = tmem + dcol;
         if (NK == 1)
             asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
         else if (NK == 5)
@@ -246,6 +245,17 @@ struct Actor {
     // this warp shares its scheduler with two epilogue warps, and what it executes between two MMA batches is latency the
     // second group of a pass waits for.
     __device__ __noinline__ void issuer_loop(int n_steps, int T) {
+        // register copies of what lives in the (local-memory) actor object
+        const uint32_t B = bars, tm = tmem;
+        const unsigned char* const image = img;
+        bool to = timed_out;
+        auto bg = [B](int g) { return B + 8 * g; };
+        auto bh = [B](int g) { return B + 8 * (2 + g); };
+        auto bw = [B](int b) { return B + 8 * (4 + b); };
+        auto bx = [B](int g) { return B + 8 * (6 + g); };
+        auto bgfree = [B](int g) { return B + 8 * (8 + g); };
+        auto bhready = [B](int g) { return B + 8 * (10 + g); };
+        auto ba2 = [B](int g) { return B + 8 * (12 + g); };
         uint32_t ph_gi[kGroups] = {0, 0}, ph_w[2] = {0, 0}, ph_x[kGroups] = {0, 0}, ph_gfree[kGroups] = {0, 0};
         uint32_t ph_hready[kGroups] = {0, 0}, ph_a2[kGroups] = {0, 0};
         const uint32_t wg_s[2] = {mlptc::smem_u32(smem), mlptc::smem_u32(smem + kWgBytes)};
@@ -257,8 +267,8 @@ struct Actor {
         const uint64_t d_w3 = mlptc::smem_desc(mlptc::smem_u32(smem + kOffW1 + kW1Bytes + kW2Bytes), kLbo, kSbo2);
         const uint32_t idesc_g = mlptc::instr_desc(kRows, kPassN), idesc_h = mlptc::instr_desc(kRows, 64), idesc_o = mlptc::instr_desc(kRows, mlptc::kN3);
         if (elect_one()) {                                                     // passes 0 and 1 of the first step
-            tma_load_1d(wg_s[0], img + kImgGate, kWgBytes, bar_w(0));
-            tma_load_1d(wg_s[1], img + kImgGate + kWgBytes, kWgBytes, bar_w(1));
+            tma_load_1d(wg_s[0], image + kImgGate, kWgBytes, bw(0));
+            tma_load_1d(wg_s[1], image + kImgGate + kWgBytes, kWgBytes, bw(1));
         }
         __syncwarp();
         int t = 0;                                                             // step within the episode
@@ -271,63 +281,68 @@ struct Actor {
 #pragma unroll
             for (int p = 0; p < kPasses; ++p) {
                 const int b = p & 1;
-                wait(bar_w(b), ph_w[b]);                                       // tile p is in weight buffer b
+                wait_on(bw(b), ph_w[b], to);                                       // tile p is in weight buffer b
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
                     // pass 0 needs the group's x rows (which also says: its head accumulators of the last step are read);
                     // later passes need the group's epilogue of the previous pass to have read the gate columns
-                    if (p == 0) wait_tc(bar_x(g), ph_x[g]);
-                    else wait_tc(bar_gfree(g), ph_gfree[g]);
+                    if (p == 0) wait_on(bx(g), ph_x[g], to);
+                    else wait_on(bgfree(g), ph_gfree[g], to);
+                    mlptc::fence_after_sync();
                     LSTM_TR(2, 100 + 10 * p + g);
                     if (elect_one()) {
-                        if (kend == 1) mma<1>(d_a[g], d_wg[b], idesc_g, kColGates + kPassN * g);
-                        else mma<kKA / 16>(d_a[g], d_wg[b], idesc_g, kColGates + kPassN * g);
-                        mlptc::umma_commit(bar_g(g));
+                        if (kend == 1) mma<1>(d_a[g], d_wg[b], idesc_g, tm + kColGates + kPassN * g);
+                        else mma<kKA / 16>(d_a[g], d_wg[b], idesc_g, tm + kColGates + kPassN * g);
+                        mlptc::umma_commit(bg(g));
                     }
                     __syncwarp();
                     LSTM_TR(2, 105 + 10 * p + g);
                 }
                 // both groups' pass p done (in-order pipe: the second commit covers the first): weight buffer b is free
-                wait(bar_g(0), ph_gi[0]);
+                wait_on(bg(0), ph_gi[0], to);
                 LSTM_TR(2, 140 + p);
-                wait(bar_g(1), ph_gi[1]);
+                wait_on(bg(1), ph_gi[1], to);
                 LSTM_TR(2, 150 + p);
-                if (elect_one()) tma_load_1d(wg_s[b], img + kImgGate + ((p + 2) % kPasses) * kWgBytes, kWgBytes, bar_w(b));
+                if (elect_one()) tma_load_1d(wg_s[b], image + kImgGate + ((p + 2) % kPasses) * kWgBytes, kWgBytes, bw(b));
                 __syncwarp();
             }
             // head: three small layers per group, interleaved
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
-                wait_tc(bar_hready(g), ph_hready[g]);                          // h_t rows are in the A tile; gate columns read
+                wait_on(bhready(g), ph_hready[g], to);
+                    mlptc::fence_after_sync();                          // h_t rows are in the A tile; gate columns read
                 LSTM_TR(2, 160 + g);
                 if (elect_one()) {
-                    mma<kKA / 16>(d_a[g], d_w1, idesc_h, kColGates + kPassN * g);
-                    mlptc::umma_commit(bar_h(g));
+                    mma<kKA / 16>(d_a[g], d_w1, idesc_h, tm + kColGates + kPassN * g);
+                    mlptc::umma_commit(bh(g));
                 }
                 __syncwarp();
             }
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
-                wait_tc(bar_a2(g), ph_a2[g]);
+                wait_on(ba2(g), ph_a2[g], to);
+                    mlptc::fence_after_sync();
                 if (elect_one()) {
-                    mma<kK2 / 16>(d_a2[g], d_w2, idesc_h, kColGates + kPassN * g);
-                    mlptc::umma_commit(bar_h(g));
+                    mma<kK2 / 16>(d_a2[g], d_w2, idesc_h, tm + kColGates + kPassN * g);
+                    mlptc::umma_commit(bh(g));
                 }
                 __syncwarp();
             }
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
-                wait_tc(bar_a2(g), ph_a2[g]);
+                wait_on(ba2(g), ph_a2[g], to);
+                    mlptc::fence_after_sync();
                 if (elect_one()) {
-                    mma<kK2 / 16>(d_a2[g], d_w3, idesc_o, kColGates + kPassN * g + kColHeadOut);
-                    mlptc::umma_commit(bar_h(g));
+                    mma<kK2 / 16>(d_a2[g], d_w3, idesc_o, tm + kColGates + kPassN * g + kColHeadOut);
+                    mlptc::umma_commit(bh(g));
                 }
                 __syncwarp();
             }
             t = t + 1 == T ? 0 : t + 1;
         }
-        wait(bar_w(0), ph_w[0]);                                               // the two tiles requested in the last passes
-        wait(bar_w(1), ph_w[1]);
+        wait_on(bw(0), ph_w[0], to);                                               // the two tiles requested in the last passes
+        wait_on(bw(1), ph_w[1], to);
+        timed_out = to;
     }
 
     // ---- env warps ----------------------------------------------------------------------------------------------------
