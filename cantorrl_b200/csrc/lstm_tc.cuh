@@ -216,30 +216,6 @@ struct Actor {
     }
 
     // ---- issuer warp ---------------------------------------------------------------------------------------------------
-    // NK consecutive K-steps of D[128 x n] = A * B^T into TMEM column `dcol` (the first one overwrites), as ONE straight-line
-    // block: the descriptors of K-step k are those of K-step 0 plus 16 k in the address field (two 128-byte core-matrix
-    // columns), formed by chained 64-bit adds that ptxas keeps on the uniform datapath (one R2UR per operand, then
-    // UIADD3.64 / UTCHMMA pairs).  The rolled loop it replaces re-derived both descriptors from vector registers for every
-    // MMA -- ~100 clocks each on a warp that shares its scheduler with two epilogue warps, i.e. ~1 000 clocks between "the
-    // epilogue released the gate columns" and "the next pass is in the tensor pipe", on the critical path of every pass.
-#define CANTOR_UMMA_STEP(ACC) "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, " ACC ";\n\tadd.s64 da, da, 16;\n\tadd.s64 db, db, 16;\n\t"
-#define CANTOR_UMMA_HEAD "{\n\t.reg .pred pt, pf;\n\t.reg .b64 da, db;\n\tsetp.eq.u32 pt, 0, 0;\n\tsetp.ne.u32 pf, 0, 0;\n\tmov.b64 da, %1;\n\tmov.b64 db, %2;\n\t"
-    template <int NK>
-    static __device__ __forceinline__ void mma(uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t d) {
-        static_assert(NK == 1 || NK == 5 || NK == 9, "K-step counts of this actor: x-part, head layers 2 / 3, full A tile");
-        if (NK == 1)
-            asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
-        else if (NK == 5)
-            asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
-                         CANTOR_UMMA_STEP("pt") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
-        else
-            asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
-                         CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
-                         "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
-    }
-#undef CANTOR_UMMA_STEP
-#undef CANTOR_UMMA_HEAD
-
     // The whole rollout from the tensor core's side: `n_steps` policy steps, episodes of `T` steps in lockstep.
     // The pass / group loops are unrolled so that every phase bit and descriptor has a static index and lives in a register:
     // this warp shares its scheduler with two epilogue warps, and what it executes between two MMA batches is latency the
@@ -291,8 +267,8 @@ struct Actor {
                     mlptc::fence_after_sync();
                     LSTM_TR(2, 100 + 10 * p + g);
                     if (elect_one()) {
-                        if (kend == 1) mma<1>(d_a[g], d_wg[b], idesc_g, tm + kColGates + kPassN * g);
-                        else mma<kKA / 16>(d_a[g], d_wg[b], idesc_g, tm + kColGates + kPassN * g);
+                        if (kend == 1) mlptc::umma_batch<1>(d_a[g], d_wg[b], idesc_g, tm + kColGates + kPassN * g);
+                        else mlptc::umma_batch<kKA / 16>(d_a[g], d_wg[b], idesc_g, tm + kColGates + kPassN * g);
                         mlptc::umma_commit(bg(g));
                     }
                     __syncwarp();
@@ -313,7 +289,7 @@ struct Actor {
                     mlptc::fence_after_sync();                          // h_t rows are in the A tile; gate columns read
                 LSTM_TR(2, 160 + g);
                 if (elect_one()) {
-                    mma<kKA / 16>(d_a[g], d_w1, idesc_h, tm + kColGates + kPassN * g);
+                    mlptc::umma_batch<kKA / 16>(d_a[g], d_w1, idesc_h, tm + kColGates + kPassN * g);
                     mlptc::umma_commit(bh(g));
                 }
                 __syncwarp();
@@ -323,7 +299,7 @@ struct Actor {
                 wait_on(ba2(g), ph_a2[g], to);
                     mlptc::fence_after_sync();
                 if (elect_one()) {
-                    mma<kK2 / 16>(d_a2[g], d_w2, idesc_h, tm + kColGates + kPassN * g);
+                    mlptc::umma_batch<kK2 / 16>(d_a2[g], d_w2, idesc_h, tm + kColGates + kPassN * g);
                     mlptc::umma_commit(bh(g));
                 }
                 __syncwarp();
@@ -333,7 +309,7 @@ struct Actor {
                 wait_on(ba2(g), ph_a2[g], to);
                     mlptc::fence_after_sync();
                 if (elect_one()) {
-                    mma<kK2 / 16>(d_a2[g], d_w3, idesc_o, tm + kColGates + kPassN * g + kColHeadOut);
+                    mlptc::umma_batch<kK2 / 16>(d_a2[g], d_w3, idesc_o, tm + kColGates + kPassN * g + kColHeadOut);
                     mlptc::umma_commit(bh(g));
                 }
                 __syncwarp();

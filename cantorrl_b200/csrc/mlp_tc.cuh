@@ -55,6 +55,31 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// NK consecutive K-steps of D[128 x n] = A * B^T into TMEM address `d` (the first one overwrites), as ONE straight-line
+// block: the descriptors of K-step k are those of K-step 0 plus 16 k in the address field (two 128-byte core-matrix
+// columns), formed by chained 64-bit adds that ptxas keeps on the uniform datapath (one R2UR per operand, then
+// UIADD3.64 / UTCHMMA pairs).  The rolled loop it replaces re-derived both descriptors from vector registers for every
+// MMA -- ~100 clocks each on the recurrent actor's issuer warp, which shares its scheduler with two epilogue warps, i.e.
+// ~1 000 clocks between "the epilogue released the gate columns" and "the next pass is in the tensor pipe" on the critical
+// path of every pass (lstm_tc.cuh: 85 -> 80.8 ms).  For the plain MLP actor, with five CTAs per SM to hide it, it is neutral.
+#define CANTOR_UMMA_STEP(ACC) "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, " ACC ";\n\tadd.s64 da, da, 16;\n\tadd.s64 db, db, 16;\n\t"
+#define CANTOR_UMMA_HEAD "{\n\t.reg .pred pt, pf;\n\t.reg .b64 da, db;\n\tsetp.eq.u32 pt, 0, 0;\n\tsetp.ne.u32 pf, 0, 0;\n\tmov.b64 da, %1;\n\tmov.b64 db, %2;\n\t"
+template <int NK>
+__device__ __forceinline__ void umma_batch(uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t d) {
+    static_assert(NK == 1 || NK == 5 || NK == 9, "K-step counts in use: K = 16 (x-part, MLP layer 1), 80 (layers 2 / 3), 144 (LSTM A tile)");
+    if (NK == 1)
+        asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+    else if (NK == 5)
+        asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
+                     CANTOR_UMMA_STEP("pt") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+    else
+        asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
+                     CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
+                     "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+}
+#undef CANTOR_UMMA_STEP
+#undef CANTOR_UMMA_HEAD
+
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
 }
@@ -177,15 +202,14 @@ struct Actor {
     }
 
     // publish this thread's freshly written A rows, then let one thread issue `ksteps` MMAs of K = 16 each
-    __device__ __forceinline__ void run_layer(uint32_t a_addr, uint32_t a_sbo, uint32_t b_addr, uint32_t b_sbo, int ksteps, uint32_t idesc) {
+    template <int KSTEPS>
+    __device__ __forceinline__ void run_layer(uint32_t a_addr, uint32_t a_sbo, uint32_t b_addr, uint32_t b_sbo, uint32_t idesc) {
         fence_before_sync();          // earlier tcgen05.ld of the accumulator this layer overwrites
         fence_proxy_async_smem();     // st.shared of the A tile -> async proxy
         __syncthreads();
         if (threadIdx.x == 0) {
             fence_after_sync();
-            for (int k = 0; k < ksteps; ++k)
-                umma_bf16(tmem, smem_desc(a_addr + k * 2 * kLbo, kLbo, a_sbo), smem_desc(b_addr + k * 2 * kLbo, kLbo, b_sbo),
-                          idesc, k > 0 ? 1u : 0u);
+            umma_batch<KSTEPS>(smem_desc(a_addr, kLbo, a_sbo), smem_desc(b_addr, kLbo, b_sbo), idesc, tmem);
             umma_commit(mbar);
         }
         wait_mma();
@@ -227,11 +251,11 @@ struct Actor {
         unsigned char* row = a1 + (m >> 3) * kSbo1 + (m & 7) * 16;
         *reinterpret_cast<uint4*>(row) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
         *reinterpret_cast<uint4*>(row + kLbo) = make_uint4(pack_bf16(x[8], x[9]), pack_bf16(x[10], x[11]), pack_bf16(x[12], x[13]), pack_bf16(x[14], x[15]));
-        run_layer(smem_u32(a1), kSbo1, smem_u32(w1), kSbo1, kK1 / 16, instr_desc(kRows, kHidden));
+        run_layer<kK1 / 16>(smem_u32(a1), kSbo1, smem_u32(w1), kSbo1, instr_desc(kRows, kHidden));
         hidden_epilogue();
-        run_layer(smem_u32(a2), kSbo2, smem_u32(w2), kSbo2, kK2 / 16, instr_desc(kRows, kHidden));
+        run_layer<kK2 / 16>(smem_u32(a2), kSbo2, smem_u32(w2), kSbo2, instr_desc(kRows, kHidden));
         hidden_epilogue();
-        run_layer(smem_u32(a2), kSbo2, smem_u32(w3), kSbo2, kK2 / 16, instr_desc(kRows, kN3));
+        run_layer<kK2 / 16>(smem_u32(a2), kSbo2, smem_u32(w3), kSbo2, instr_desc(kRows, kN3));
         uint32_t r0, r1;
         tmem_ld2(tmem + ((uint32_t)(m & ~31) << 16), r0, r1);
         tmem_ld_wait();
