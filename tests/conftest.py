@@ -49,3 +49,16 @@ def load_env_case(name):
 @pytest.fixture(params=ENV_CASES)
 def env_case(request):
     return (request.param,) + load_env_case(request.param)
+
+
+@pytest.fixture(autouse=True)
+def _release_device_memory_between_tests(request):
+    """The full-size tests (34 - 100 GB books) must not find the caching allocator still holding the previous test's blocks."""
+    yield
+    if "gpu" in request.keywords:
+        import gc
+
+        import torch
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
