@@ -41,6 +41,7 @@ struct cantor_vecenv {
     int32_t* next_path = nullptr;
     cantor_reset_rule rule;
     int64_t global_step = 0;
+    bool direct_small_outputs = true;     // CANTOR_HOST_NO_DIRECT=1 in the environment turns the mapped-memory path off (A/B runs)
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
 };
 
@@ -85,6 +86,8 @@ cantor_env_state state_of(const cantor_vecenv* e, int64_t first) {
 
 }  // namespace
 
+static bool env_flag(const char* name) { const char* v = getenv(name); return v != nullptr && v[0] != '\0' && v[0] != '0'; }
+
 extern "C" int cantor_vecenv_create(cantor_vecenv** out, const cantor_env_params* params, int32_t precision,
                                     int64_t n_envs, int32_t device, int32_t n_chunks) {
     CANTOR_REQUIRE(out != nullptr && params != nullptr, "out/params is NULL");
@@ -99,6 +102,7 @@ extern "C" int cantor_vecenv_create(cantor_vecenv** out, const cantor_env_params
     e->precision = precision;
     e->device = device;
     e->n_envs = n_envs;
+    e->direct_small_outputs = !env_flag("CANTOR_HOST_NO_DIRECT");
     if (n_chunks <= 0) n_chunks = n_envs >= (1 << 16) ? 8 : 1;
     e->n_chunks = (int)(n_chunks > n_envs ? n_envs : n_chunks);
     e->rule = cantor_reset_rule{CANTOR_RESET_SAME_PATH, 0, nullptr, 0x5EED5EEDull, 0, 0};
@@ -210,6 +214,21 @@ extern "C" int cantor_vecenv_step_host(cantor_vecenv* e, const float* actions_ho
         CANTOR_CUDA(cudaStreamSynchronize(e->streams[0]));
         rule.mode = CANTOR_RESET_FROM_ARRAY;
     }
+    // Page-locked, device-mapped result buffers (cantor_host_register / cudaHostAlloc): the step kernel writes the 5 small
+    // bytes per env -- reward and done -- straight into them over PCIe, which saves two of the three D2H copies of every chunk
+    // (16 copy-engine launches per step at 8 chunks: 1.264 -> 1.229 ms per 2^20-env step); the observations (52 B per env) still go
+    // by DMA -- letting the kernel's TMA stores write them into host memory too measured slower (1.259 ms).
+    auto mapped = [](const void* host) -> void* {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (at.type == cudaMemoryTypeHost && at.devicePointer != nullptr) ? at.devicePointer : nullptr;
+    };
+    char* reward_direct = (char*)mapped(reward_host);
+    uint8_t* done_direct = (uint8_t*)mapped(done_host);
+    const bool direct = e->direct_small_outputs && reward_direct != nullptr && done_direct != nullptr;
     const int C = e->n_chunks;
     // chunk boundaries on multiples of 128 envs so every chunk keeps the aligned TMA obs store
     const int64_t per = ((e->n_envs + C - 1) / C + 127) / 128 * 128;
@@ -224,13 +243,15 @@ extern "C" int cantor_vecenv_step_host(cantor_vecenv* e, const float* actions_ho
         r.env_offset = rule.env_offset + first;
         r.next_path = e->next_path + first;
         int rc = cantor_env_step(&e->params, &b, &st, n, e->precision, e->actions + first * 2,
-                                 e->obs + first * CANTOR_OBS_DIM, (char*)e->reward + first * rb, e->done + first, nullptr, 1,
-                                 &r, nullptr, s);
+                                 e->obs + first * CANTOR_OBS_DIM, direct ? (void*)(reward_direct + first * rb) : (void*)((char*)e->reward + first * rb),
+                                 direct ? done_direct + first : e->done + first, nullptr, 1, &r, nullptr, s);
         if (rc) return rc;
         CANTOR_CUDA(cudaMemcpyAsync(obs_host + first * CANTOR_OBS_DIM, e->obs + first * CANTOR_OBS_DIM,
                                     n * CANTOR_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CANTOR_CUDA(cudaMemcpyAsync((char*)reward_host + first * rb, (char*)e->reward + first * rb, n * rb, cudaMemcpyDeviceToHost, s));
-        CANTOR_CUDA(cudaMemcpyAsync(done_host + first, e->done + first, n, cudaMemcpyDeviceToHost, s));
+        if (!direct) {
+            CANTOR_CUDA(cudaMemcpyAsync((char*)reward_host + first * rb, (char*)e->reward + first * rb, n * rb, cudaMemcpyDeviceToHost, s));
+            CANTOR_CUDA(cudaMemcpyAsync(done_host + first, e->done + first, n, cudaMemcpyDeviceToHost, s));
+        }
     }
     for (auto& s : e->streams) CANTOR_CUDA(cudaStreamSynchronize(s));
     e->global_step += 1;
@@ -243,7 +264,7 @@ extern "C" int cantor_vecenv_num_paths(const cantor_vecenv* e) { return e ? e->n
 // Page-lock / unlock a caller-owned host buffer so the per-step copies run at full PCIe speed and asynchronously.
 extern "C" int cantor_host_register(void* ptr, size_t bytes) {
     CANTOR_REQUIRE(ptr != nullptr && bytes > 0, "NULL / empty buffer");
-    CANTOR_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    CANTOR_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
     return CANTOR_OK;
 }
 extern "C" int cantor_host_unregister(void* ptr) {
