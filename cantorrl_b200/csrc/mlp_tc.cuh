@@ -215,27 +215,36 @@ struct Actor {
         wait_mma();
     }
 
-    // accumulator row of this thread (64 columns) -> ReLU -> bf16 -> this thread's A2 row
+    // accumulator row of this thread (64 columns) -> ReLU -> bf16 -> this thread's A2 row; two TMEM loads in flight per wait
+    // (all four at once cost 30 more registers and a resident CTA per SM: 7.99 ms instead of 6.9 for the 2^20 x 252 sweep)
     __device__ __forceinline__ void hidden_epilogue() {
         const int m = threadIdx.x;
         const uint32_t lane_addr = tmem + ((uint32_t)(m & ~31) << 16);
         unsigned char* row = a2 + (m >> 3) * kSbo2 + (m & 7) * 16;
 #pragma unroll
-        for (int c = 0; c < kHidden / 16; ++c) {
-            uint32_t r[16];
-            tmem_ld16(lane_addr + c * 16, r);
+        for (int c2 = 0; c2 < kHidden / 32; ++c2) {
+            uint32_t r[2][16];
+            tmem_ld16(lane_addr + (2 * c2) * 16, r[0]);
+            tmem_ld16(lane_addr + (2 * c2 + 1) * 16, r[1]);
             tmem_ld_wait();
-            uint4 lo, hi;
-            lo.x = relu_pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
-            lo.y = relu_pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-            lo.z = relu_pack_bf16(__uint_as_float(r[4]), __uint_as_float(r[5]));
-            lo.w = relu_pack_bf16(__uint_as_float(r[6]), __uint_as_float(r[7]));
-            hi.x = relu_pack_bf16(__uint_as_float(r[8]), __uint_as_float(r[9]));
-            hi.y = relu_pack_bf16(__uint_as_float(r[10]), __uint_as_float(r[11]));
-            hi.z = relu_pack_bf16(__uint_as_float(r[12]), __uint_as_float(r[13]));
-            hi.w = relu_pack_bf16(__uint_as_float(r[14]), __uint_as_float(r[15]));
-            *reinterpret_cast<uint4*>(row + (2 * c) * kLbo) = lo;
-            *reinterpret_cast<uint4*>(row + (2 * c + 1) * kLbo) = hi;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = 2 * c2 + h;
+                // ties the registers of the asynchronous loads to this point: nothing below may be scheduled above the wait
+                asm volatile("" : "+r"(r[h][0]), "+r"(r[h][1]), "+r"(r[h][2]), "+r"(r[h][3]), "+r"(r[h][4]), "+r"(r[h][5]), "+r"(r[h][6]), "+r"(r[h][7]),
+                                  "+r"(r[h][8]), "+r"(r[h][9]), "+r"(r[h][10]), "+r"(r[h][11]), "+r"(r[h][12]), "+r"(r[h][13]), "+r"(r[h][14]), "+r"(r[h][15]) :: "memory");
+                uint4 lo, hi;
+                lo.x = relu_pack_bf16(__uint_as_float(r[h][0]), __uint_as_float(r[h][1]));
+                lo.y = relu_pack_bf16(__uint_as_float(r[h][2]), __uint_as_float(r[h][3]));
+                lo.z = relu_pack_bf16(__uint_as_float(r[h][4]), __uint_as_float(r[h][5]));
+                lo.w = relu_pack_bf16(__uint_as_float(r[h][6]), __uint_as_float(r[h][7]));
+                hi.x = relu_pack_bf16(__uint_as_float(r[h][8]), __uint_as_float(r[h][9]));
+                hi.y = relu_pack_bf16(__uint_as_float(r[h][10]), __uint_as_float(r[h][11]));
+                hi.z = relu_pack_bf16(__uint_as_float(r[h][12]), __uint_as_float(r[h][13]));
+                hi.w = relu_pack_bf16(__uint_as_float(r[h][14]), __uint_as_float(r[h][15]));
+                *reinterpret_cast<uint4*>(row + (2 * c) * kLbo) = lo;
+                *reinterpret_cast<uint4*>(row + (2 * c + 1) * kLbo) = hi;
+            }
         }
     }
 
