@@ -35,7 +35,10 @@ constexpr int kSbo1 = (kK1 / 8) * 128;           // bytes between 8-row groups, 
 constexpr int kSbo2 = (kK2 / 8) * 128;           // K = 80
 constexpr int kW1Bytes = kHidden * kK1 * 2, kW2Bytes = kHidden * kK2 * 2, kW3Bytes = kN3 * kK2 * 2;
 constexpr int kA1Bytes = kRows * kK1 * 2, kA2Bytes = kRows * kK2 * 2;
-constexpr int kSmemBytes = kW1Bytes + kW2Bytes + kW3Bytes + kA1Bytes + kA2Bytes + 16 + 128;   // + mbarrier (8) + TMEM address (4) + mean / inv_std (2 x 16 floats)
+// The layer-1 operand tile A1 (4 KB) ALIASES the head of the A2 tile: A2 is first written by the layer-1 epilogue, after the
+// layer-1 MMA has read A1, and A1 is next written after the layer-3 MMA has read A2.  36 KB per CTA instead of 40: six CTAs
+// per SM fit instead of five.  (The A2 rows' constant tail, which A1 overwrites for some rows, is rewritten by the epilogue.)
+constexpr int kSmemBytes = kW1Bytes + kW2Bytes + kW3Bytes + kA2Bytes + 16 + 128;   // + mbarrier (8) + TMEM address (4) + mean / inv_std (2 x 16 floats)
 constexpr int kTmemCols = 64;
 constexpr unsigned kSpinLimit = 1u << 24;
 
@@ -123,8 +126,8 @@ struct Actor {
         w1 = smem;
         w2 = w1 + kW1Bytes;
         w3 = w2 + kW2Bytes;
-        a1 = w3 + kW3Bytes;
-        a2 = a1 + kA1Bytes;
+        a2 = w3 + kW3Bytes;
+        a1 = a2;
         uint64_t* bar = reinterpret_cast<uint64_t*>(a2 + kA2Bytes);
         uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
         mbar = smem_u32(bar);
@@ -246,6 +249,8 @@ struct Actor {
                 *reinterpret_cast<uint4*>(row + (2 * c + 1) * kLbo) = hi;
             }
         }
+        *reinterpret_cast<uint4*>(row + 8 * kLbo) = make_uint4(0x00003F80u, 0u, 0u, 0u);     // column 64 = bf16(1.0): the bias column
+        *reinterpret_cast<uint4*>(row + 9 * kLbo) = make_uint4(0u, 0u, 0u, 0u);
     }
 
     // The actor on this thread's observation; CTA-collective (every thread of the CTA must call it each step).

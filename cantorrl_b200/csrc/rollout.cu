@@ -20,6 +20,9 @@
 namespace cantor {
 
 constexpr int kRollThreads = 128;
+#ifndef CANTOR_MLP_TC_BLOCKS
+#define CANTOR_MLP_TC_BLOCKS 6       // resident CTAs per SM of the tensor-core MLP actor (80 registers, 36 KB of shared memory each)
+#endif
 // How many copies of the step body the inner loop (one Philox call = up to 4 steps) is unrolled into.  The body is ~1 000
 // SASS instructions; four copies (64 KB) showed 23 % of the stall samples in `no_instruction`.  Measured on the B200
 // (2^20 envs x 252 steps, GBM on the fly, delta policy): 1 copy 2.09 ms, 2 copies 2.04 ms, 4 copies 2.12 ms; the recurrent
@@ -137,7 +140,7 @@ __device__ __noinline__ float2 policy_mlp(const float* o, const float* __restric
 //      The recurrent form runs 256 envs per CTA (two groups of 128 that ping-pong) plus a ninth warp that only issues MMAs /
 //      TMA copies (lstmtc::Actor::issuer_loop).
 template <int SRC, int MLP, bool WRITE>
-__global__ void __launch_bounds__(MLP == 3 ? lstmtc::kThreads : kRollThreads)
+__global__ void __launch_bounds__(MLP == 3 ? lstmtc::kThreads : kRollThreads, MLP == 2 ? CANTOR_MLP_TC_BLOCKS : 1)
 rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const PolicyConsts pc, long long n_envs,
                long long env_offset, long long total_envs, int n_steps, const StatsOut st, const RolloutOut out,
                int obs_tma_ok, int share_quote) {
