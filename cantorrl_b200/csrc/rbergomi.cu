@@ -157,23 +157,23 @@ struct InnerConsts {
     float log2_xi_plus_dk[kInnerSteps];   // log2(xi) + dk * log2(e): v_k = exp2(X_k log2e + this)
     float rho, rho_c, r_dt, half_dt, sqrt_dt, log_s0;
 };
-__device__ __forceinline__ void fill_inner_consts(InnerConsts& c, float S, float xi, double H, double eta, double rho,
+// Called by threads 0 .. kInnerSteps of the CTA: thread n computes tap n (one float64 log + exp each -- done by a single
+// thread the 31 taps were 27 % of the kernel's instructions and a serial prologue in front of every pricing), thread 0 the scalars.
+__device__ __forceinline__ void fill_inner_consts(InnerConsts& c, int n, float S, float xi, double H, double eta, double rho,
                                                   const RbConsts& k) {
     const double cc = sqrt(2.0 * H) * eta / sqrt((double)kInnerM);
-    c.L[0] = 0.f;
     const double l2xi = log2((double)fmaxf(xi, 1e-30f));
-#pragma unroll
-    for (int n = 0; n <= kInnerSteps; ++n) {
-        const double lam = (n == 0) ? 0.0 : 0.5 * exp(2.0 * H * log((double)n * k.dt));
-        if (n >= 1) c.L[n] = (float)(cc * lam);
-        if (n < kInnerSteps) c.log2_xi_plus_dk[n] = (float)(l2xi - eta * eta * lam * 1.4426950408889634);
+    const double lam = (n == 0) ? 0.0 : 0.5 * exp(2.0 * H * log((double)n * k.dt));
+    c.L[n] = (n == 0) ? 0.f : (float)(cc * lam);
+    if (n < kInnerSteps) c.log2_xi_plus_dk[n] = (float)(l2xi - eta * eta * lam * 1.4426950408889634);
+    if (n == 0) {
+        c.rho = (float)rho;
+        c.rho_c = (float)sqrt(fmax(0.0, 1.0 - rho * rho));
+        c.r_dt = (float)(k.r * k.dt);
+        c.half_dt = (float)(0.5 * k.dt);
+        c.sqrt_dt = k.sqrt_dt_f;
+        c.log_s0 = logf(S);
     }
-    c.rho = (float)rho;
-    c.rho_c = (float)sqrt(fmax(0.0, 1.0 - rho * rho));
-    c.r_dt = (float)(k.r * k.dt);
-    c.half_dt = (float)(0.5 * k.dt);
-    c.sqrt_dt = k.sqrt_dt_f;
-    c.log_s0 = logf(S);
 }
 
 template <int NW>
@@ -295,8 +295,8 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
         xi0 = st.y;                                                                             // xi := v_t (:439)
     }
     const int n_mc = k.n_mc;
-    if (threadIdx.x == 0)
-        fill_inner_consts(sc, S, xi0, path_params[2LL * n_paths + p], path_params[3LL * n_paths + p], path_params[4LL * n_paths + p], k);
+    if (threadIdx.x <= kInnerSteps)
+        fill_inner_consts(sc, (int)threadIdx.x, S, xi0, path_params[2LL * n_paths + p], path_params[3LL * n_paths + p], path_params[4LL * n_paths + p], k);
     const unsigned long long gp = (unsigned long long)(k.path_offset + p);
     InnerDraws dr{ex_dW1, ex_dW2, (unsigned)gp, (unsigned)t | ((k.shared_draws ? 0u : (unsigned)kind) << 24),   // independent draws per kind (:437-446)
                   make_uint2(k.seed_lo, k.seed_hi)};
