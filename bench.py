@@ -240,6 +240,11 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the e2e leg stages 65 B per env-step through page-locked host memory: keep this rank (and the memory it pins) on the
+    # NUMA node of its GPU's PCIe root; the CPU baseline below gets the full core set back
+    from cantorrl_b200.distributed import bind_to_gpu_numa_node
+    all_cpus = os.sched_getaffinity(0)
+    bound_cpus = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, T, K, W = args.envs, args.episode_length, args.steps, args.warmup
@@ -514,7 +519,10 @@ def main():
                 kernel="rbergomi_price_kernel<tcgen05 split-TF32 FIR> (5000 inner paths x 30 steps per ATM call / put)", ms=rb_res[0],
                 pricings=rb_res[1], inner_path_steps_per_s=rb_res[1] * 5000.0 * 30 / (rb_res[0] * 1e-3),
                 reference_workload_seconds=100000 * 252 * 2 / (rb_res[1] / (rb_res[0] * 1e-3)))
+        line["config"]["host_numa_bind"] = (f"{len(bound_cpus)} of {len(all_cpus)} CPUs (GPU-local node)" if bound_cpus
+                                            else "none (single node, unknown topology or disabled)")
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -39,3 +39,48 @@ def init_process_group(backend: str = "nccl", device=None):
             kw["device_id"] = device
         dist.init_process_group(backend, rank=rank, world_size=world, **kw)
     return rank, local_rank, world
+
+
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_local_cpus(pci_bus_id: str, sysfs: str = "/sys/bus/pci/devices") -> set:
+    """CPUs on the NUMA node whose PCIe root the GPU ``pci_bus_id`` ("0000:1b:00.0") hangs off (sysfs ``local_cpulist``);
+    empty when sysfs does not say (a VM without NUMA information, node −1)."""
+    try:
+        with open(os.path.join(sysfs, pci_bus_id.lower(), "local_cpulist")) as f:
+            return _parse_cpulist(f.read())
+    except (OSError, ValueError):
+        return set()
+
+
+def bind_to_gpu_numa_node(device_index: int, sysfs: str = "/sys/bus/pci/devices"):
+    """Restrict this process to the CPUs local to CUDA device ``device_index`` BEFORE it page-locks its staging buffers.
+
+    The host-buffer entry points (``cantor_vecenv_step_host``) move 65 B per env-step over PCIe; Linux places page-locked
+    memory on the NUMA node of the allocating thread, so an unbound rank of an 8-GPU job stages half of its traffic
+    through the other socket.  One process per GPU + this call keeps every rank's DMA on its own root complex.
+    Never fails: returns the CPU set it bound to, or None when the topology is unknown, the local CPUs are outside the
+    cgroup's cpuset, or ``CANTOR_NO_NUMA_BIND`` is set.
+    """
+    if os.environ.get("CANTOR_NO_NUMA_BIND") or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        allowed = os.sched_getaffinity(0)
+        cpus = gpu_local_cpus(bus, sysfs) & allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:           # topology probing must never take a job down
+        return None

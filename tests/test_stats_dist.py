@@ -137,3 +137,26 @@ def test_rollout_oracle_free_running_is_self_consistent():
     assert np.isclose(vec[3] / vec[0], s["mean_abs_pnl"]) and np.isclose(vec[5] / vec[0], s["mean_cost"])
     u = rollout_oracle.uniform_actions(7, np.arange(1000), 3)
     assert u.dtype == np.float32 and u.min() >= -1 and u.max() < 1 and abs(u.mean()) < 0.05
+
+
+def test_gpu_local_cpu_list_from_sysfs(tmp_path):
+    """cantorrl_b200.distributed: the CPU set a rank binds to comes from the GPU's sysfs ``local_cpulist``."""
+    from cantorrl_b200.distributed import _parse_cpulist, gpu_local_cpus
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("\n") == set()
+    d = tmp_path / "0000:1b:00.0"
+    d.mkdir()
+    (d / "local_cpulist").write_text("0-55,112-167\n")
+    cpus = gpu_local_cpus("0000:1B:00.0", sysfs=str(tmp_path))
+    assert len(cpus) == 112 and 55 in cpus and 56 not in cpus and 167 in cpus
+    assert gpu_local_cpus("0000:9a:00.0", sysfs=str(tmp_path)) == set()       # unknown device: no binding, no error
+
+
+def test_numa_bind_is_a_no_op_without_a_gpu_or_when_disabled(monkeypatch):
+    import os
+    from cantorrl_b200.distributed import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None                                   # no CUDA device here: must not raise
+    monkeypatch.setenv("CANTOR_NO_NUMA_BIND", "1")
+    assert bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
