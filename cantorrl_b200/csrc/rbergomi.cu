@@ -33,6 +33,9 @@ constexpr unsigned kStreamRbInner = 0x52424900u;    // "RBI\0"
 constexpr int kInnerSteps = 30;                     // int(T_OPTION_TENOR / DT)  (:250)
 constexpr int kInnerM = 32;                         // next_power_of_two(31)     (:262)
 constexpr int kPriceThreads = 128;
+#ifndef CANTOR_RB_PRICE_BLOCKS
+#define CANTOR_RB_PRICE_BLOCKS 4          // resident pricing CTAs per SM the tensor-core pricer is compiled for (register cap 65536 / (128 x this))
+#endif
 constexpr int kOuterThreads = 256;
 constexpr int kOuterMaxM = 1024;
 
@@ -233,8 +236,9 @@ struct InnerDraws {
     unsigned c0, c1;
     uint2 key;
 };
+template <bool EX>
 __device__ __forceinline__ void draw_w1(const InnerDraws& d, long long row, unsigned q, float (&w1)[kInnerM]) {
-    if (d.dW1 != nullptr) {
+    if (EX) {
         const double* a = d.dW1 + (row + q) * kInnerM;
 #pragma unroll
         for (int j = 0; j < kInnerM; ++j) w1[j] = (float)a[j];
@@ -247,8 +251,9 @@ __device__ __forceinline__ void draw_w1(const InnerDraws& d, long long row, unsi
         }
     }
 }
+template <bool EX>
 __device__ __forceinline__ void draw_w2(const InnerDraws& d, long long row, unsigned q, int chunk, float (&w2)[4]) {
-    if (d.dW2 != nullptr) {
+    if (EX) {
         const double* a = d.dW2 + (row + q) * kInnerM + 4 * chunk;
 #pragma unroll
         for (int j = 0; j < 4; ++j) w2[j] = (float)a[j];
@@ -270,9 +275,9 @@ __device__ __forceinline__ float inner_step(float logS, float Xk, float w1k, flo
 }
 
 // grid = (n_paths, n_days, 2): CTA (p, d, kind) prices the ATM call (kind 0) or put (1) of path p at day t_begin + d;
-// with exported draws: grid = (batch), inputs from the arrays, price written to price_out.
-template <bool TC>
-__global__ void __launch_bounds__(kPriceThreads)
+// with exported draws (EX, the parity form): grid = (batch), inputs from the arrays, price written to price_out.
+template <bool TC, bool EX>
+__global__ void __launch_bounds__(kPriceThreads, TC ? CANTOR_RB_PRICE_BLOCKS : 1)
 rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, int n_paths, int T, int t_begin,
                       const double* __restrict__ path_params, const double* __restrict__ ex_S0, const double* __restrict__ ex_K,
                       const double* __restrict__ ex_xi, const double* __restrict__ ex_dW1, const double* __restrict__ ex_dW2,
@@ -280,7 +285,7 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
     __shared__ InnerConsts sc;
     __shared__ float red[kPriceThreads / 32];
     extern __shared__ __align__(128) unsigned char dyn[];                                       // TC: A_hi, A_lo, B_hi, B_lo, mbarrier, TMEM slot
-    const bool exported = ex_dW1 != nullptr;
+    constexpr bool exported = EX;
     const int p = blockIdx.x, t = t_begin + blockIdx.y;
     const int kind = exported ? ex_is_put : blockIdx.z;
     float S, K, xi0;
@@ -310,12 +315,12 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
         for (int n = 0; n <= kInnerSteps; ++n) L[n] = sc.L[n];                                  // filter taps in registers
         for (int q = threadIdx.x; q < n_mc; q += kPriceThreads) {
             float w1[kInnerM];
-            draw_w1(dr, row, (unsigned)q, w1);
+            draw_w1<EX>(dr, row, (unsigned)q, w1);
             float logS = sc.log_s0;
 #pragma unroll
             for (int kk = 0; kk < kInnerSteps; ++kk) {
                 float w2[4];
-                if ((kk & 3) == 0) draw_w2(dr, row, (unsigned)q, kk >> 2, w2);
+                if ((kk & 3) == 0) draw_w2<EX>(dr, row, (unsigned)q, kk >> 2, w2);
                 float acc = 0.f;
 #pragma unroll
                 for (int n = 1; n <= kInnerSteps; ++n) acc = fmaf(L[n], w1[(kk - n) & (kInnerM - 1)], acc);
@@ -367,7 +372,7 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
             const int q = it * kPriceThreads + threadIdx.x;
             const bool live = q < n_mc;
             float w1[kInnerM];
-            draw_w1(dr, row, (unsigned)(live ? q : 0), w1);
+            draw_w1<EX>(dr, row, (unsigned)(live ? q : 0), w1);
 #pragma unroll
             for (int cch = 0; cch < kInnerM / 4; ++cch) {                                       // this thread's A row, hi and lo
                 float4 h, l;
@@ -414,7 +419,7 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
                     const int kk = half * 16 + j;
                     if (kk < kInnerSteps) {
                         float w2[4];
-                        if ((kk & 3) == 0) draw_w2(dr, row, (unsigned)(live ? q : 0), kk >> 2, w2);
+                        if ((kk & 3) == 0) draw_w2<EX>(dr, row, (unsigned)(live ? q : 0), kk >> 2, w2);
                         logS = inner_step(logS, X[j], w1[kk], w2[kk & 3], kk, sc);
                     }
                 }
@@ -439,6 +444,17 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
             if (t == T - 1) reinterpret_cast<float*>(rec + (long long)T * ld + p)[kind == 0 ? 2 : 3] = price;   // stale marks of row T
         }
     }
+}
+
+// The tensor-core pricer needs 41 KB of shared memory per CTA; without a stated preference the driver picks a carve-out that
+// holds only three of them per SM.  Ask for the largest one (per device, once) so that CANTOR_RB_PRICE_BLOCKS CTAs fit.
+static void prefer_shared_memory_for_pricer() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaFuncSetAttribute(rbergomi_price_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(rbergomi_price_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    done[dev] = true;
 }
 
 static int make_rb_consts(const cantor_rbergomi_params* p, RbConsts* k) {
@@ -495,12 +511,13 @@ extern "C" int cantor_rbergomi_price_atm(const cantor_rbergomi_params* params, f
     if (t_end == t_begin) return CANTOR_OK;
     const dim3 grid((unsigned)n_paths, (unsigned)(t_end - t_begin), 2u);
     cudaStream_t s = (cudaStream_t)stream;
+    if (params->tensor_cores) prefer_shared_memory_for_pricer();
     if (params->tensor_cores)
-        rbergomi_price_kernel<true><<<grid, kPriceThreads, rbtc::kSmemBytes, s>>>(k, (float4*)svcp, ld, n_paths, episode_length, t_begin,
+        rbergomi_price_kernel<true, false><<<grid, kPriceThreads, rbtc::kSmemBytes, s>>>(k, (float4*)svcp, ld, n_paths, episode_length, t_begin,
                                                                                   path_params, nullptr, nullptr, nullptr, nullptr,
                                                                                   nullptr, 0, nullptr);
     else
-        rbergomi_price_kernel<false><<<grid, kPriceThreads, 0, s>>>(k, (float4*)svcp, ld, n_paths, episode_length, t_begin, path_params,
+        rbergomi_price_kernel<false, false><<<grid, kPriceThreads, 0, s>>>(k, (float4*)svcp, ld, n_paths, episode_length, t_begin, path_params,
                                                                     nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
     return check_launch("rbergomi_price_kernel");
 }
@@ -520,11 +537,12 @@ extern "C" int cantor_rbergomi_price_from_increments(const cantor_rbergomi_param
     k.n_mc = n_mc;
     const double* pp = H - 2LL * batch;
     cudaStream_t s = (cudaStream_t)stream;
+    if (params->tensor_cores) prefer_shared_memory_for_pricer();
     if (params->tensor_cores)
-        rbergomi_price_kernel<true><<<(unsigned)batch, kPriceThreads, rbtc::kSmemBytes, s>>>(k, nullptr, 0, batch, 0, 0, pp, S0, K, xi, dW1,
+        rbergomi_price_kernel<true, true><<<(unsigned)batch, kPriceThreads, rbtc::kSmemBytes, s>>>(k, nullptr, 0, batch, 0, 0, pp, S0, K, xi, dW1,
                                                                                              dW2, is_put, price);
     else
-        rbergomi_price_kernel<false><<<(unsigned)batch, kPriceThreads, 0, s>>>(k, nullptr, 0, batch, 0, 0, pp, S0, K, xi, dW1, dW2, is_put,
+        rbergomi_price_kernel<false, true><<<(unsigned)batch, kPriceThreads, 0, s>>>(k, nullptr, 0, batch, 0, 0, pp, S0, K, xi, dW1, dW2, is_put,
                                                                                price);
     return check_launch("rbergomi_price_kernel (exported increments)");
 }
