@@ -34,7 +34,8 @@ constexpr int kInnerSteps = 30;                     // int(T_OPTION_TENOR / DT) 
 constexpr int kInnerM = 32;                         // next_power_of_two(31)     (:262)
 constexpr int kPriceThreads = 128;
 #ifndef CANTOR_RB_PRICE_BLOCKS
-#define CANTOR_RB_PRICE_BLOCKS 4          // resident pricing CTAs per SM the tensor-core pricer is compiled for (register cap 65536 / (128 x this))
+#define CANTOR_RB_PRICE_BLOCKS 5          // resident pricing CTAs per SM the tensor-core pricer is compiled for (register cap 65536 / (128 x this));
+                                          // measured 3 / 4 / 5: 11.39 / 11.20 / 11.07 ms on the 512 x 32-day bench, no spills at 96 registers
 #endif
 constexpr int kOuterThreads = 256;
 constexpr int kOuterMaxM = 1024;
