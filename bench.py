@@ -63,40 +63,121 @@ def parse_args():
 
 
 # --------------------------------------------------------------------------------------------- CPU legs
-def _cpu_book(n_paths=4096, T=252, seed=42):
-    """Env-schema arrays with the GPU config's dynamics, NumPy."""
-    from oracle import bs_oracle
-    rng = np.random.default_rng(seed)
-    z = rng.standard_normal((n_paths, T))
-    logS = np.cumsum((R - 0.5 * XI) * DT + np.sqrt(XI * DT) * z, axis=1)
-    S = S0 * np.exp(np.concatenate([np.zeros((n_paths, 1)), logS], axis=1))
-    V = np.full_like(S, XI)
-    Cc, Pp = bs_oracle.atm_book(S, V)
-    return S, V, Cc, Pp
+# The CPU arm is the UNMODIFIED reference env (src/env/hedging_env_v2.py, staged byte for byte into the git-ignored
+# oracle/_ref/ by oracle/stage_ref.py -- run by __graft_entry__.build() -- and loaded under oracle/_gym_stub): P forked
+# processes, one env each, which is the reference's SubprocVecEnv model (src/agents/train_ppo_v2.py:131-134) without the
+# pipes.  The scalar port (oracle/hedge_scalar.py) is timed next to it as a second, labelled number.
+REF_PATHS = 4096
+_ref_env = None
 
 
-def _cpu_worker(args):
+def _ref_init(npz_path, seed_base):
+    """Pool initializer: one reference env per worker process, constructed (it np.loads the file) outside any timed region."""
+    global _ref_env
+    import warnings
+    from oracle import ref_runner
+    warnings.simplefilter("ignore")
+    wid = os.getpid()
+    env = ref_runner.reference_env_class("v2")(npz_path, record_metrics=True, **ENV_KW)
+    acts = np.random.default_rng(seed_base + wid).uniform(-1, 1, (4096, 2)).astype(np.float32)
+    acts[:, 1] = 0.0                                                            # one European call: the put leg is never traded
+    env.reset(seed=seed_base + wid)
+    _ref_env = [env, acts, 0]
+
+
+def _ref_steps(n_steps):
+    """n_steps env-steps of this worker's reference env (reset on terminated); returns (steps, seconds)."""
+    env, acts, at = _ref_env
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        _, _, term, _, _ = env.step(acts[at & 4095])
+        at += 1
+        if term:
+            env.reset()
+    _ref_env[2] = at
+    return n_steps, time.perf_counter() - t0
+
+
+def _ref_seconds(seconds):
+    env, acts, at = _ref_env
+    n, t0 = 0, time.perf_counter()
+    while True:
+        for _ in range(256):
+            _, _, term, _, _ = env.step(acts[at & 4095])
+            at += 1
+            if term:
+                env.reset()
+        n += 256
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            _ref_env[2] = at
+            return n, el
+
+
+def _port_worker(args):
     seconds, seed = args
     from oracle.hedge_oracle import EnvParams
     from oracle.hedge_scalar import time_scalar_env
-    S, V, Cc, Pp = _cpu_book(256, 252, 42)
+    from oracle.ref_runner import gbm_env_schema
+    S, V, Cc, Pp = gbm_env_schema(256, 252, 42)
     return time_scalar_env(S, V, Cc, Pp, EnvParams(**ENV_KW), seconds, seed)
 
 
-def cpu_baseline(seconds, procs):
-    """P forked processes, one scalar env each: the reference's SubprocVecEnv model without the pipes."""
+def _side_baselines():
+    """the reference's own repricing / delta-hedge functions and the NumPy outer path step, one core."""
+    from oracle import ref_runner as rr
+    out = {}
+    if rr.staged():
+        v, s = rr.time_black_scholes_vectorized(1 << 20, repeats=2)
+        out["black_scholes_vectorized"] = dict(value=v, unit="repricings/s (call+put)", seconds=s, kind="reference",
+                                               what="src/sim/option_price_assignment.py:10-21 on 2^20 float64 elements, 1 core")
+        v, s = rr.time_bs_delta_hedge(16, 252)
+        out["bs_delta_hedge"] = dict(value=v, unit="path-steps/s", seconds=s, kind="reference",
+                                     what="src/tools/bs_delta.py:36-55 on 16 GBM paths x 253, 1 core")
+    v, s = rr.time_numpy_outer_step(1 << 20, 8)
+    out["numpy_outer_euler_step"] = dict(value=v, unit="path-steps/s", seconds=s, kind="port",
+                                         what="NumPy float64 restatement of src/sim/rbergomi_sim.py:454-464 on 2^20 paths x 8 days, 1 core "
+                                              "(the file itself needs CuPy + a GPU)")
+    return out
+
+
+def cpu_baseline(seconds, procs, side=True):
+    """P forked processes x one UNMODIFIED reference env each (kind "reference"); the port as a second number."""
     import multiprocessing as mp
+    from oracle import ref_runner as rr
     ctx = mp.get_context("fork")
+    out = {}
+    if rr.staged():
+        tmp, npz = rr.tmp_npz(REF_PATHS, 252, 42)
+        with ctx.Pool(procs, initializer=_ref_init, initargs=(npz, 1000)) as pool:
+            pool.map(_ref_seconds, [0.5] * procs)                                  # warm-up (BASELINE.md section 3.3: >= 1 s in all)
+            pool.map(_ref_seconds, [0.5] * procs)
+            t0 = time.perf_counter()
+            res = pool.map(_ref_seconds, [seconds] * procs)
+            wall = time.perf_counter() - t0
+            one = None
+        with ctx.Pool(1, initializer=_ref_init, initargs=(npz, 2000)) as pool:     # (a) of section 3.4: one process alone
+            pool.map(_ref_seconds, [0.5])
+            one = pool.map(_ref_seconds, [min(seconds, 3.0)])[0]
+        tmp.cleanup()
+        steps = sum(r[0] for r in res)
+        out = dict(value=sum(r[0] / r[1] for r in res), unit="env-steps/s", cores=procs, kind="reference",
+                   single_process_value=one[0] / one[1],
+                   sample=f"{procs} forked processes x 1 UNMODIFIED reference HedgingEnv (src/env/hedging_env_v2.py staged in oracle/_ref, "
+                          f"gymnasium stub), record_metrics=True, v2 training keywords, uniform float32 actions (put leg 0), reset on "
+                          f"terminated, {REF_PATHS} GBM paths x 252 steps; {steps} env-steps in {wall:.1f} s wall")
     with ctx.Pool(procs) as pool:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(seconds, i) for i in range(procs)])
-        wall = time.perf_counter() - t0
-    steps = sum(r[0] for r in res)
-    rate = sum(r[0] / r[1] for r in res)
-    return dict(value=rate, unit="env-steps/s", cores=procs, kind="port",
-                sample=f"{procs} processes x 1 scalar reference-shaped env (oracle/hedge_scalar.py), greeks on, "
-                       f"uniform float32 actions, {steps} env-steps in {wall:.1f} s wall on 256 GBM paths x 252 steps",
-                cpu=_cpu_model())
+        pres = pool.map(_port_worker, [(min(seconds, 4.0), i) for i in range(procs)])
+    port = dict(value=sum(r[0] / r[1] for r in pres), unit="env-steps/s", cores=procs, kind="port",
+                sample=f"{procs} processes x 1 scalar reference-shaped env (oracle/hedge_scalar.py) on 256 GBM paths x 252 steps")
+    if out:
+        out["port"] = port
+    else:                                   # oracle/_ref not staged (build() did not run where /root/reference exists)
+        out = port
+    out["cpu"] = _cpu_model()
+    if side:
+        out["side_baselines"] = _side_baselines()
+    return out
 
 
 def _cpu_model():
@@ -109,60 +190,63 @@ def _cpu_model():
     return "unknown"
 
 
+def _numa_note(local_rank):
+    """config.host_numa_bind, computed the same way by both arms so that their configs compare equal on one box."""
+    try:
+        from cantorrl_b200.distributed import bind_to_gpu_numa_node
+        all_cpus = os.sched_getaffinity(0)
+        bound = bind_to_gpu_numa_node(local_rank)
+        note = f"{len(bound)} of {len(all_cpus)} CPUs (GPU-local node)" if bound else "none (single node, unknown topology or disabled)"
+        return note, all_cpus, bound
+    except Exception:
+        return "none (single node, unknown topology or disabled)", None, None
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference-shaped CPU port on all host cores; one 'step' = one 252-step episode per process."""
+    """--impl reference: the unmodified reference env on all host cores; one bench 'step' = EP episodes x 252 steps per process."""
     if rank != 0:
         return
     import multiprocessing as mp
-    from oracle.hedge_oracle import EnvParams
-    from oracle.hedge_scalar import ScalarEnv
+    from oracle import ref_runner as rr
     procs = os.cpu_count() or 1
     T = args.episode_length
+    note, all_cpus, _ = _numa_note(int(os.environ.get("LOCAL_RANK", "0")))
+    if all_cpus:
+        os.sched_setaffinity(0, all_cpus)                 # the CPU arm uses every core
     ctx = mp.get_context("fork")
-    S, V, Cc, Pp = _cpu_book(256, T, 42)
-
     EP = 8                                                # episodes per process per bench step (bounded sample)
-
-    def episode_batch(seed):
-        env = ScalarEnv(S, V, Cc, Pp, EnvParams(**ENV_KW), seed=seed)
-        acts = np.random.default_rng(seed).uniform(-1, 1, (EP * T, 2)).astype(np.float32)
-        acts[:, 1] = 0.0
-        env.reset()
-        n = 0
-        for a in acts:
-            _, _, term, _, _ = env.step(a)
-            n += 1
-            if term:
-                env.reset()
-        return n
-
-    global _episode_batch
-    _episode_batch = episode_batch
-    with ctx.Pool(procs) as pool:
-        for w in range(args.warmup):
-            pool.map(_call_episode_batch, range(procs))
-        t0 = time.perf_counter()
-        total = 0
-        for k in range(args.steps):
-            total += sum(pool.map(_call_episode_batch, range(k * procs, (k + 1) * procs)))
-        el = time.perf_counter() - t0
+    kind = "reference" if rr.staged() else "port"
+    if kind == "reference":
+        tmp, npz = rr.tmp_npz(REF_PATHS, T, 42)
+        with ctx.Pool(procs, initializer=_ref_init, initargs=(npz, 1000)) as pool:
+            for w in range(args.warmup):
+                pool.map(_ref_steps, [EP * T] * procs)
+            t0 = time.perf_counter()
+            total = 0
+            for k in range(args.steps):
+                total += sum(r[0] for r in pool.map(_ref_steps, [EP * T] * procs))
+            el = time.perf_counter() - t0
+        tmp.cleanup()
+        what = "UNMODIFIED reference HedgingEnv (src/env/hedging_env_v2.py staged in oracle/_ref, gymnasium stub)"
+    else:
+        with ctx.Pool(procs) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_port_worker, [(max(1.0, 0.2 * args.steps), i) for i in range(procs)])
+            el = time.perf_counter() - t0
+        total = sum(r[0] for r in res)
+        what = "scalar reference-shaped port (oracle/hedge_scalar.py): oracle/_ref is not staged"
     value = total / el
-    sample = (f"{procs} processes x 1 scalar reference-shaped env (oracle/hedge_scalar.py, greeks on) x {EP} episodes x {T} steps "
-              f"per bench step; {total} env-steps in {el:.1f} s")
+    sample = (f"{procs} processes x 1 {what}, greeks on, x {EP} episodes x {T} steps per bench step on {REF_PATHS} GBM paths; "
+              f"{total} env-steps in {el:.1f} s")
+    cfg = _config(args, world)
+    cfg["host_numa_bind"] = note
     line = dict(impl="reference", metric="env-steps/sec (fused hedge step)", value=value, unit="env-steps/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el / max(args.steps, 1),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=_config(args, world), gpu_launches=0,
-                cpu_baseline=dict(value=value, unit="env-steps/s", cores=procs, kind="port", sample=sample, cpu=_cpu_model()),
+                config=cfg, gpu_launches=0,
+                cpu_baseline=dict(value=value, unit="env-steps/s", cores=procs, kind=kind, sample=sample, cpu=_cpu_model()),
                 e2e=dict(value=value, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
-
-
-_episode_batch = None
-
-
-def _call_episode_batch(seed):
-    return _episode_batch(seed)
 
 
 # --------------------------------------------------------------------------------------------- GPU side

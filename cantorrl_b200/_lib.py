@@ -156,6 +156,8 @@ SIGNATURES = {
     "cantor_vecenv_num_paths": (C.c_int, [C.c_void_p]),
     "cantor_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "cantor_host_unregister": (C.c_int, [C.c_void_p]),
+    "cantor_host_copy_probe": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double,
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cantor_env_reset": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_env_step": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,

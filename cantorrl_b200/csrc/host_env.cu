@@ -9,6 +9,7 @@
 //
 // Replaces: HedgingEnv.__init__ / reset / step (src/env/hedging_env_v2.py:10-77, :145-173, :175-294) as seen
 // through SB3's VecEnv by src/agents/train_ppo_v2.py:127-141.
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -270,5 +271,71 @@ extern "C" int cantor_host_register(void* ptr, size_t bytes) {
 extern "C" int cantor_host_unregister(void* ptr) {
     CANTOR_REQUIRE(ptr != nullptr, "NULL buffer");
     CANTOR_CUDA(cudaHostUnregister(ptr));
+    return CANTOR_OK;
+}
+
+// Raw ceiling of the host-buffer face: the copies of cantor_vecenv_step_host and nothing else.  One round moves h2d_bytes
+// host -> device and d2h_bytes device -> host between page-locked host memory and HBM in n_chunks pieces round-robined over
+// three streams (the H2D piece of a chunk, then its D2H piece, on the chunk's stream), then -- with sync_each_round, as a gym
+// step must -- waits for all three streams.  Repeats for at least `seconds` of wall time.
+extern "C" int cantor_host_copy_probe(int32_t device, int64_t d2h_bytes, int64_t h2d_bytes, int32_t n_chunks,
+                                      int32_t sync_each_round, double seconds, double* d2h_gbs, double* h2d_gbs,
+                                      double* rounds_per_s) {
+    CANTOR_REQUIRE(d2h_bytes >= 0 && h2d_bytes >= 0 && d2h_bytes + h2d_bytes > 0, "nothing to copy");
+    CANTOR_REQUIRE(n_chunks >= 1 && n_chunks <= 4096 && seconds > 0 && seconds <= 60, "n_chunks in [1, 4096], seconds in (0, 60]");
+    CANTOR_REQUIRE(d2h_gbs && h2d_gbs && rounds_per_s, "output pointer is NULL");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+        return fail(CANTOR_ERR_NO_DEVICE, "%s: %s", "cantor_host_copy_probe", "no usable CUDA device");
+    CANTOR_CUDA(cudaSetDevice(device));
+    void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    cudaError_t err = cudaSuccess;
+    if (h2d_bytes) err = cudaHostAlloc(&h_in, h2d_bytes, cudaHostAllocPortable);
+    if (err == cudaSuccess && d2h_bytes) err = cudaHostAlloc(&h_out, d2h_bytes, cudaHostAllocPortable);
+    if (err == cudaSuccess && h2d_bytes) err = cudaMalloc(&d_in, h2d_bytes);
+    if (err == cudaSuccess && d2h_bytes) err = cudaMalloc(&d_out, d2h_bytes);
+    if (err == cudaSuccess && h_in) memset(h_in, 1, h2d_bytes);
+    if (err == cudaSuccess && h_out) memset(h_out, 0, d2h_bytes);
+    for (int i = 0; i < 3 && err == cudaSuccess; ++i) err = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    long long rounds = 0;
+    double elapsed = 0.0;
+    if (err == cudaSuccess) {
+        const int64_t din = (h2d_bytes / n_chunks + 15) / 16 * 16, dout = (d2h_bytes / n_chunks + 15) / 16 * 16;
+        auto one_round = [&]() -> cudaError_t {
+            cudaError_t e = cudaSuccess;
+            for (int c = 0; c < n_chunks && e == cudaSuccess; ++c) {
+                const int64_t i0 = (int64_t)c * din, o0 = (int64_t)c * dout;
+                const int64_t ni = i0 < h2d_bytes ? (i0 + din <= h2d_bytes ? din : h2d_bytes - i0) : 0;
+                const int64_t no = o0 < d2h_bytes ? (o0 + dout <= d2h_bytes ? dout : d2h_bytes - o0) : 0;
+                if (ni > 0) e = cudaMemcpyAsync((char*)d_in + i0, (char*)h_in + i0, ni, cudaMemcpyHostToDevice, st[c % 3]);
+                if (e == cudaSuccess && no > 0) e = cudaMemcpyAsync((char*)h_out + o0, (char*)d_out + o0, no, cudaMemcpyDeviceToHost, st[c % 3]);
+            }
+            return e;
+        };
+        auto sync_all = [&]() -> cudaError_t {
+            cudaError_t e = cudaSuccess;
+            for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamSynchronize(st[i]);
+            return e;
+        };
+        err = one_round();                                   // warm-up
+        if (err == cudaSuccess) err = sync_all();
+        const auto t0 = std::chrono::steady_clock::now();
+        while (err == cudaSuccess) {
+            err = one_round();
+            if (err == cudaSuccess && (sync_each_round || (rounds & 7) == 7)) err = sync_all();
+            ++rounds;
+            elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (elapsed >= seconds && (sync_each_round || (rounds & 7) == 0)) break;
+        }
+        if (err == cudaSuccess) err = sync_all();
+        elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    for (auto& s : st) if (s) cudaStreamDestroy(s);
+    cudaFreeHost(h_in); cudaFreeHost(h_out); cudaFree(d_in); cudaFree(d_out);
+    if (err != cudaSuccess) return cuda_fail(err, "cantor_host_copy_probe");
+    *rounds_per_s = rounds / elapsed;
+    *d2h_gbs = (double)d2h_bytes * rounds / elapsed / 1e9;
+    *h2d_gbs = (double)h2d_bytes * rounds / elapsed / 1e9;
     return CANTOR_OK;
 }

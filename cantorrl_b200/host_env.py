@@ -180,3 +180,13 @@ class HostVecEnv:
             self.close()
         except Exception:
             pass
+
+
+def host_copy_probe(device=0, d2h_bytes=57 << 20, h2d_bytes=8 << 20, n_chunks=8, sync_each_round=True, seconds=0.5):
+    """Raw copy ceiling of the host-buffer face (``cantor_host_copy_probe``): the page-locked H2D / D2H traffic of one
+    ``HostVecEnv.step`` with no kernel in between.  Returns ``dict(d2h_gbs, h2d_gbs, rounds_per_s)``."""
+    d2h, h2d, rps = C.c_double(), C.c_double(), C.c_double()
+    _lib.check(_lib.lib().cantor_host_copy_probe(int(device), int(d2h_bytes), int(h2d_bytes), int(n_chunks),
+                                                 int(bool(sync_each_round)), float(seconds), C.byref(d2h), C.byref(h2d),
+                                                 C.byref(rps)), "cantor_host_copy_probe")
+    return dict(d2h_gbs=d2h.value, h2d_gbs=h2d.value, rounds_per_s=rps.value)

@@ -394,6 +394,11 @@ int cantor_vecenv_num_paths(const cantor_vecenv* env);
 /* cudaHostRegister / cudaHostUnregister of a caller-owned buffer (page-locked copies run at full PCIe speed). */
 int cantor_host_register(void* ptr, size_t bytes);
 int cantor_host_unregister(void* ptr);
+/* Raw ceiling of the host-buffer face: only the copies of cantor_vecenv_step_host, no kernel.  One round = h2d_bytes in and
+ * d2h_bytes out between page-locked host memory and HBM, in n_chunks pieces over three streams; sync_each_round = 1 waits for
+ * the streams after every round like a gym step has to.  Runs for >= seconds; reports GB/s per direction and rounds/s. */
+int cantor_host_copy_probe(int32_t device, int64_t d2h_bytes, int64_t h2d_bytes, int32_t n_chunks, int32_t sync_each_round,
+                           double seconds, double* d2h_gbs, double* h2d_gbs, double* rounds_per_s);
 
 #ifdef __cplusplus
 }
