@@ -88,7 +88,8 @@ VECNORM_DOUBLES = 16704
 
 class Policy(C.Structure):
     _fields_ = [("kind", C.c_int32), ("put_leg_disabled", C.c_int32), ("mlp", C.c_void_p), ("actions", C.c_void_p),
-                ("seed", C.c_uint64), ("mlp_tensor_cores", C.c_int32), ("action_squash", C.c_int32)]
+                ("seed", C.c_uint64), ("mlp_tensor_cores", C.c_int32), ("action_squash", C.c_int32), ("obs_clip", C.c_float),
+                ("reserved", C.c_int32)]
 
 
 class StatsOut(C.Structure):
@@ -103,7 +104,12 @@ class RolloutOut(C.Structure):
 
 
 class InfoOut(C.Structure):
-    _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p)]
+    _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p), ("f32", C.c_void_p)]
+
+
+class EnvSim(C.Structure):
+    _fields_ = [("sim", C.POINTER(SimParams)), ("sv", C.c_void_p), ("total_envs", C.c_int64), ("episode_length", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/cantor_hedge.h declares must appear here
@@ -142,7 +148,7 @@ SIGNATURES = {
                                       C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_void_p]),
     "cantor_rollout": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(SimParams), C.c_int32,
-                                 C.POINTER(Policy), C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(StatsOut),
+                                 C.POINTER(Policy), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(StatsOut),
                                  C.POINTER(RolloutOut), C.c_void_p]),
     "cantor_vecenv_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(EnvParams), C.c_int32, C.c_int64, C.c_int32, C.c_int32]),
     "cantor_vecenv_destroy": (C.c_int, [C.c_void_p]),
@@ -163,6 +169,11 @@ SIGNATURES = {
     "cantor_env_step": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.POINTER(ResetRule), C.POINTER(InfoOut), C.c_void_p]),
+    "cantor_env_reset_sim": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvSim), C.POINTER(EnvState), C.c_int64, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cantor_env_step_sim": (C.c_int, [C.POINTER(EnvParams), C.POINTER(EnvSim), C.POINTER(EnvState), C.c_int64, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                      C.POINTER(InfoOut), C.c_int32, C.c_void_p]),
     "cantor_env_step_many": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
                                        C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.POINTER(ResetRule), C.c_void_p]),

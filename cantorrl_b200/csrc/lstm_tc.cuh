@@ -132,7 +132,7 @@ struct Actor {
     __device__ __forceinline__ float* obs_staging(int g) const { return reinterpret_cast<float*>(a2_tile(g)); }
 
     // CTA-collective (all kThreads threads).
-    __device__ __forceinline__ void setup(unsigned char* smem_base, const unsigned char* image) {
+    __device__ __forceinline__ void setup(unsigned char* smem_base, const unsigned char* image, float obs_clip) {
         smem = smem_base;
         img = image;
         uint64_t* bar_mem = reinterpret_cast<uint64_t*>(smem + kOffBars);
@@ -158,7 +158,7 @@ struct Actor {
             uint4* d = reinterpret_cast<uint4*>(smem + kOffW1);
             for (int j = tid; j < (kW1Bytes + kW2Bytes + kW3Bytes) / 16; j += kThreads) d[j] = __ldg(s + j);
         }
-        if (tid < 32) norm_s[tid] = reinterpret_cast<const float*>(img + kImgNorm)[tid];
+        if (tid < 32) norm_s[tid] = tid == 15 ? obs_clip : reinterpret_cast<const float*>(img + kImgNorm)[tid];   // [15] = clip of the normalised obs
         norm = norm_s;
         for (int j = tid; j < kGroups * kABytes / 16; j += kThreads) reinterpret_cast<uint4*>(smem + kOffA)[j] = make_uint4(0u, 0u, 0u, 0u);
         if (tid < 32) {
@@ -401,8 +401,9 @@ struct Actor {
 #endif
         LSTM_TR(grp, 1);
         float x[16];
+        const float clip = nrm[15];
 #pragma unroll
-        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - nrm[i]) * nrm[16 + i], -10.f), 10.f);
+        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - nrm[i]) * nrm[16 + i], -clip), clip);
         x[13] = 1.0f;
         x[14] = 0.f;
         x[15] = 0.f;

@@ -122,7 +122,7 @@ struct Actor {
 
     // One-time CTA setup: converts the float32 weight block to bf16 tiles, allocates 64 TMEM columns, arms the mbarrier.
     // `w` = W1[13][64] b1[64] W2[64][64] b2[64] W3[64][2] b3[2] mean[13] inv_std[13] (cantor_policy.mlp), in global memory.
-    __device__ __forceinline__ void setup(unsigned char* smem, const float* __restrict__ w) {
+    __device__ __forceinline__ void setup(unsigned char* smem, const float* __restrict__ w, float obs_clip) {
         w1 = smem;
         w2 = w1 + kW1Bytes;
         w3 = w2 + kW2Bytes;
@@ -141,7 +141,7 @@ struct Actor {
         const float* b3 = W3 + kHidden * kOut;
         const int tid = threadIdx.x;
         float* norm_s = reinterpret_cast<float*>(a2 + kA2Bytes + 16);
-        if (tid < 32) norm_s[tid] = (tid & 15) < kIn ? (b3 + kOut)[(tid >> 4) * kIn + (tid & 15)] : 0.f;
+        if (tid < 32) norm_s[tid] = (tid & 15) < kIn ? (b3 + kOut)[(tid >> 4) * kIn + (tid & 15)] : (tid == 15 ? obs_clip : 0.f);   // [15] = clip
         norm = norm_s;
         __nv_bfloat16* w1h = reinterpret_cast<__nv_bfloat16*>(w1);
         for (int e = tid; e < kHidden * kK1; e += kRows) {           // B1(n, k) = W1[k][n], k = 13 -> b1[n]
@@ -257,8 +257,9 @@ struct Actor {
     __device__ __forceinline__ float2 forward(const float* o) {
         const int m = threadIdx.x;
         float x[kK1];
+        const float clip = norm[15];                                  // VecNormalize's clip_obs (+inf: the deployment wrapper clips nothing)
 #pragma unroll
-        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - norm[i]) * norm[16 + i], -10.f), 10.f);
+        for (int i = 0; i < kIn; ++i) x[i] = fminf(fmaxf((o[i] - norm[i]) * norm[16 + i], -clip), clip);
         x[13] = 1.0f;
         x[14] = 0.f;
         x[15] = 0.f;

@@ -318,9 +318,9 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
             float w1[kInnerM];
             draw_w1<EX>(dr, row, (unsigned)q, w1);
             float logS = sc.log_s0;
+            float w2[4] = {0.f, 0.f, 0.f, 0.f};                                                 // one draw call serves four consecutive steps
 #pragma unroll
             for (int kk = 0; kk < kInnerSteps; ++kk) {
-                float w2[4];
                 if ((kk & 3) == 0) draw_w2<EX>(dr, row, (unsigned)q, kk >> 2, w2);
                 float acc = 0.f;
 #pragma unroll
@@ -411,6 +411,7 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             float logS = sc.log_s0;
+            float w2[4] = {0.f, 0.f, 0.f, 0.f};                                                 // persists over the four steps of a draw call
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float X[16];
@@ -419,7 +420,6 @@ rbergomi_price_kernel(const RbConsts k, float4* __restrict__ rec, long long ld, 
                 for (int j = 0; j < 16; ++j) {
                     const int kk = half * 16 + j;
                     if (kk < kInnerSteps) {
-                        float w2[4];
                         if ((kk & 3) == 0) draw_w2<EX>(dr, row, (unsigned)(live ? q : 0), kk >> 2, w2);
                         logS = inner_step(logS, X[j], w1[kk], w2[kk & 3], kk, sc);
                     }

@@ -35,6 +35,7 @@ constexpr int kMlpFloats = kMlpIn * kMlpHidden + kMlpHidden + kMlpHidden * kMlpH
 
 struct PolicyConsts {
     int kind, put_disabled, squash;
+    float obs_clip;             // network policies: clip of the normalised observation (+inf = none)
     const float* mlp;
     const float2* actions;      // CANTOR_POLICY_ACTIONS: [n_steps, n_envs] open-loop actions
     unsigned seed_lo, seed_hi;
@@ -89,7 +90,7 @@ __device__ __forceinline__ float2 policy_random(const PolicyConsts& pc, unsigned
 
 // ReLU MLP 13 -> 64 -> 64 -> 2 on the normalised observation; weights broadcast from shared memory.
 // noinline: inlined into the 4x-unrolled step loop the 64-wide accumulator arrays no longer fit the register file
-__device__ __noinline__ float2 policy_mlp(const float* o, const float* __restrict__ w) {
+__device__ __noinline__ float2 policy_mlp(const float* o, const float* __restrict__ w, float obs_clip) {
     const float* W1 = w;
     const float* b1 = W1 + kMlpIn * kMlpHidden;
     const float* W2 = b1 + kMlpHidden;
@@ -100,7 +101,7 @@ __device__ __noinline__ float2 policy_mlp(const float* o, const float* __restric
     const float* inv_std = mean + kMlpIn;
     float x[kMlpIn];
 #pragma unroll
-    for (int i = 0; i < kMlpIn; ++i) x[i] = fminf(fmaxf((o[i] - mean[i]) * inv_std[i], -10.f), 10.f);   // VecNormalize clip
+    for (int i = 0; i < kMlpIn; ++i) x[i] = fminf(fmaxf((o[i] - mean[i]) * inv_std[i], -obs_clip), obs_clip);   // VecNormalize clip
     float h1[kMlpHidden];
 #pragma unroll
     for (int j = 0; j < kMlpHidden; ++j) h1[j] = b1[j];
@@ -142,8 +143,8 @@ __device__ __noinline__ float2 policy_mlp(const float* o, const float* __restric
 template <int SRC, int MLP, bool WRITE>
 __global__ void __launch_bounds__(MLP == 3 ? lstmtc::kThreads : kRollThreads, MLP == 2 ? CANTOR_MLP_TC_BLOCKS : 0)   // 0 = no occupancy hint (a hint of 1 let ptxas take 104 registers for the plain policies: 15.8 -> 17.9 ms)
 rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const PolicyConsts pc, long long n_envs,
-               long long env_offset, long long total_envs, int n_steps, const StatsOut st, const RolloutOut out,
-               int obs_tma_ok, int share_quote) {
+               long long env_offset, long long total_envs, long long first_episode, int n_steps, const StatsOut st,
+               const RolloutOut out, int obs_tma_ok, int share_quote) {
     extern __shared__ __align__(128) float smem_f[];
     float* w_mlp = smem_f;                                                     // [kMlpFloats] float32 weights (MLP == 1)
     constexpr int mlp_floats = MLP == 1 ? (kMlpFloats + 3) / 4 * 4 : (MLP == 2 ? mlptc::kSmemBytes / 4 : (MLP == 3 ? lstmtc::kSmemBytes / 4 : 0));
@@ -151,7 +152,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
     constexpr int kThreads = MLP == 3 ? lstmtc::kThreads : kRollThreads;
     mlptc::Actor actor;
     lstmtc::Actor lstm;
-    if (MLP == 3) lstm.setup(reinterpret_cast<unsigned char*>(smem_f), reinterpret_cast<const unsigned char*>(pc.mlp));
+    if (MLP == 3) lstm.setup(reinterpret_cast<unsigned char*>(smem_f), reinterpret_cast<const unsigned char*>(pc.mlp), pc.obs_clip);
     // [kEnv * 13] observation staging tile when WRITE; the recurrent actor lends its A2 tiles for it (no shared memory left):
     // one [128 x 13] piece per group
     float* tile = MLP == 3 ? lstm.obs_staging(0) : smem_f + mlp_floats;
@@ -160,7 +161,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
     if (MLP == 1) {
         for (int j = threadIdx.x; j < kMlpFloats; j += kRollThreads) w_mlp[j] = pc.mlp[j];
     }
-    if (MLP == 2) actor.setup(reinterpret_cast<unsigned char*>(smem_f), pc.mlp);
+    if (MLP == 2) actor.setup(reinterpret_cast<unsigned char*>(smem_f), pc.mlp, pc.obs_clip);
     __syncthreads();
 
     const bool env_thread = threadIdx.x < kEnv;                                // the others: the recurrent actor's issuer warp
@@ -179,7 +180,8 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
 
     // env state, all in registers
     int pos_c = 0, pos_p = 0, t = 0;
-    long long episode = 0;
+    long long episode = first_episode;
+    const unsigned first_step = (unsigned)((unsigned long long)first_episode * (unsigned long long)k.T);   // random-action stream continues too
     unsigned long long gp = genv;                                              // global path of the current episode
     float4 cur = make_float4(0.f, 0.f, 0.f, 0.f), prev;
     Greeks gk{0.f, 0.f, 0.f};                                                  // ATM greeks of `cur` (on-the-fly, shared with its price)
@@ -231,10 +233,10 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             } else if (MLP == 2) {
                 a = actor.forward(o);                                          // CTA-collective: all 128 threads, every step
             } else if (MLP == 1) {
-                a = policy_mlp(o, w_mlp);
+                a = policy_mlp(o, w_mlp, pc.obs_clip);
             } else {
                 switch (pc.kind) {
-                    case CANTOR_POLICY_RANDOM: a = policy_random(pc, genv, (unsigned)g); break;
+                    case CANTOR_POLICY_RANDOM: a = policy_random(pc, genv, first_step + (unsigned)g); break;
                     case CANTOR_POLICY_DELTA_BASELINES: a = policy_delta_baselines(o, k); break;
                     case CANTOR_POLICY_DELTA_BENCHMARK: a = policy_delta_benchmark(o, k, pos_c, pos_p); break;
                     case CANTOR_POLICY_ACTIONS: a = live ? __ldcs(pc.actions + (long long)g * n_envs + i) : make_float2(0.f, 0.f); break;
@@ -308,8 +310,8 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             if (terminated) {
                 if (live) {
                     const float eb = episode_statistics(stat, acc_reward, acc_pps, acc_abs, acc_cost, k.inv_T_f, st);
-                    if (st.episode_b != nullptr && episode < st.episode_slots)
-                        st.episode_b[episode * n_envs + i] = eb;
+                    if (st.episode_b != nullptr && episode - first_episode < st.episode_slots)
+                        st.episode_b[(episode - first_episode) * n_envs + i] = eb;
                 }
                 ++episode;
                 begin_episode();
@@ -339,11 +341,11 @@ using namespace cantor;
 
 extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_replay_book* book,
                               const cantor_sim_params* sim, int32_t episode_length, const cantor_policy* policy,
-                              int64_t n_envs, int64_t env_offset, int64_t total_envs, int32_t n_steps,
+                              int64_t n_envs, int64_t env_offset, int64_t total_envs, int64_t first_episode, int32_t n_steps,
                               const cantor_stats_out* stats, const cantor_rollout_out* out, void* stream) {
     CANTOR_REQUIRE(params != nullptr && policy != nullptr, "params/policy is NULL");
     CANTOR_REQUIRE((book != nullptr) != (sim != nullptr), "exactly one of book / sim must be given");
-    CANTOR_REQUIRE(n_envs > 0 && n_steps >= 0 && total_envs >= n_envs && env_offset >= 0, "bad sizes");
+    CANTOR_REQUIRE(n_envs > 0 && n_steps >= 0 && total_envs >= n_envs && env_offset >= 0 && first_episode >= 0, "bad sizes");
     CANTOR_REQUIRE(policy->kind >= CANTOR_POLICY_NO_HEDGE && policy->kind <= CANTOR_POLICY_LSTM, "policy kind");
     CANTOR_REQUIRE((policy->kind != CANTOR_POLICY_MLP && policy->kind != CANTOR_POLICY_LSTM) || policy->mlp != nullptr, "policy.mlp is NULL");
     CANTOR_REQUIRE(policy->kind != CANTOR_POLICY_LSTM || aligned16(policy->mlp), "the LSTM weight image must be 16-byte aligned");
@@ -366,7 +368,8 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
     int rc = make_step_consts(params, T, &k);
     if (rc) return rc;
     CANTOR_REQUIRE(policy->action_squash == CANTOR_SQUASH_CLIP || policy->action_squash == CANTOR_SQUASH_TANH, "policy.action_squash");
-    PolicyConsts pc{policy->kind, policy->put_leg_disabled, policy->action_squash, policy->mlp, (const float2*)policy->actions,
+    const float obs_clip = (policy->obs_clip > 0.f) ? policy->obs_clip : __builtin_inff();      // <= 0 / NaN: no clip
+    PolicyConsts pc{policy->kind, policy->put_leg_disabled, policy->action_squash, obs_clip, policy->mlp, (const float2*)policy->actions,
                     (unsigned)(policy->seed & 0xffffffffull), (unsigned)(policy->seed >> 32)};
     StatsOut so;
     rc = make_stats_out(stats, &so);
@@ -394,7 +397,7 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
             cudaError_t e_ = cudaFuncSetAttribute(rollout_kernel<SRC, MLP, WRITE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e_ != cudaSuccess) return cuda_fail(e_, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");                         \
         }                                                                                                                            \
-        rollout_kernel<SRC, MLP, WRITE><<<grid, MLP == 3 ? lstmtc::kThreads : kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, n_steps, so, ro, tma_ok, share); \
+        rollout_kernel<SRC, MLP, WRITE><<<grid, MLP == 3 ? lstmtc::kThreads : kRollThreads, smem, s>>>(k, b, sk, pc, n_envs, env_offset, total_envs, first_episode, n_steps, so, ro, tma_ok, share); \
     } while (0)
 #define LAUNCH_SRC(SRC)                                                      \
     do {                                                                     \

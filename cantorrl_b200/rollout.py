@@ -206,7 +206,7 @@ class HedgingRollout:
 
     def run(self, n_steps: int, policy: Union[str, torch.Tensor] = "delta_every_step", *, mlp: Optional[torch.Tensor] = None,
             actions: Optional[torch.Tensor] = None, seed: int = 0, stats: Optional[EpisodeStats] = None,
-            store: bool = False, squash: str = "clip") -> RolloutResult:
+            store: bool = False, squash: str = "clip", obs_clip: Optional[float] = None, first_episode: int = 0) -> RolloutResult:
         """``n_steps`` env-steps of every env (auto-reset at episode ends), statistics accumulated into ``stats``.
 
         policy   "no_hedge" | "random" | "delta_every_step" | "delta_benchmark" | "actions" (open loop, ``actions``
@@ -216,6 +216,12 @@ class HedgingRollout:
         store    also write the rollout (obs the policy saw, actions, reward, done), time-major
         squash   network policies: "clip" the action means to [-1, 1] (SB3 stepping the env) or "tanh" (the reference's
                  deployment wrapper, quantconnect/model_wrapper.py:202)
+        obs_clip network policies: clip of the normalised observation.  Default: 10 with squash="clip" (SB3 VecNormalize's
+                 clip_obs, train_ppo_v2.py:204-208) and none with squash="tanh" (quantconnect/model_wrapper.py:131 does not clip)
+        first_episode  episode number every env starts with: the launch plays episodes first_episode, first_episode + 1, ... (global
+                 path ``e * total_envs + g``; the random policy's stream continues likewise).  0 replays the same rollout on
+                 every call; pass the number of episodes already played (``n_steps // T`` per call) to collect fresh data.
+                 Statistics count finished episodes only: a trailing partial episode (``n_steps % T``) runs but is not reported.
         """
         n, dev = self.num_envs, self.device
         pol = _lib.Policy()
@@ -223,6 +229,11 @@ class HedgingRollout:
         if squash not in ("clip", "tanh"):
             raise ValueError("squash must be 'clip' or 'tanh'")
         pol.action_squash = _lib.SQUASH_TANH if squash == "tanh" else _lib.SQUASH_CLIP
+        if obs_clip is None:
+            obs_clip = float("inf") if squash == "tanh" else 10.0
+        pol.obs_clip = float(obs_clip) if obs_clip > 0 else float("inf")
+        if first_episode < 0:
+            raise ValueError("first_episode must be >= 0")
         pol.seed = int(seed) & (2 ** 64 - 1)
         if policy in ("mlp", "mlp_bf16"):
             pol.mlp_tensor_cores = int(policy == "mlp_bf16")
@@ -257,6 +268,6 @@ class HedgingRollout:
             _lib.check(_lib.lib().cantor_rollout(
                 C.byref(self._params), C.byref(self._book) if self._sim is None else None,
                 C.byref(self._sim) if self._sim is not None else None, self.episode_length, C.byref(pol), n,
-                self.env_offset, self.total_envs, int(n_steps), C.byref(st), C.byref(out) if out is not None else None,
+                self.env_offset, self.total_envs, int(first_episode), int(n_steps), C.byref(st), C.byref(out) if out is not None else None,
                 _lib.current_stream_ptr(dev)), "cantor_rollout")
         return res

@@ -54,6 +54,7 @@ class EpisodeStats:
         self._l_hist_sum = torch.zeros(self.hist_bins, dtype=torch.float64, device=dev) if hist_bins > 0 else None
         # fused all-reduce (enable_fused_all_reduce): symmetric "global" block that every rank's kernels add into
         self._g = self._hdl = self._ticket = None
+        self._c = None                              # the cantor_stats_out struct handed to the C ABI (see c_struct)
         self.fused_transport = None
         self.episode_slots = int(episode_slots)
         self.episode_b = (torch.full((self.episode_slots, int(n_envs)), float("nan"), dtype=torch.float32, device=dev)
@@ -116,11 +117,17 @@ class EpisodeStats:
         self._peers = [int(p) for p in hdl.buffer_ptrs]
         self.fused_transport = "multimem" if self._mc else "p2p"
         hdl.barrier(channel=1)                  # every block is zero before anyone adds into it
+        self.c_struct()                         # refresh the struct in place: envs / rollouts holding a pointer to it switch too
         return self.fused_transport
 
     def c_struct(self) -> _lib.StatsOut:
-        st = _lib.StatsOut(self._l_sums.data_ptr(), _lib.ptr(self._l_hist), _lib.ptr(self._l_hist_sum), _lib.ptr(self.episode_b),
-                           self.hist_max, self.hist_bins, 0, self.episode_slots)
+        """The ``cantor_stats_out`` view of these buffers.  ONE struct object per EpisodeStats, refreshed in place: an env that
+        stored a pointer to it at construction (``HedgingVecEnv(stats=...)``) sees a later ``enable_fused_all_reduce``."""
+        if self._c is None:
+            self._c = _lib.StatsOut()
+        st = self._c
+        st.sums, st.hist, st.hist_sum = self._l_sums.data_ptr(), _lib.ptr(self._l_hist), _lib.ptr(self._l_hist_sum)
+        st.episode_b, st.hist_max, st.hist_bins, st.episode_slots = _lib.ptr(self.episode_b), self.hist_max, self.hist_bins, self.episode_slots
         if self._g is not None:
             st.mc_global = self._mc or None
             for r, p in enumerate(self._peers):

@@ -163,7 +163,8 @@ class VecNormalize:
     # --------------------------------------------------------------------------------------- checkpoint / resume
     def state_dict(self):
         return {"rms": self._rms[:32].cpu(), "returns": self.returns.cpu(), "clip_obs": self.clip_obs, "clip_reward": self.clip_reward,
-                "gamma": self.gamma, "epsilon": self.epsilon, "norm_obs": self.norm_obs, "norm_reward": self.norm_reward}
+                "gamma": self.gamma, "epsilon": self.epsilon, "norm_obs": self.norm_obs, "norm_reward": self.norm_reward,
+                "training": self.training}                     # SB3's pickle keeps the training flag too
 
     def load_state_dict(self, sd):
         self._rms[:32].copy_(sd["rms"])
@@ -171,6 +172,7 @@ class VecNormalize:
             self.returns.copy_(sd["returns"])
         for k in ("clip_obs", "clip_reward", "gamma", "epsilon", "norm_obs", "norm_reward"):
             setattr(self, k, sd[k])
+        self.training = bool(sd.get("training", self.training))        # files written before the flag was saved keep the default
 
     def save(self, path):
         """Like ``VecNormalize.save`` (train_ppo_v2.py:315-317, save_vecnormalize=True): statistics only, not the env."""
@@ -192,8 +194,8 @@ class VecNormalize:
             self._rms[:32].copy_(rms)
             return self
         sd = torch.load(path, weights_only=False)
-        self = cls(venv, norm_obs=sd["norm_obs"], norm_reward=sd["norm_reward"], clip_obs=sd["clip_obs"], clip_reward=sd["clip_reward"],
-                   gamma=sd["gamma"], epsilon=sd["epsilon"])
+        self = cls(venv, training=sd.get("training", True), norm_obs=sd["norm_obs"], norm_reward=sd["norm_reward"],
+                   clip_obs=sd["clip_obs"], clip_reward=sd["clip_reward"], gamma=sd["gamma"], epsilon=sd["epsilon"])
         self.load_state_dict(sd)
         return self
 

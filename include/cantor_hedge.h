@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define CANTOR_ABI_VERSION 1
+#define CANTOR_ABI_VERSION 2
 #define CANTOR_OBS_DIM 13            /* hedging_env_v2.py:138-142 */
 
 enum {
@@ -127,6 +127,8 @@ typedef struct cantor_info_out {
                       scaled_float_put, initial_S0_for_episode */
     int32_t* i32;  /* [6 * n_envs]: call_contracts, put_contracts, requested_calls_rounded_clipped,
                       requested_puts_rounded_clipped, actual_calls_traded, actual_puts_traded */
+    float* f32;    /* CANTOR_F32 only, optional: the same 17 keys as float32 [17 * n_envs]; when not NULL the float keys go
+                      here and f64 is not written (92 instead of 160 info bytes per env-step).  Ignored in CANTOR_F64 mode. */
 } cantor_info_out;
 
 /* ---- library ------------------------------------------------------------------------------------ */
@@ -269,13 +271,39 @@ int cantor_env_step(const cantor_env_params* params, const cantor_replay_book* b
                     int32_t auto_reset, const cantor_reset_rule* reset_rule, const cantor_info_out* info,
                     void* stream);
 
-/* n_steps consecutive cantor_env_step calls (auto_reset on, no info) launched back to back from C, for open-loop
- * action sequences / rollout storage: step t reads actions[t] and writes obs[t], reward[t], done[t] of
- * [n_steps, n_envs, ...] buffers.  Same kernel, no Python between launches.  terminal_obs is [n_envs, 13] or NULL. */
+/* n_steps consecutive cantor_env_step calls (auto_reset on, no info) for open-loop action sequences / rollout storage:
+ * step t reads actions[t] and writes obs[t], reward[t], done[t] of [n_steps, n_envs, ...] buffers; results are identical
+ * to n_steps cantor_env_step calls.  Because the action tape is known, the whole call is ONE persistent launch that keeps
+ * the env state in registers (81 + 40 / n_steps algorithmic bytes per env-step instead of 137); CANTOR_STEP_MANY_LAUNCHES=1
+ * in the environment selects n_steps chained launches of the per-step kernel instead.  terminal_obs is [n_envs, 13] or NULL. */
 int cantor_env_step_many(const cantor_env_params* params, const cantor_replay_book* book,
                          const cantor_env_state* state, int64_t n_envs, int32_t precision, int32_t n_steps,
                          const float* actions, float* obs, void* reward, uint8_t* done, float* terminal_obs,
                          const cantor_reset_rule* reset_rule, void* stream);
+
+/* ---- K3, on-the-fly mode: the fused hedge step with the path generated inside the kernel -------------------------
+ * No book in memory: the env carries {S, v} of its current day; each step draws the day's Philox normals (the counters of
+ * cantor_sim_paths), advances the path (src/sim/rbergomi_sim.py:454-464), re-prices the ATM call / put before and after the move
+ * (the pre-advance marks feed the slippage term, hedging_env_v2.py:206-209; the terminal step keeps the stale marks, :226-231)
+ * and runs the same step body as cantor_env_step.  Outputs are bit-identical to cantor_env_step over a book that
+ * cantor_sim_paths wrote with the same parameters.  121 bytes per env-step (SURVEY 8(d) counts 129 with a 24-byte state).
+ * Episode e of global env g (= sim->path_offset + local index) runs global path e * total_envs + g, like cantor_rollout;
+ * state.core[...].path holds the episode number e. */
+typedef struct cantor_env_sim {
+    const cantor_sim_params* sim;   /* dynamics, seed, tenor; sim->path_offset = global index of env 0 of this shard */
+    float* sv;                      /* [n_envs * 2] carried {S, v} (v unclamped), caller-owned state, 8-byte aligned */
+    int64_t total_envs;             /* global env population (>= n_envs) */
+    int32_t episode_length;         /* T */
+    int32_t reserved;
+} cantor_env_sim;
+/* episode [n_envs] = episode number each (masked) env starts, or NULL = 0. */
+int cantor_env_reset_sim(const cantor_env_params* params, const cantor_env_sim* source, const cantor_env_state* state,
+                         int64_t n_envs, int32_t precision, const uint8_t* mask, const int32_t* episode, float* obs,
+                         void* stream);
+/* flags: CANTOR_STEP_* bits.  With auto_reset a finished env continues with its next episode (e + 1). */
+int cantor_env_step_sim(const cantor_env_params* params, const cantor_env_sim* source, const cantor_env_state* state,
+                        int64_t n_envs, int32_t precision, const float* actions, float* obs, void* reward, uint8_t* done,
+                        float* terminal_obs, int32_t auto_reset, const cantor_info_out* info, int32_t flags, void* stream);
 
 /* ---- VecNormalize on the device -------------------------------------------------------------------------------
  * Replaces Stable-Baselines3's VecNormalize as the reference uses it around its env (src/agents/train_ppo_v2.py:204-208,
@@ -321,6 +349,10 @@ typedef struct cantor_policy {
     int32_t mlp_tensor_cores;            /* CANTOR_POLICY_MLP: 0 = float32 FFMA (parity form), 1 = bf16 tcgen05.mma (throughput form) */
     int32_t action_squash;               /* network policies: CANTOR_SQUASH_CLIP = clip the action means to [-1, 1] (what SB3 does with the
                                             Box bounds when it steps the env), CANTOR_SQUASH_TANH = tanh (quantconnect/model_wrapper.py:202) */
+    float obs_clip;                      /* network policies: the normalised observation is clipped to +-obs_clip before the first layer:
+                                            10 = SB3 VecNormalize's clip_obs (train_ppo_v2.py:204-208); +inf (or <= 0) = no clip, which is
+                                            what the deployment wrapper does (quantconnect/model_wrapper.py:131) */
+    int32_t reserved;
 } cantor_policy;
 enum { CANTOR_SQUASH_CLIP = 0, CANTOR_SQUASH_TANH = 1 };
 
@@ -362,10 +394,14 @@ typedef struct cantor_rollout_out {      /* optional rollout storage, time-major
     uint8_t* done;                       /* [n_steps, n_envs] */
 } cantor_rollout_out;
 
-/* Exactly one of book / sim is non-NULL (episode_length is taken from the book when replaying). */
+/* Exactly one of book / sim is non-NULL (episode_length is taken from the book when replaying).
+ * first_episode: episode number the envs start with -- a launch runs episodes first_episode, first_episode + 1, ... of every
+ * env, so consecutive calls (e.g. PPO collection phases) see fresh paths and fresh random actions when the caller advances it by
+ * the number of episodes already played; 0 reproduces the same rollout.  Statistics count finished episodes only: steps of a
+ * trailing partial episode (n_steps % T) run but are not reported. */
 int cantor_rollout(const cantor_env_params* params, const cantor_replay_book* book, const cantor_sim_params* sim,
                    int32_t episode_length, const cantor_policy* policy, int64_t n_envs, int64_t env_offset,
-                   int64_t total_envs, int32_t n_steps, const cantor_stats_out* stats,
+                   int64_t total_envs, int64_t first_episode, int32_t n_steps, const cantor_stats_out* stats,
                    const cantor_rollout_out* out, void* stream);
 
 /* ---- host-buffer face (what a NumPy / SubprocVecEnv-style caller binds) ---------------------------------

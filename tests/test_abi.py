@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_functions():
         assert hasattr(handle, name), f"{name} declared in cantor_hedge.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in cantorrl_b200/_lib.py"
-    assert handle.cantor_abi_version() == 1
+    assert handle.cantor_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
@@ -34,7 +34,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     import subprocess
     from cantorrl_b200 import _lib
     pairs = {"cantor_env_params": _lib.EnvParams, "cantor_replay_book": _lib.ReplayBook, "cantor_env_state": _lib.EnvState,
-             "cantor_reset_rule": _lib.ResetRule, "cantor_info_out": _lib.InfoOut, "cantor_sim_params": _lib.SimParams,
+             "cantor_reset_rule": _lib.ResetRule, "cantor_info_out": _lib.InfoOut, "cantor_env_sim": _lib.EnvSim, "cantor_sim_params": _lib.SimParams,
              "cantor_policy": _lib.Policy, "cantor_stats_out": _lib.StatsOut, "cantor_rollout_out": _lib.RolloutOut, "cantor_rbergomi_params": _lib.RbergomiParams}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cantor_hedge.h"', 'int main(void) {']
     for cname, ct in pairs.items():

@@ -90,3 +90,37 @@ def test_host_env_speaks_the_sb3_vecenv_protocol():
     with pytest.raises(AttributeError):
         env.set_attr("lambda_cost", 2.0)
     env.close()
+
+
+def test_sb3_vecenv_subclass_against_a_stub_base_class():
+    """cantorrl_b200.sb3.cantor_vec_env_class over a stand-in for SB3's VecEnv ABC: instantiable (every abstract method
+    implemented), base-class constructor fed, step = step_async + step_wait, arrays owned by the caller, infos a list."""
+    from cantorrl_b200.host_env import HostVecEnv
+    from cantorrl_b200.sb3 import cantor_vec_env_class
+    from sb3_stub import VecEnv, VecNormalizeLike
+    cls = cantor_vec_env_class(VecEnv)
+    assert issubclass(cls, VecEnv) and issubclass(cls, HostVecEnv)
+    kw = dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3, lambda_cost=1e-4)
+    sim = dict(num_paths=300, n_steps=6, model="gbm", seed=3)
+    venv = cls(num_envs=300, simulate=sim, **kw)
+    plain = HostVecEnv(num_envs=300, simulate=sim, **kw)
+    assert venv.num_envs == 300 and venv.observation_space.shape == (13,) and venv.action_space.shape == (2,)
+    assert venv.get_attr("episode_length") == [6] * 300
+    wrapped = VecNormalizeLike(venv)
+    o0 = venv.reset()
+    np.testing.assert_array_equal(o0, plain.reset())
+    rng = np.random.default_rng(0)
+    kept = []
+    for t in range(14):
+        a = rng.uniform(-1, 1, (300, 2)).astype(np.float32)
+        o, r, d, infos = wrapped.step(a)
+        po, pr, pd, _ = plain.step(a)
+        np.testing.assert_array_equal(o, po)
+        np.testing.assert_array_equal(r, pr)
+        np.testing.assert_array_equal(d, pd)
+        assert bool(d.all()) == ((t + 1) % 6 == 0)
+        kept.append((o, po.copy()))
+    for o, po in kept:                      # returned arrays are the caller's: later steps did not overwrite them
+        np.testing.assert_array_equal(o, po)
+    venv.close()
+    plain.close()
