@@ -40,8 +40,13 @@
 #define CANTOR_OBS_EVICT_FIRST 1      // the env, and must not displace the state / path rows that the next launch re-reads
 #endif                                // (2^20 envs: 21.25 -> 18.05 us per launch; no effect once nothing fits L2: 174 vs 171 us at 2^23).
 #ifndef CANTOR_MANY_MIN_BLOCKS
-#define CANTOR_MANY_MIN_BLOCKS 12     // persistent multi-step kernel: 40 registers, two 6.5 KB observation tiles per CTA
-#endif
+#define CANTOR_MANY_MIN_BLOCKS 10     // persistent multi-step kernel: 48 registers, two 6.5 KB observation tiles per CTA
+#endif                                // (2^20 envs x 252 steps: 8 CTAs / SM 3.94 ms, 10: 3.78 ms, 12: 3.76 ms with spills, 16: 4.85 ms)
+#ifndef CANTOR_MANY_TMA               // 1: the persistent kernel stores its observation tiles with TMA bulk copies like the per-step
+#define CANTOR_MANY_TMA 0             // kernel.  Off: the fence.proxy.async every thread needs before the bulk copy compiles to
+#endif                                // DEPBAR + MEMBAR.ALL.CTA, which waits for the thread's in-flight PREFETCH loads of the next step
+                                      // -- once per step, exposing the DRAM latency the prefetch was there to hide.  Plain 16-byte
+                                      // streaming stores out of the staged tile need only the CTA barrier.
 
 namespace cantor {
 
@@ -461,6 +466,7 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
         }
         // ---- the CTA's observation tile of step s ---------------------------------------------------------------
         float* dst = obs + ((long long)s * n_envs + first_env) * CANTOR_OBS_DIM;
+#if CANTOR_MANY_TMA
         if (use_tma) {
             // the store issued two steps ago read this step's buffer: thread 0 makes sure it has, before the barrier everybody passes
             if (threadIdx.x == 0) tma_store_wait_read();
@@ -474,12 +480,28 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
                 tma_store_1d(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
                 tma_store_commit();
             }
+            continue;
+        }
+#endif
+        __syncthreads();                          // tile s complete; everybody finished copying tile s - 1 (the other buffer) out
+        if (use_tma) {                            // 16-byte aligned tile of whole float4s: coalesced 16-byte streaming stores
+            const float4* src4 = reinterpret_cast<const float4*>(tile);
+            float4* dst4 = reinterpret_cast<float4*>(dst);
+            const int n4 = rows * CANTOR_OBS_DIM / 4;
+#pragma unroll
+            for (int j = threadIdx.x; j < kStepThreads * CANTOR_OBS_DIM / 4; j += kStepThreads) {
+                if (j < n4) {
+                    if (keep_in_l2) dst4[j] = src4[j];
+                    else __stcs(dst4 + j, src4[j]);
+                }
+            }
         } else {
-            __syncthreads();                                                  // tile s complete; tile s - 1 fully copied out by everybody
             for (int j = threadIdx.x; j < rows * CANTOR_OBS_DIM; j += kStepThreads) dst[j] = tile[j];
         }
     }
+#if CANTOR_MANY_TMA
     if (use_tma && threadIdx.x == 0) tma_store_wait_read();                     // shared memory must outlive the last bulk reads
+#endif
     if (live) store_env<F64>(e, core_arr, cash_arr, pv_arr, i);
     if (MON) monitor_epilogue(mon, stat, finished_episode, red, (double)n_envs * (double)n_steps);
 }

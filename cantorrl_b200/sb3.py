@@ -48,6 +48,10 @@ def cantor_vec_env_class(base=None):
         def step_async(self, actions):
             self._actions = np.asarray(actions, np.float32)
 
+        def step(self, actions):                                 # SB3's VecEnv.step; HostVecEnv.step would win the MRO otherwise
+            self.step_async(actions)
+            return self.step_wait()
+
         def step_wait(self):
             obs, reward, done, _ = HostVecEnv.step(self, self._actions)
             infos = _LazyInfos([self._empty] * self.num_envs)

@@ -43,8 +43,13 @@ def uniform_actions(seed, global_env, step):
     return (u * F32(2.0 ** -23) + F32(-1.0)).astype(F32)            # fmaf is exact here (24-bit integer * 2^-23 - 1)
 
 
-def mlp_actor(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8):
-    """float32 actor: clip((obs - mean) / sqrt(var + eps), +-10) -> ReLU(64) -> ReLU(64) -> 2, clipped to [-1, 1].
+def _squash(out, squash):
+    """SB3 clips the action means to the Box when it steps the env; the deployment wrapper applies tanh (model_wrapper.py:202)."""
+    return np.tanh(out).astype(F32) if squash == "tanh" else np.clip(out, -1, 1).astype(F32)
+
+
+def mlp_actor(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8, squash="clip", obs_clip=10.0):
+    """float32 actor: clip((obs - mean) / sqrt(var + eps), +-obs_clip) -> ReLU(64) -> ReLU(64) -> 2, clipped to [-1, 1] (or tanh).
 
     Weights in ``torch.nn.Linear`` layout (``[out, in]``).  Accumulation in float64 then rounded: the CUDA kernel's
     float32 FMA chain agrees to ~1e-6 relative.
@@ -52,11 +57,11 @@ def mlp_actor(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8):
     x = np.asarray(obs, F32)
     if mean is not None:
         inv = (1.0 / np.sqrt(np.asarray(var, np.float64) + epsilon)).astype(F32)
-        x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-10), F32(10))
+        x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-obs_clip), F32(obs_clip))
     h = np.maximum(x.astype(np.float64) @ np.asarray(W1, np.float64).T + b1, 0)
     h = np.maximum(h @ np.asarray(W2, np.float64).T + b2, 0)
     out = h @ np.asarray(W3, np.float64).T + b3
-    return np.clip(out, -1, 1).astype(F32)
+    return _squash(out, squash)
 
 
 def _bf16(x):
@@ -66,17 +71,17 @@ def _bf16(x):
     return r.astype(np.uint32).view(F32)
 
 
-def mlp_actor_bf16(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8):
+def mlp_actor_bf16(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8, squash="clip", obs_clip=10.0):
     """The tensor-core form of ``mlp_actor`` (cantorrl_b200/csrc/mlp_tc.cuh): inputs, weights, biases and hidden
     activations rounded to bfloat16, products accumulated in float32 (float64 here: the order is the hardware's)."""
     x = np.asarray(obs, F32)
     if mean is not None:
         inv = (1.0 / np.sqrt(np.asarray(var, np.float64) + epsilon)).astype(F32)
-        x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-10), F32(10))
+        x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-obs_clip), F32(obs_clip))
     h = _bf16(x).astype(np.float64) @ _bf16(W1).astype(np.float64).T + _bf16(b1)
     h = _bf16(np.maximum(h, 0).astype(F32)).astype(np.float64) @ _bf16(W2).astype(np.float64).T + _bf16(b2)
     out = _bf16(np.maximum(h, 0).astype(F32)).astype(np.float64) @ _bf16(W3).astype(np.float64).T + _bf16(b3)
-    return np.clip(out, -1, 1).astype(F32)
+    return _squash(out, squash)
 
 
 def lstm_actor_sequence(obs_seq, done_seq, w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8,

@@ -346,6 +346,44 @@ def make_lstm_golden():
           f"max |normalised obs| = {worst:.2f}, actions in [{acts.min():.3f}, {acts.max():.3f}]")
 
 
+def make_mlp_golden():
+    """Pins the plain MLP policy (BASELINE configs[4]: 13-64-64-2) on the reference's own network and shipped weights.
+
+    The reference ships no 13-input MLP: its head ``mlp_extractor.policy_net`` (Linear(128, 64) ReLU Linear(64, 64) ReLU) +
+    ``action_net`` (Linear(64, 2)) + tanh (quantconnect/model_wrapper.py:177-185, 202) reads the 128 LSTM outputs.  Following
+    SURVEY section 8(d) (C5), the head is fed from a FIXED 13 -> 128 linear projection P of the normalised observation
+    (seeded, stored in the fixture): actions = tanh(action_net(policy_net(P x))), evaluated by the reference's own
+    ``RecurrentPPOModel`` sub-modules with ``policy_weights.pth`` loaded.  Because P and the first head layer are both linear,
+    this network IS a 13-64-64-2 ReLU MLP with first layer W1 P -- which is what the kernels run.  Observations, normalisation
+    statistics and head weights are those of lstm_golden.npz (same generator conventions)."""
+    import types
+
+    import torch
+    sys.modules.setdefault("AlgorithmImports", types.ModuleType("AlgorithmImports"))
+    mw = _load("ref_model_wrapper", os.path.join(REF, "quantconnect", "model_wrapper.py"))
+    sd = torch.load(os.path.join(REF, "quantconnect", "model_files", "policy_weights.pth"), map_location="cpu", weights_only=False)
+    model = mw.RecurrentPPOModel()
+    ours = {"lstm_actor." + k: sd["lstm_actor." + k] for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")}
+    for j in (0, 2):
+        for kind in ("weight", "bias"):
+            ours[f"mlp_extractor_policy_net.{j}.{kind}"] = sd[f"mlp_extractor.policy_net.{j}.{kind}"]
+    ours["action_net.weight"], ours["action_net.bias"], ours["log_std"] = sd["action_net.weight"], sd["action_net.bias"], sd["log_std"]
+    model.load_state_dict(ours)
+    model.eval()
+    g = np.load(os.path.join(HERE, "lstm_golden.npz"))
+    obs = g["obs"].reshape(-1, 13)                                                             # 320 observations of the reference env
+    mean, var = g["obs_mean"].astype(np.float64), g["obs_var"].astype(np.float64)
+    P = (0.3 * np.random.default_rng(128).standard_normal((128, 13)) / np.sqrt(13)).astype(np.float32)   # keeps most actions off the tanh plateaus
+    x = ((obs - mean) / np.sqrt(var + 1e-8)).astype(np.float32)                                # model_wrapper.py:131
+    with torch.no_grad():
+        feats = model.mlp_extractor_policy_net(torch.as_tensor(x @ P.T))
+        means = model.action_net(feats)
+        acts = torch.tanh(means).numpy()                                                       # model_wrapper.py:202
+    np.savez_compressed(os.path.join(HERE, "mlp_golden.npz"), obs=obs, projection=P, action_means=means.numpy(), actions=acts)
+    print(f"mlp_golden: {obs.shape[0]} observations through the reference's shipped head behind a fixed 13->128 projection; "
+          f"actions in [{acts.min():.3f}, {acts.max():.3f}], std {acts.std():.3f}")
+
+
 def make_calibration_golden():
     """estimate_base_params (rbergomi_sim.py:171-193) of the unmodified reference on the shipped price history and on
     synthetic histories of several lengths (short ones exercise the default / guard branches)."""
@@ -391,6 +429,9 @@ if __name__ == "__main__":
     if "--lstm-only" in sys.argv:
         make_lstm_golden()
         sys.exit(0)
+    if "--mlp-only" in sys.argv:
+        make_mlp_golden()
+        sys.exit(0)
     if "--policy-only" in sys.argv:
         make_policy_golden()
         sys.exit(0)
@@ -401,3 +442,4 @@ if __name__ == "__main__":
     make_rbergomi_golden()
     make_calibration_golden()
     make_lstm_golden()
+    make_mlp_golden()

@@ -138,3 +138,29 @@ def test_shipped_sb3_vecnormalize_pickle_is_readable_without_sb3_and_confirms_th
             pickle.dump(os.path.join, f)
             f.flush()
             read_sb3_vecnormalize(f.name)
+
+
+def _shipped_mlp():
+    """The plain 13-64-64-2 MLP built from the reference's shipped head behind the fixture's fixed 13 -> 128 projection."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mlp_golden.npz"))
+    l = np.load(os.path.join(ROOT, "tests", "golden", "lstm_golden.npz"))
+    W1 = (l["W1"].astype(np.float64) @ g["projection"].astype(np.float64)).astype(np.float32)          # Linear(128, 64) o P
+    return g, dict(W1=W1, b1=l["b1"], W2=l["W2"], b2=l["b2"], W3=l["W3"], b3=l["b3"]), l["obs_mean"], l["obs_var"]
+
+
+def test_plain_mlp_oracle_reproduces_the_reference_head_on_the_shipped_weights():
+    """oracle/rollout_oracle.mlp_actor against tests/golden/mlp_golden.npz: the reference's own mlp_extractor.policy_net +
+    action_net + tanh (quantconnect/model_wrapper.py:177-185, 202) with policy_weights.pth, fed from a fixed 13 -> 128 projection
+    of the normalised observation (:131) -- BASELINE configs[4]'s MLP, no longer 'parity unpinned'
+    (generator: tests/golden/make_golden.py --mlp-only)."""
+    from oracle import rollout_oracle
+    g, w, mean, var = _shipped_mlp()
+    got = rollout_oracle.mlp_actor(g["obs"], **w, mean=mean, var=var, squash="tanh", obs_clip=np.inf)
+    np.testing.assert_allclose(got, g["actions"], rtol=0, atol=3e-6)           # float32 torch (two matmuls) vs float64 NumPy (one)
+    assert (np.abs(g["actions"]) > 0.99).mean() < 0.05 and g["actions"].std() > 0.3
+    q = rollout_oracle.mlp_actor_bf16(g["obs"], **w, mean=mean, var=var, squash="tanh", obs_clip=np.inf)
+    assert np.abs(q - g["actions"]).max() < 2e-2 and np.abs(q - g["actions"]).mean() < 3e-3
+    # SB3's own conventions (clip the means to the Box, clip the normalised observation at 10) differ where they should
+    c = rollout_oracle.mlp_actor(g["obs"], **w, mean=mean, var=var)
+    big = np.abs(g["action_means"]) < 0.3
+    np.testing.assert_allclose(c[big], g["action_means"][big], atol=3e-6)

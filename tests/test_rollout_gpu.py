@@ -264,3 +264,34 @@ def test_config2_size_heston_16m_paths_replay_equals_on_the_fly():
     torch.cuda.synchronize()
     assert float(st.sums[0]) == n and float(st.sums[11]) == float(n) * T
     assert torch.allclose(st.sums[:12], replayed, rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("policy,tol_max,tol_mean", [("mlp", 2e-5, 2e-6), ("mlp_bf16", 3e-2, 3e-3)])
+def test_plain_mlp_policy_with_the_shipped_head_weights(policy, tol_max, tol_mean):
+    """BASELINE configs[4]'s MLP 13-64-64-2 pinned on the reference: the shipped mlp_extractor.policy_net / action_net tensors
+    behind the fixed 13 -> 128 projection of tests/golden/mlp_golden.npz (the oracle network reproduces the reference's own
+    modules on it to 3e-6, tests/test_oracle_policy.py), tanh squash and no observation clip like the deployment wrapper
+    (quantconnect/model_wrapper.py:131, 202), run inside the rollout kernel and compared on the kernel's own observations."""
+    from cantorrl_b200.rollout import HedgingRollout, pack_mlp
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g, l = np.load(os.path.join(here, "mlp_golden.npz")), np.load(os.path.join(here, "lstm_golden.npz"))
+    W1 = (l["W1"].astype(np.float64) @ g["projection"].astype(np.float64)).astype(np.float32)
+    w = dict(W1=W1, b1=l["b1"], W2=l["W2"], b2=l["b2"], W3=l["W3"], b3=l["b3"])
+    n_paths, T, n_envs, n_steps = 61, 16, 300, 40
+    S, V, C, P = _book(n_paths, T, heston=True)
+    ro = HedgingRollout(data=dict(paths=S, volatilities=V, call_prices_atm=C, put_prices_atm=P), num_envs=n_envs, **KW)
+    stats = ro.new_stats()
+    res = ro.run(n_steps, policy, mlp=pack_mlp(**w, obs_mean=l["obs_mean"], obs_var=l["obs_var"]), stats=stats, store=True, squash="tanh")
+    torch.cuda.synchronize()
+    assert float(stats.sums[15]) == 0.0, "a tcgen05 MMA timed out"
+    obs, act = res.obs.cpu().numpy(), res.actions.cpu().numpy()
+    fn = rollout_oracle.mlp_actor_bf16 if policy == "mlp_bf16" else rollout_oracle.mlp_actor
+    want = fn(obs.reshape(-1, 13), **w, mean=l["obs_mean"], var=l["obs_var"], squash="tanh", obs_clip=np.inf).reshape(act.shape)
+    err = np.abs(act - want)
+    assert err.max() < tol_max and err.mean() < tol_mean, (err.max(), err.mean())
+    full = rollout_oracle.mlp_actor(obs.reshape(-1, 13), **w, mean=l["obs_mean"], var=l["obs_var"], squash="tanh", obs_clip=np.inf).reshape(act.shape)
+    assert np.abs(act - full).mean() < 1e-2 and act.std() > 0.05
+    # with SB3's conventions (default squash="clip": Box clip + observation clip at 10) the same weights give clipped means
+    res2 = ro.run(n_steps, policy, mlp=pack_mlp(**w, obs_mean=l["obs_mean"], obs_var=l["obs_var"]), store=True)
+    want2 = fn(res2.obs.cpu().numpy().reshape(-1, 13), **w, mean=l["obs_mean"], var=l["obs_var"]).reshape(act.shape)
+    assert np.abs(res2.actions.cpu().numpy() - want2).max() < max(tol_max, 5e-5) * 3
