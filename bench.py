@@ -709,7 +709,8 @@ def main():
             mult = kw.pop("n_mult", 1)
             l2free[name] = ring_step_bench(L, dev, stream, big * mult, T, peak=peak, **kw)
             torch.cuda.empty_cache()
-        for name, kernel in (("per_step_replay_fp32", "hedge_step_kernel<F64=false,INFO=false>@2^23"),):
+        for name, kernel in (("per_step_replay_fp32", "hedge_step_kernel<F64=false,INFO=false>@2^23"),
+                             ("per_step_on_the_fly_gbm_fp32", "hedge_step_sim_kernel<gbm,F64=false>@2^23")):
             tr, per_env = _traffic(kernel)
             if per_env is not None and name in l2free:
                 l2free[name]["dram_traffic_bytes_per_env_step"] = per_env

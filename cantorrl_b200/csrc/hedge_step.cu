@@ -43,14 +43,18 @@
 #define CANTOR_MANY_MIN_BLOCKS 10     // persistent multi-step kernel: 48 registers, two 6.5 KB observation tiles per CTA
 #endif                                // (2^20 envs x 252 steps: 8 CTAs / SM 3.94 ms, 10: 3.78 ms, 12: 3.76 ms with spills, 16: 4.85 ms)
 #ifndef CANTOR_MANY_TMA               // 1: the persistent kernel stores its observation tiles with TMA bulk copies like the per-step
-#define CANTOR_MANY_TMA 0             // kernel.  Off: the fence.proxy.async every thread needs before the bulk copy compiles to
-#endif                                // DEPBAR + MEMBAR.ALL.CTA, which waits for the thread's in-flight PREFETCH loads of the next step
-                                      // -- once per step, exposing the DRAM latency the prefetch was there to hide.  Plain 16-byte
-                                      // streaming stores out of the staged tile need only the CTA barrier.
+#define CANTOR_MANY_TMA 1             // kernel; 0: plain 16-byte streaming stores out of the staged tile.  The fence.proxy.async before a
+#endif                                // bulk copy compiles to DEPBAR + MEMBAR.ALL.CTA and so waits for the thread's in-flight prefetch
+                                      // loads once per step -- yet measured (2^20 envs x 252 steps) TMA 3.755 ms, plain stores 3.862 ms.
+
+#ifndef CANTOR_MANY_THREADS
+#define CANTOR_MANY_THREADS 128       // envs per CTA of the persistent kernel
+#endif
 
 namespace cantor {
 
 constexpr int kStepThreads = CANTOR_STEP_THREADS;
+constexpr int kManyThreads = CANTOR_MANY_THREADS;
 
 struct ResetRule {
     int mode;
@@ -325,12 +329,13 @@ __device__ __forceinline__ void write_terminal_obs(float* __restrict__ terminal_
 // MON epilogue: finished episodes -> statistics vector (warp shuffle -> shared -> one atomic per statistic per CTA, only
 // when some env of this CTA finished: block-uniform vote, so the barrier inside is safe), the env-step counter, and the
 // fused all-reduce of the statistics (last CTA of the launch; no-op unless a ticket is attached).
+template <int THREADS>
 __device__ __forceinline__ void monitor_epilogue(const Monitor& mon, double (&stat)[11], bool finished_episode, double* red,
                                                  double env_steps) {
     if (mon.stats.sums == nullptr) return;
-    if (__syncthreads_or(finished_episode)) block_accumulate<11, kStepThreads>(stat, mon.stats.sums, red);
+    if (__syncthreads_or(finished_episode)) block_accumulate<11, THREADS>(stat, mon.stats.sums, red);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(mon.stats.sums + 11, env_steps);
-    push_statistics_to_all_ranks<kStepThreads>(mon.stats);
+    push_statistics_to_all_ranks<THREADS>(mon.stats);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -390,7 +395,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
-    if (MON) monitor_epilogue(mon, stat, finished_episode, red, (double)n_envs);
+    if (MON) monitor_epilogue<kStepThreads>(mon, stat, finished_episode, red, (double)n_envs);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -398,23 +403,23 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
 // the thread reads its action and ONE new path record (both requested a step ahead) and the CTA writes one observation tile
 // (double-buffered in shared memory: the TMA store of step s drains while step s + 1 computes), 128 rewards and 128 dones.
 template <bool F64, bool MON>
-__global__ void __launch_bounds__(kStepThreads, (MON || F64) ? 6 : CANTOR_MANY_MIN_BLOCKS)
+__global__ void __launch_bounds__(kManyThreads, (MON || F64) ? (6 * 128 / kManyThreads) : (CANTOR_MANY_MIN_BLOCKS * 128 / kManyThreads))
 hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                        double* __restrict__ pv_arr, long long n_envs, int n_steps, const float2* __restrict__ actions,
                        float* __restrict__ obs, void* __restrict__ reward_arr, unsigned char* __restrict__ done_arr,
                        float* __restrict__ terminal_obs, const ResetRule rr, int obs_tma_ok, const Monitor mon) {
-    __shared__ __align__(128) float tiles[2][kStepThreads * CANTOR_OBS_DIM];
-    __shared__ double red[MON ? 11 * (kStepThreads / 32) : 1];
+    __shared__ __align__(128) float tiles[2][kManyThreads * CANTOR_OBS_DIM];
+    __shared__ double red[MON ? 11 * (kManyThreads / 32) : 1];
     double stat[11];
     bool finished_episode = false;
     if (MON) {
 #pragma unroll
         for (int s = 0; s < 11; ++s) stat[s] = 0.0;
     }
-    const long long first_env = (long long)blockIdx.x * kStepThreads;
+    const long long first_env = (long long)blockIdx.x * kManyThreads;
     const long long i = first_env + threadIdx.x;
     const bool live = i < n_envs;
-    const int rows = (int)min((long long)kStepThreads, n_envs - first_env);
+    const int rows = (int)min((long long)kManyThreads, n_envs - first_env);
     const bool use_tma = (obs_tma_ok & 1) && (rows % 4 == 0) && ((n_envs & 3) == 0);   // every step's tile 16-byte aligned
     const bool keep_in_l2 = (obs_tma_ok & 2) != 0;
     const size_t rb = F64 ? sizeof(double) : sizeof(float);
@@ -489,21 +494,21 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
             float4* dst4 = reinterpret_cast<float4*>(dst);
             const int n4 = rows * CANTOR_OBS_DIM / 4;
 #pragma unroll
-            for (int j = threadIdx.x; j < kStepThreads * CANTOR_OBS_DIM / 4; j += kStepThreads) {
+            for (int j = threadIdx.x; j < kManyThreads * CANTOR_OBS_DIM / 4; j += kManyThreads) {
                 if (j < n4) {
                     if (keep_in_l2) dst4[j] = src4[j];
                     else __stcs(dst4 + j, src4[j]);
                 }
             }
         } else {
-            for (int j = threadIdx.x; j < rows * CANTOR_OBS_DIM; j += kStepThreads) dst[j] = tile[j];
+            for (int j = threadIdx.x; j < rows * CANTOR_OBS_DIM; j += kManyThreads) dst[j] = tile[j];
         }
     }
 #if CANTOR_MANY_TMA
     if (use_tma && threadIdx.x == 0) tma_store_wait_read();                     // shared memory must outlive the last bulk reads
 #endif
     if (live) store_env<F64>(e, core_arr, cash_arr, pv_arr, i);
-    if (MON) monitor_epilogue(mon, stat, finished_episode, red, (double)n_envs * (double)n_steps);
+    if (MON) monitor_epilogue<kManyThreads>(mon, stat, finished_episode, red, (double)n_envs * (double)n_steps);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -628,7 +633,7 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
-    if (MON) monitor_epilogue(mon, stat, finished_episode, red, (double)n_envs);
+    if (MON) monitor_epilogue<kStepThreads>(mon, stat, finished_episode, red, (double)n_envs);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -830,7 +835,8 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
         const void* fn = precision == CANTOR_F64
             ? (mon_on ? (const void*)hedge_step_many_kernel<true, true> : (const void*)hedge_step_many_kernel<true, false>)
             : (mon_on ? (const void*)hedge_step_many_kernel<false, true> : (const void*)hedge_step_many_kernel<false, false>);
-        return launch_pdl(fn, dim3(grid), dim3(kStepThreads), s, args);
+        const unsigned grid_many = (unsigned)((n_envs + kManyThreads - 1) / kManyThreads);
+        return launch_pdl(fn, dim3(grid_many), dim3(kManyThreads), s, args);
     }
     for (int32_t t = 0; t < n_steps; ++t) {
         // step t of a rollout writes slab t of the caller's [n_steps, n_envs, ...] buffers

@@ -195,6 +195,8 @@ class HedgingVecEnv:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.CantorError("HedgingVecEnv runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:                # "cuda" -> "cuda:<current>": tensors report an indexed device
+            self.device = torch.device("cuda", torch.cuda.current_device())
 
         # -- data (hedging_env_v2.py:36-51), or no data at all: the on-the-fly mode generates each day inside the step kernel ------
         self.simulate = None

@@ -85,13 +85,14 @@ def mlp_actor_bf16(obs, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-
 
 
 def lstm_actor_sequence(obs_seq, done_seq, w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b2, W3, b3, mean=None, var=None, epsilon=1e-8,
-                        bf16=True, squash="clip"):
+                        bf16=True, squash="clip", obs_clip=10.0):
     """The recurrent actor LSTM(13 -> 128) -> ReLU MLP(128 -> 64 -> 64) -> 2 (quantconnect/model_wrapper.py:167-204) over an
     observation sequence ``[n_steps, n_envs, 13]``; the state (h, c) of an env is zeroed after a step on which it finished
     (``done_seq [n_steps, n_envs]``), as SB3 does at episode starts.  ``torch.nn.LSTM`` weight layout, gate order i, f, g, o.
 
     ``squash``: "clip" (SB3 clips the action means to the Box when it steps the env) or "tanh" (the reference's deployment
-    wrapper, quantconnect/model_wrapper.py:202).  Pinned: with ``bf16=False, squash="tanh"`` this reproduces the reference's
+    wrapper, quantconnect/model_wrapper.py:202).  ``obs_clip``: SB3 VecNormalize's clip of the normalised observation (10); the
+    deployment wrapper does not clip (:131) -- pass ``np.inf``.  Pinned: with ``bf16=False, squash="tanh"`` this reproduces the reference's
     own ``RecurrentPPOModel`` run on the shipped ``policy_weights.pth`` (tests/golden/lstm_golden.npz, tests/test_oracle_policy.py).
     ``bf16=True`` follows the rounding points of cantorrl_b200/csrc/lstm_tc.cuh (inputs, weights, biases, h and the head's
     activations in bfloat16; products accumulated wide; c in float32); ``bf16=False`` is the plain float64 network.
@@ -110,7 +111,7 @@ def lstm_actor_sequence(obs_seq, done_seq, w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b
         x = np.asarray(obs_seq[t], F32)
         if mean is not None:
             inv = (1.0 / np.sqrt(np.asarray(var, np.float64) + epsilon)).astype(F32)
-            x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-10), F32(10))
+            x = np.clip((x - np.asarray(mean, F32)) * inv, F32(-obs_clip), F32(obs_clip))
         g = q(x).astype(np.float64) @ wi.T + q(h.astype(F32)).astype(np.float64) @ wh.T + bb
         gi, gf, gg, go = g[:, 0:128], g[:, 128:256], g[:, 256:384], g[:, 384:512]
         c = (sig(gf) * c + sig(gi) * np.tanh(gg)).astype(F32).astype(np.float64) if bf16 else sig(gf) * c + sig(gi) * np.tanh(gg)

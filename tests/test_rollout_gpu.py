@@ -230,10 +230,13 @@ def test_recurrent_policy_with_the_shipped_weights_and_tanh_squash():
     ref = rollout_oracle.run_rollout(S, V, C, P, EnvParams(**KW), "actions", n_envs, n_steps, forced_actions=got["actions"])
     assert np.array_equal(got["done"], ref["done"])
     np.testing.assert_allclose(got["obs"], ref["obs"], rtol=1e-4, atol=2e-6)
-    want = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=True, squash="tanh")
+    # squash="tanh" is the deployment wrapper's convention, which does not clip the normalised observation (model_wrapper.py:131)
+    want = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=True, squash="tanh",
+                                              obs_clip=np.inf)
     err = np.abs(got["actions"] - want)
     assert err.max() < 2e-2 and err.mean() < 1e-3, (err.max(), err.mean())
-    full = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=False, squash="tanh")
+    full = rollout_oracle.lstm_actor_sequence(got["obs"], got["done"], **w, mean=g["obs_mean"], var=g["obs_var"], bf16=False, squash="tanh",
+                                              obs_clip=np.inf)
     assert np.abs(got["actions"] - full).mean() < 2e-2
     assert np.abs(got["actions"]).max() <= 1.0 and got["actions"].std() > 0.05
 
