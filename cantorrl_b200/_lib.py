@@ -49,9 +49,14 @@ class ReplayBook(C.Structure):
     _fields_ = [("svcp", C.c_void_p), ("ld", C.c_int64), ("n_paths", C.c_int32), ("episode_length", C.c_int32)]
 
 
+class VecNormFuse(C.Structure):
+    _fields_ = [("partial", C.c_void_p), ("returns", C.c_void_p), ("gamma", C.c_double), ("n_partial_ctas", C.c_int64),
+                ("norm_obs", C.c_int32), ("norm_reward", C.c_int32)]
+
+
 class EnvState(C.Structure):
     _fields_ = [("core", C.c_void_p), ("cash", C.c_void_p), ("pv_prev", C.c_void_p), ("episode_acc", C.c_void_p),
-                ("episode_return", C.c_void_p), ("episode_length", C.c_void_p), ("stats", C.c_void_p)]
+                ("episode_return", C.c_void_p), ("episode_length", C.c_void_p), ("stats", C.c_void_p), ("vecnorm", C.c_void_p)]
 
 
 class ResetRule(C.Structure):
@@ -147,6 +152,8 @@ SIGNATURES = {
     "cantor_vecnorm_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_void_p]),
+    "cantor_vecnorm_step_fused": (C.c_int, [C.c_void_p, C.POINTER(VecNormFuse), C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                            C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]),
     "cantor_rollout": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(SimParams), C.c_int32,
                                  C.POINTER(Policy), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(StatsOut),
                                  C.POINTER(RolloutOut), C.c_void_p]),

@@ -47,6 +47,9 @@
 #endif                                // bulk copy compiles to DEPBAR + MEMBAR.ALL.CTA and so waits for the thread's in-flight prefetch
                                       // loads once per step -- yet measured (2^20 envs x 252 steps) TMA 3.755 ms, plain stores 3.862 ms.
 
+#ifndef CANTOR_MANY_EVICT_FIRST       // L2 policy of the persistent kernel's observation stores.  Nothing it touches is ever re-read, so there
+#define CANTOR_MANY_EVICT_FIRST 0     // is nothing to protect in L2: the plain policy measured 3.689 ms against 3.771 ms with evict-first
+#endif                                // (2^20 envs x 252 steps) -- evict-first lines leave L2 in smaller, less DRAM-friendly batches.
 #ifndef CANTOR_MANY_THREADS
 #define CANTOR_MANY_THREADS 128       // envs per CTA of the persistent kernel
 #endif
@@ -77,6 +80,72 @@ struct Monitor {
     int* episode_length;       // [n]
     StatsOut stats;            // stats.sums == NULL: no reduction
 };
+
+// Optional VecNormalize fusion (cantor_env_state.vecnorm): the step kernel also produces what cantor_vecnorm_step's moments
+// kernel would have to re-read the batch for -- per-CTA partial sums of the observation columns (sum, sum of squares: 26 values)
+// and of the updated discounted returns (2 values), written with plain stores to partial[statistic][CTA] and folded later
+// in a fixed order (cantor_vecnorm_step_fused), so the running statistics stay bitwise reproducible.
+struct VecNormFuse {
+    double* partial;           // [28, n_cta] (NULL = off)
+    double* returns;           // [n] discounted returns, updated in place: ret <- ret * gamma + reward
+    double gamma;
+    int norm_obs, norm_reward;
+};
+constexpr int kVnFuseSums = 2 * CANTOR_OBS_DIM + 2;
+
+// Called by every thread of the CTA after the observation tile is complete and a CTA barrier has been passed.
+// `reward` = this thread's raw reward of the step (ignored for threads without an env).
+template <int THREADS>
+__device__ __forceinline__ void vecnorm_partials(const VecNormFuse& vn, const float* tile, int rows, bool live, long long i,
+                                                 double reward, double* scratch /* [2 * 8 * 13 + 2 * THREADS / 32] */) {
+    constexpr int C = CANTOR_OBS_DIM, PARTS = 8;
+    double* part = scratch;                            // [2][PARTS][C]
+    double* wsum = scratch + 2 * PARTS * C;            // [2][THREADS / 32]
+    const int n_cta = (int)gridDim.x;
+    if (vn.norm_obs && threadIdx.x < PARTS * C) {      // (part v, column c): rows v, v + 8, ... in a fixed order
+        const int v = threadIdx.x / C, c = threadIdx.x % C;
+        double a = 0.0, q = 0.0;
+        for (int r = v; r < rows; r += PARTS) {
+            const double x = (double)tile[r * C + c];
+            a += x;
+            q = fma(x, x, q);
+        }
+        part[v * C + c] = a;
+        part[(PARTS + v) * C + c] = q;
+    }
+    double rs = 0.0, rq = 0.0;
+    if (vn.norm_reward && live) {
+        const double ret = fma(vn.returns[i], vn.gamma, reward);
+        vn.returns[i] = ret;
+        rs = ret;
+        rq = ret * ret;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        rs += __shfl_down_sync(0xffffffffu, rs, off);
+        rq += __shfl_down_sync(0xffffffffu, rq, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        wsum[threadIdx.x >> 5] = rs;
+        wsum[THREADS / 32 + (threadIdx.x >> 5)] = rq;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * C) {                         // column sums: the 8 parts in order
+        const int kind = threadIdx.x / C, c = threadIdx.x % C;
+        double a = 0.0;
+        if (vn.norm_obs) {
+#pragma unroll
+            for (int v = 0; v < PARTS; ++v) a += part[(kind * PARTS + v) * C + c];
+        }
+        vn.partial[(long long)threadIdx.x * n_cta + blockIdx.x] = a;
+    } else if (threadIdx.x < 2 * C + 2) {              // returns: the warps in order
+        const int kind = threadIdx.x - 2 * C;
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w) a += wsum[kind * (THREADS / 32) + w];
+        vn.partial[(long long)threadIdx.x * n_cta + blockIdx.x] = a;
+    }
+}
 
 // The env state of one thread, in registers.  `path` is the replay path index (replay mode) or the episode number (on the fly).
 struct EnvRegs {
@@ -159,7 +228,7 @@ template <bool F64, bool INFO, bool MON, bool SHARE>
 __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const float2 a, const float4& prev, const float4& cur,
                                           const Greeks& g_cur, float* __restrict__ o, long long i, long long n_envs,
                                           void* __restrict__ reward_slot, const InfoOut& info, const Monitor& mon,
-                                          double (&stat)[11], bool& finished_episode) {
+                                          double (&stat)[11], bool& finished_episode, double* reward_out = nullptr) {
     const int pos_c = e.pos_c, pos_p = e.pos_p;
     const bool already_done = e.step >= k.T;                                  // only reachable with auto_reset = 0
     const int t_prev = already_done ? k.T - 1 : e.step;
@@ -216,6 +285,7 @@ __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const
             e.pv_prev = pv;
         }
         __stcs(reinterpret_cast<double*>(reward_slot), reward);
+        if (reward_out != nullptr) *reward_out = reward;
         if (MON && !already_done) {
             double2* ap = reinterpret_cast<double2*>(mon.acc) + 2 * i;
             double2 a0 = ap[0], a1 = ap[1];                                   // {reward, pps}, {|pps|, cost}
@@ -259,6 +329,7 @@ __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const
         }
         if (!already_done) e.cash_f = cash_new;
         __stcs(reinterpret_cast<float*>(reward_slot), reward);
+        if (reward_out != nullptr) *reward_out = (double)reward;
         if (MON && !already_done) {
             float4* ap = reinterpret_cast<float4*>(mon.acc) + i;
             float4 m = *ap;                                                   // {reward, pps, |pps|, cost}
@@ -340,15 +411,17 @@ __device__ __forceinline__ void monitor_epilogue(const Monitor& mon, double (&st
 
 // ---------------------------------------------------------------------------------------------------
 // Gym-style step, replay mode: one launch = one env-step.
-template <bool F64, bool INFO, bool MON>
-__global__ void __launch_bounds__(kStepThreads, (MON || INFO || F64) ? 8 : CANTOR_STEP_MIN_BLOCKS)
+template <bool F64, bool INFO, bool MON, bool VN>
+__global__ void __launch_bounds__(kStepThreads, (MON || INFO || F64 || VN) ? 8 : CANTOR_STEP_MIN_BLOCKS)
 hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                   double* __restrict__ pv_arr, long long n_envs, const float2* __restrict__ actions,
                   float* __restrict__ obs, void* __restrict__ reward_arr, unsigned char* __restrict__ done_arr,
                   float* __restrict__ terminal_obs, int auto_reset, const ResetRule rr, const InfoOut info,
-                  int obs_tma_ok, const Monitor mon) {
+                  int obs_tma_ok, const Monitor mon, const VecNormFuse vn) {
     __shared__ __align__(128) float tile[kStepThreads * CANTOR_OBS_DIM];
     __shared__ double red[MON ? 11 * (kStepThreads / 32) : 1];
+    __shared__ double vn_scratch[VN ? 2 * 8 * CANTOR_OBS_DIM + 2 * (kStepThreads / 32) : 1];
+    double my_reward = 0.0;
     double stat[11];
     bool finished_episode = false;                                            // MON: this thread's env just ended an episode
     if (MON) {
@@ -376,7 +449,8 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         const Greeks none{0.f, 0.f, 0.f};
         const size_t rb = F64 ? sizeof(double) : sizeof(float);
         const bool terminated = step_body<F64, INFO, MON, false>(k, e, a, prev, cur, none, o, i, n_envs,
-                                                                 (char*)reward_arr + i * rb, info, mon, stat, finished_episode);
+                                                                 (char*)reward_arr + i * rb, info, mon, stat, finished_episode,
+                                                                 VN ? &my_reward : nullptr);
 #if CANTOR_STEP_PREFETCH
         // the next step of this env reads rows `step` (just read: L2-resident) and `step + 1` (new): start that DRAM read now
         if (!terminated) prefetch_l2(rp + 2 * b.ld);
@@ -395,6 +469,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
+    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, vn_scratch);
     if (MON) monitor_epilogue<kStepThreads>(mon, stat, finished_episode, red, (double)n_envs);
 }
 
@@ -478,7 +553,7 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
             fence_proxy_async_smem();
             __syncthreads();
             if (threadIdx.x == 0) {
-#if CANTOR_OBS_EVICT_FIRST
+#if CANTOR_MANY_EVICT_FIRST
                 if (!keep_in_l2) tma_store_1d_evict_first(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
                 else
 #endif
@@ -548,15 +623,17 @@ __device__ __forceinline__ float4 sim_first_record(const SimConsts& sk, Greeks& 
     return r0;
 }
 
-template <int MODEL, bool F64, bool INFO, bool MON>
+template <int MODEL, bool F64, bool INFO, bool MON, bool VN>
 __global__ void __launch_bounds__(kStepThreads, 8)
 hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource src, int4* __restrict__ core_arr,
                       void* __restrict__ cash_arr, double* __restrict__ pv_arr, long long n_envs,
                       const float2* __restrict__ actions, float* __restrict__ obs, void* __restrict__ reward_arr,
                       unsigned char* __restrict__ done_arr, float* __restrict__ terminal_obs, int auto_reset,
-                      const InfoOut info, int obs_tma_ok, int share_quote, const Monitor mon) {
+                      const InfoOut info, int obs_tma_ok, int share_quote, const Monitor mon, const VecNormFuse vn) {
     __shared__ __align__(128) float tile[kStepThreads * CANTOR_OBS_DIM];
     __shared__ double red[MON ? 11 * (kStepThreads / 32) : 1];
+    __shared__ double vn_scratch[VN ? 2 * 8 * CANTOR_OBS_DIM + 2 * (kStepThreads / 32) : 1];
+    double my_reward = 0.0;
     double stat[11];
     bool finished_episode = false;
     if (MON) {
@@ -610,10 +687,10 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
         bool terminated;
         if (!F64 && share_quote)
             terminated = step_body<F64, INFO, MON, true>(k, e, a, prev, cur, g_cur, o, i, n_envs, (char*)reward_arr + i * rb, info,
-                                                         mon, stat, finished_episode);
+                                                         mon, stat, finished_episode, VN ? &my_reward : nullptr);
         else
             terminated = step_body<F64, INFO, MON, false>(k, e, a, prev, cur, g_cur, o, i, n_envs, (char*)reward_arr + i * rb, info,
-                                                          mon, stat, finished_episode);
+                                                          mon, stat, finished_episode, VN ? &my_reward : nullptr);
         if (!terminated || auto_reset) sv = make_float2(S, v);                // a finished env without auto-reset stays at day T - 1
         if (terminated) {
             if (terminal_obs != nullptr) write_terminal_obs(terminal_obs, i, o);
@@ -633,6 +710,7 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
+    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, vn_scratch);
     if (MON) monitor_epilogue<kStepThreads>(mon, stat, finished_episode, red, (double)n_envs);
 }
 
@@ -708,6 +786,18 @@ static int make_info(const cantor_info_out* info, int precision, InfoOut* io) {
 static int make_monitor(const cantor_env_state* state, Monitor* mon) {
     *mon = Monitor{state->episode_acc, state->episode_return, state->episode_length, {}};
     return make_stats_out(state->episode_acc ? state->stats : nullptr, &mon->stats);
+}
+
+// state->vecnorm: fused VecNormalize moments (INFO must be off: the info path keeps the two-kernel cantor_vecnorm_step).
+static int make_vecnorm(const cantor_env_state* state, bool info_on, int64_t n_envs, VecNormFuse* vn) {
+    *vn = VecNormFuse{nullptr, nullptr, 0.0, 0, 0};
+    const cantor_vecnorm_fuse* f = state->vecnorm;
+    if (f == nullptr) return CANTOR_OK;
+    CANTOR_REQUIRE(!info_on, "state.vecnorm (fused VecNormalize moments) cannot be combined with info output");
+    CANTOR_REQUIRE(f->partial != nullptr && f->returns != nullptr, "vecnorm.partial / vecnorm.returns is NULL");
+    CANTOR_REQUIRE(f->n_partial_ctas >= (n_envs + kStepThreads - 1) / kStepThreads, "vecnorm.partial is too small for n_envs");
+    *vn = VecNormFuse{f->partial, f->returns, f->gamma, f->norm_obs, f->norm_reward};
+    return CANTOR_OK;
 }
 
 static int make_sim_source(const cantor_env_sim* src, SimConsts* sk, SimSource* ss) {
@@ -817,6 +907,10 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
     rc = make_monitor(state, &mon);
     if (rc) return rc;
     const bool mon_on = state->episode_acc != nullptr;
+    VecNormFuse vn;
+    rc = make_vecnorm(state, info != nullptr, n_envs, &vn);
+    if (rc) return rc;
+    CANTOR_REQUIRE(vn.partial == nullptr || !persistent || n_steps <= 1, "cantor_env_step_many does not produce fused VecNormalize moments");
     if (n_envs == 0 || n_steps == 0) return CANTOR_OK;
     const unsigned grid = (unsigned)((n_envs + kStepThreads - 1) / kStepThreads);
     cudaStream_t s = (cudaStream_t)stream;
@@ -846,10 +940,11 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
         unsigned char* done_t = done + (size_t)t * n_envs;
         int tma_ok = (aligned16(obs_t) ? 1 : 0) | keep;
         void* args[] = {&k, &b, &core, &cash, &pv, &n, &a_t, &obs_t, &rew_t, &done_t, &terminal_obs, &auto_reset,
-                        &rr, &io, &tma_ok, &mon};
+                        &rr, &io, &tma_ok, &mon, &vn};
         const void* fn;
-#define PICK(F64) (info ? (mon_on ? (const void*)hedge_step_kernel<F64, true, true> : (const void*)hedge_step_kernel<F64, true, false>) \
-                        : (mon_on ? (const void*)hedge_step_kernel<F64, false, true> : (const void*)hedge_step_kernel<F64, false, false>))
+#define PICK(F64) (info ? (mon_on ? (const void*)hedge_step_kernel<F64, true, true, false> : (const void*)hedge_step_kernel<F64, true, false, false>) \
+                        : (vn.partial ? (mon_on ? (const void*)hedge_step_kernel<F64, false, true, true> : (const void*)hedge_step_kernel<F64, false, false, true>) \
+                                      : (mon_on ? (const void*)hedge_step_kernel<F64, false, true, false> : (const void*)hedge_step_kernel<F64, false, false, false>)))
         if (precision == CANTOR_F64) fn = PICK(true);
         else fn = PICK(false);
 #undef PICK
@@ -901,6 +996,9 @@ extern "C" int cantor_env_step_sim(const cantor_env_params* params, const cantor
     rc = make_monitor(state, &mon);
     if (rc) return rc;
     const bool mon_on = state->episode_acc != nullptr;
+    VecNormFuse vn;
+    rc = make_vecnorm(state, info != nullptr, n_envs, &vn);
+    if (rc) return rc;
     if (n_envs == 0) return CANTOR_OK;
     const unsigned grid = (unsigned)((n_envs + kStepThreads - 1) / kStepThreads);
     int4* core = (int4*)state->core;
@@ -911,10 +1009,11 @@ extern "C" int cantor_env_step_sim(const cantor_env_params* params, const cantor
     int tma_ok = (aligned16(obs) ? 1 : 0) | ((flags & CANTOR_STEP_KEEP_OBS_IN_L2) ? 2 : 0);
     int share = share_quote_ok(params, k, sk);
     void* args[] = {&k, &sk, &ss, &core, &cash, &pv, &n, &a, &obs, &reward, &done, &terminal_obs, &auto_reset, &io, &tma_ok,
-                    &share, &mon};
+                    &share, &mon, &vn};
     const void* fn;
-#define PICK2(MODEL, F64) (info ? (mon_on ? (const void*)hedge_step_sim_kernel<MODEL, F64, true, true> : (const void*)hedge_step_sim_kernel<MODEL, F64, true, false>) \
-                                : (mon_on ? (const void*)hedge_step_sim_kernel<MODEL, F64, false, true> : (const void*)hedge_step_sim_kernel<MODEL, F64, false, false>))
+#define PICK2(MODEL, F64) (info ? (mon_on ? (const void*)hedge_step_sim_kernel<MODEL, F64, true, true, false> : (const void*)hedge_step_sim_kernel<MODEL, F64, true, false, false>) \
+                                : (vn.partial ? (mon_on ? (const void*)hedge_step_sim_kernel<MODEL, F64, false, true, true> : (const void*)hedge_step_sim_kernel<MODEL, F64, false, false, true>) \
+                                              : (mon_on ? (const void*)hedge_step_sim_kernel<MODEL, F64, false, true, false> : (const void*)hedge_step_sim_kernel<MODEL, F64, false, false, false>)))
     if (source->sim->model == CANTOR_MODEL_GBM) fn = precision == CANTOR_F64 ? PICK2(0, true) : PICK2(0, false);
     else fn = precision == CANTOR_F64 ? PICK2(1, true) : PICK2(1, false);
 #undef PICK2

@@ -46,6 +46,42 @@ struct ChunkMap {
     }
 };
 
+// RunningMeanStd.update_from_moments for the 13 observation columns and the returns, from the batch sums in cols[]
+// ({obs sum [13], obs sumsq [13], return sum, return sumsq}); called by every thread of ONE CTA (>= 14 threads); resets the ticket.
+__device__ __forceinline__ void running_update(double* __restrict__ rms, const double* cols, long long n, int norm_obs,
+                                               int norm_reward, double epsilon, unsigned* ticket) {
+    const int j = threadIdx.x;
+    const double bc = (double)n;
+    const double count = rms[kObsCount];
+    if (j < kVnCols) {                                                               // per column
+        if (norm_obs) {
+            const double bmean = cols[j] / bc;
+            const double bvar = fmax(cols[kVnCols + j] / bc - bmean * bmean, 0.0);
+            const double mean = rms[kObsMean + j], var = rms[kObsVar + j];
+            const double t = count + bc, delta = bmean - mean;
+            rms[kObsMean + j] = mean + delta * bc / t;
+            rms[kObsVar + j] = (var * count + bvar * bc + delta * delta * count * bc / t) / t;
+        }
+        rms[kDerived + j] = 1.0 / sqrt(rms[kObsVar + j] + epsilon);
+    } else if (j == kVnCols) {
+        if (norm_reward) {
+            const double bmean = cols[2 * kVnCols] / bc;
+            const double bvar = fmax(cols[2 * kVnCols + 1] / bc - bmean * bmean, 0.0);
+            const double rc = rms[kRetCount], mean = rms[kRetMean], var = rms[kRetVar];
+            const double t = rc + bc, delta = bmean - mean;
+            rms[kRetMean] = mean + delta * bc / t;
+            rms[kRetVar] = (var * rc + bvar * bc + delta * delta * rc * bc / t) / t;
+            rms[kRetCount] = t;
+        }
+        rms[kDerived + kVnCols] = 1.0 / sqrt(rms[kRetVar] + epsilon);
+    }
+    __syncthreads();
+    if (j == 0) {
+        if (norm_obs) rms[kObsCount] = count + bc;                                   // after every column used the old count
+        *ticket = 0u;                                                                // ready for the next launch
+    }
+}
+
 __global__ void __launch_bounds__(kVnThreads, 2)
 vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, long long n,
                        const float* __restrict__ obs, const void* __restrict__ reward, int reward_f64, double gamma,
@@ -191,36 +227,51 @@ vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, l
         if (lane == 0) cols[s] = a;
     }
     __syncthreads();
-    const int j = threadIdx.x;
-    const double bc = (double)n;
-    const double count = rms[kObsCount];
-    if (j < kVnCols) {                                                               // RunningMeanStd.update_from_moments, per column
-        if (norm_obs) {
-            const double bmean = cols[j] / bc;
-            const double bvar = fmax(cols[kVnCols + j] / bc - bmean * bmean, 0.0);
-            const double mean = rms[kObsMean + j], var = rms[kObsVar + j];
-            const double t = count + bc, delta = bmean - mean;
-            rms[kObsMean + j] = mean + delta * bc / t;
-            rms[kObsVar + j] = (var * count + bvar * bc + delta * delta * count * bc / t) / t;
-        }
-        rms[kDerived + j] = 1.0 / sqrt(rms[kObsVar + j] + epsilon);
-    } else if (j == kVnCols) {
-        if (norm_reward) {
-            const double bmean = cols[2 * kVnCols] / bc;
-            const double bvar = fmax(cols[2 * kVnCols + 1] / bc - bmean * bmean, 0.0);
-            const double rc = rms[kRetCount], mean = rms[kRetMean], var = rms[kRetVar];
-            const double t = rc + bc, delta = bmean - mean;
-            rms[kRetMean] = mean + delta * bc / t;
-            rms[kRetVar] = (var * rc + bvar * bc + delta * delta * rc * bc / t) / t;
-            rms[kRetCount] = t;
-        }
-        rms[kDerived + kVnCols] = 1.0 / sqrt(rms[kRetVar] + epsilon);
+    running_update(rms, cols, n, norm_obs, norm_reward, epsilon, ticket);
+}
+
+// Fused form (cantor_vecnorm_step_fused): the step kernel already wrote the per-CTA partial sums partial[statistic][CTA]
+// (hedge_step.cu: vecnorm_partials).  One CTA per statistic sums its row in a fixed order (thread-strided, then a fixed tree);
+// the last of the 28 CTAs (atomic ticket) runs the running-statistics update.  ~64 KB per CTA at 2^20 envs.
+constexpr int kFoldThreads = 256;
+__global__ void __launch_bounds__(kFoldThreads)
+vecnorm_fold_kernel(double* __restrict__ rms, const double* __restrict__ partial, int n_cta, long long n, int norm_obs,
+                    int norm_reward, double epsilon) {
+    __shared__ double sh[kFoldThreads];
+    __shared__ double cols[kVnSums];
+    __shared__ int is_last;
+    pdl_wait_prior_grid();
+    const double* row = partial + (long long)blockIdx.x * n_cta;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;                                  // four independent chains, fixed assignment
+    int j = threadIdx.x;
+    for (; j + 3 * kFoldThreads < n_cta; j += 4 * kFoldThreads) {
+        a0 += __ldcg(row + j);
+        a1 += __ldcg(row + j + kFoldThreads);
+        a2 += __ldcg(row + j + 2 * kFoldThreads);
+        a3 += __ldcg(row + j + 3 * kFoldThreads);
+    }
+    for (; j < n_cta; j += kFoldThreads) a0 += __ldcg(row + j);
+    sh[threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+#pragma unroll
+    for (int off = kFoldThreads / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    pdl_launch_dependents();
+    double* folded = rms + kPartial;                                                 // [28]: reuse the head of the moments kernel's scratch
+    unsigned* ticket = reinterpret_cast<unsigned*>(rms + kTicket);
+    if (threadIdx.x == 0) {
+        folded[blockIdx.x] = sh[0];
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
     }
     __syncthreads();
-    if (j == 0) {
-        if (norm_obs) rms[kObsCount] = count + bc;                                   // after every column used the old count
-        *ticket = 0u;                                                                // ready for the next launch
-    }
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < kVnSums) cols[threadIdx.x] = __ldcg(folded + threadIdx.x);
+    __syncthreads();
+    running_update(rms, cols, n, norm_obs, norm_reward, epsilon, ticket);
 }
 
 __global__ void __launch_bounds__(kVnThreads, 2)
@@ -347,20 +398,34 @@ extern "C" int cantor_vecnorm_init(double* rms, double* returns, int64_t n_envs,
     return CANTOR_OK;
 }
 
-extern "C" int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs, float* obs, void* reward,
-                                   int32_t reward_precision, const uint8_t* done, float* terminal_obs, double gamma,
-                                   double clip_obs, double clip_reward, double epsilon, int32_t training, int32_t norm_obs,
-                                   int32_t norm_reward, void* stream) {
-    CANTOR_REQUIRE(rms && returns && obs && reward && done, "array is NULL");
+static int launch_apply(double* rms, double* returns, long long n, float* obs, void* reward, int f64, const uint8_t* done,
+                        float* terminal_obs, double clip_obs, double clip_reward, double epsilon, int norm_obs, int norm_reward,
+                        cudaStream_t s);
+
+extern "C" int cantor_vecnorm_step_fused(double* rms, const cantor_vecnorm_fuse* fuse, int64_t n_envs, float* obs, void* reward,
+                                         int32_t reward_precision, const uint8_t* done, float* terminal_obs, double clip_obs,
+                                         double clip_reward, double epsilon, void* stream) {
+    CANTOR_REQUIRE(rms && fuse && obs && reward && done, "array is NULL");
+    CANTOR_REQUIRE(fuse->partial != nullptr && fuse->returns != nullptr, "fuse.partial / fuse.returns is NULL");
     CANTOR_REQUIRE(reward_precision == CANTOR_F32 || reward_precision == CANTOR_F64, "reward_precision must be 32 or 64");
     CANTOR_REQUIRE(n_envs >= 0, "n_envs < 0");
     if (n_envs == 0) return CANTOR_OK;
+    const long long n_cta_ll = (n_envs + 127) / 128;                              // the step kernels run 128 envs per CTA
+    CANTOR_REQUIRE(fuse->n_partial_ctas >= n_cta_ll && n_cta_ll <= 0x7fffffffLL, "fuse.partial is too small for n_envs");
     cudaStream_t s = (cudaStream_t)stream;
     long long n = n_envs;
-    const int f64 = reward_precision == CANTOR_F64;
-    const long long n_chunks = (n + kVnRows - 1) / kVnRows;
-    // grid-stride over chunks of 128 envs with exactly one resident wave: SMs x (CTAs that fit per SM), so no partial tail wave
-    // (cached per device: the query costs microseconds and this runs every env-step)
+    int n_cta = (int)n_cta_ll;
+    const double* partial = fuse->partial;
+    int norm_obs = fuse->norm_obs, norm_reward = fuse->norm_reward;
+    void* a1[] = {&rms, &partial, &n_cta, &n, &norm_obs, &norm_reward, &epsilon};
+    int rc = launch_pdl((const void*)vecnorm_fold_kernel, dim3(kVnSums), dim3(kFoldThreads), s, a1);
+    if (rc) return rc;
+    return launch_apply(rms, fuse->returns, n, obs, reward, reward_precision == CANTOR_F64, done, terminal_obs, clip_obs, clip_reward,
+                        epsilon, norm_obs, norm_reward, s);
+}
+
+// occupancy-sized grids (cached per device: the query costs microseconds and this runs every env-step)
+static int vn_occupancy(int* occ_moments, int* occ_apply, int* n_sm) {
     static int occ_cache[64][3];                                             // [device] = {CTAs/SM moments, CTAs/SM apply, SM count}
     int dev = 0;
     CANTOR_CUDA(cudaGetDevice(&dev));
@@ -374,12 +439,47 @@ extern "C" int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs,
         occ_cache[dev][1] = oa;
         occ_cache[dev][2] = sm;                                              // written last: a racing thread recomputes the same values
     }
-    const int occ_moments = occ_cache[dev][0], occ_apply = occ_cache[dev][1], n_sm = occ_cache[dev][2];
-    const long long cap_m = (long long)n_sm * (occ_moments > 0 ? occ_moments : 1), cap_a = (long long)n_sm * (occ_apply > 0 ? occ_apply : 1);
-    const unsigned grid = (unsigned)(n_chunks < cap_m ? n_chunks : (cap_m < kVnMaxGrid ? cap_m : kVnMaxGrid));
+    *occ_moments = occ_cache[dev][0];
+    *occ_apply = occ_cache[dev][1];
+    *n_sm = occ_cache[dev][2];
+    return CANTOR_OK;
+}
+
+static int launch_apply(double* rms, double* returns, long long n, float* obs, void* reward, int f64, const uint8_t* done,
+                        float* terminal_obs, double clip_obs, double clip_reward, double epsilon, int norm_obs, int norm_reward,
+                        cudaStream_t s) {
+    int om, oa, n_sm;
+    int rc = vn_occupancy(&om, &oa, &n_sm);
+    if (rc) return rc;
+    const long long n_chunks = (n + kVnRows - 1) / kVnRows;
+    const long long cap_a = (long long)n_sm * (oa > 0 ? oa : 1);
     const unsigned grid_apply = (unsigned)(n_chunks < cap_a ? n_chunks : cap_a);
     int vec_ok = aligned16(obs) && (terminal_obs == nullptr || aligned16(terminal_obs)) ? 1 : 0;
-    int rc;
+    const double* rms_c = rms;
+    void* a3[] = {&rms_c, &returns, &n, &obs, &reward, (void*)&f64, &done, &terminal_obs, &clip_obs, &clip_reward, &norm_obs,
+                  &norm_reward, &vec_ok, &epsilon};
+    return launch_pdl((const void*)vecnorm_apply_kernel, dim3(grid_apply), dim3(kVnThreads), s, a3);
+}
+
+extern "C" int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs, float* obs, void* reward,
+                                   int32_t reward_precision, const uint8_t* done, float* terminal_obs, double gamma,
+                                   double clip_obs, double clip_reward, double epsilon, int32_t training, int32_t norm_obs,
+                                   int32_t norm_reward, void* stream) {
+    CANTOR_REQUIRE(rms && returns && obs && reward && done, "array is NULL");
+    CANTOR_REQUIRE(reward_precision == CANTOR_F32 || reward_precision == CANTOR_F64, "reward_precision must be 32 or 64");
+    CANTOR_REQUIRE(n_envs >= 0, "n_envs < 0");
+    if (n_envs == 0) return CANTOR_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    long long n = n_envs;
+    const int f64 = reward_precision == CANTOR_F64;
+    const long long n_chunks = (n + kVnRows - 1) / kVnRows;
+    // grid-stride over chunks of 128 envs with exactly one resident wave: SMs x (CTAs that fit per SM), so no partial tail wave
+    int om, oa, n_sm;
+    int rc = vn_occupancy(&om, &oa, &n_sm);
+    if (rc) return rc;
+    const long long cap_m = (long long)n_sm * (om > 0 ? om : 1);
+    const unsigned grid = (unsigned)(n_chunks < cap_m ? n_chunks : (cap_m < kVnMaxGrid ? cap_m : kVnMaxGrid));
+    int vec_ok = aligned16(obs) && (terminal_obs == nullptr || aligned16(terminal_obs)) ? 1 : 0;
     const float* obs_c = obs;
     const void* rew_c = reward;
     if (training) {
@@ -387,8 +487,5 @@ extern "C" int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs,
         rc = launch_pdl((const void*)vecnorm_moments_kernel, dim3(grid), dim3(kVnThreads), s, a1);
         if (rc) return rc;
     }
-    const double* rms_c = rms;
-    void* a3[] = {&rms_c, &returns, &n, &obs, &reward, (void*)&f64, &done, &terminal_obs, &clip_obs, &clip_reward, &norm_obs,
-                  &norm_reward, &vec_ok, &epsilon};
-    return launch_pdl((const void*)vecnorm_apply_kernel, dim3(grid_apply), dim3(kVnThreads), s, a3);
+    return launch_apply(rms, returns, n, obs, reward, f64, done, terminal_obs, clip_obs, clip_reward, epsilon, norm_obs, norm_reward, s);
 }

@@ -8,6 +8,8 @@ behaviour (attribute and method names included); all arithmetic runs in ``cantor
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -67,7 +69,7 @@ class RunningMeanStdView:
 
 class VecNormalize:
     def __init__(self, venv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0, gamma=0.99,
-                 epsilon=1e-8, keep_original=False):
+                 epsilon=1e-8, keep_original=False, fuse=True):
         _lib.lib()
         self.venv = venv
         self.num_envs = venv.num_envs
@@ -90,6 +92,17 @@ class VecNormalize:
         self.old_obs = self.old_reward = None
         self._zero_done = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
         self._dummy_reward = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        # Fusion with the step kernel (cantor_vecnorm_step_fused): a HedgingVecEnv without record_info computes the batch moments
+        # while its observation tile is still in shared memory, so the wrapper's own pass over the batch (the moments kernel)
+        # disappears: step -> 28-CTA fold -> in-place apply.  fuse=False (or any other venv) keeps the two-kernel form.
+        self._fuse = self._fuse_ptr = None
+        if fuse and hasattr(venv, "_state") and getattr(venv, "_info", None) is None and hasattr(_lib.EnvState, "vecnorm"):
+            n_cta = (self.num_envs + 127) // 128
+            self._partial = torch.zeros(28 * n_cta, dtype=torch.float64, device=self.device)
+            self._fuse = _lib.VecNormFuse(self._partial.data_ptr(), self.returns.data_ptr(), self.gamma, n_cta,
+                                          int(self.norm_obs), int(self.norm_reward))
+            self._fuse_ptr = C.cast(C.pointer(self._fuse), C.c_void_p)
+            self._fused_fn = _lib.lib().cantor_vecnorm_step_fused
 
     # ------------------------------------------------------------------------------------------------ core
     def _apply(self, obs, reward, done_u8, terminal_obs, norm_reward):
@@ -114,12 +127,28 @@ class VecNormalize:
 
     def step(self, actions):
         """``venv.step`` followed by SB3's ``VecNormalize.step_wait``; obs / rewards are normalised in place."""
+        fused = self._fuse is not None and self.training
+        if self._fuse is not None:          # the step kernel produces the batch moments itself while training
+            self._fuse.gamma, self._fuse.norm_obs, self._fuse.norm_reward = self.gamma, int(self.norm_obs), int(self.norm_reward)
+            self.venv._state.vecnorm = self._fuse_ptr if fused else None
         obs, reward, done, infos = self.venv.step(actions)
         if self.keep_original:
             self.old_obs, self.old_reward = obs.clone(), reward.clone()
         term = infos["terminal_observation"] if hasattr(infos, "__getitem__") else None
         done_u8 = self.venv._done if getattr(self.venv, "_done_bool", None) is done else done.view(torch.uint8)
-        self._apply(obs, reward, done_u8, term, self.norm_reward)
+        if fused:
+            args = (self._rms_ptr, C.byref(self._fuse), self.num_envs, obs.data_ptr(), reward.data_ptr(),
+                    _lib.F64 if reward.dtype is torch.float64 else _lib.F32, done_u8.data_ptr(), _lib.ptr(term),
+                    self.clip_obs, self.clip_reward, self.epsilon)
+            if torch.cuda.current_device() == self._dev_index:
+                status = self._fused_fn(*args, torch.cuda.current_stream().cuda_stream)
+            else:
+                with torch.cuda.device(self.device):
+                    status = self._fused_fn(*args, _lib.current_stream_ptr(self.device))
+            if status != 0:
+                _lib.check(status, "cantor_vecnorm_step_fused")
+        else:
+            self._apply(obs, reward, done_u8, term, self.norm_reward)
         return obs, reward, done, infos
 
     def step_async(self, actions):

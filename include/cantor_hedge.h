@@ -87,6 +87,16 @@ typedef struct cantor_replay_book {
 
 /* Per-env state, struct of arrays, caller-owned.  Packed so one env-step moves 20 B (F32) of state each way. */
 struct cantor_stats_out;
+/* Optional fusion of VecNormalize's batch moments into the step kernel (see cantor_vecnorm_step_fused): while the CTA's
+ * observation tile is still in shared memory the step kernel writes per-CTA partial sums of the observation columns and of
+ * the updated discounted returns, so the wrapper does not re-read the batch to get them. */
+typedef struct cantor_vecnorm_fuse {
+    double* partial;          /* [28 * n_partial_ctas] scratch: statistic-major {obs sum [13], obs sum of squares [13], return sum, sumsq} */
+    double* returns;          /* [n_envs] discounted returns (VecNormalize.returns): ret <- ret * gamma + reward, in place */
+    double gamma;
+    int64_t n_partial_ctas;   /* capacity of `partial` in CTAs: >= ceil(n_envs / 128) */
+    int32_t norm_obs, norm_reward;
+} cantor_vecnorm_fuse;
 typedef struct cantor_env_state {
     int32_t* core;         /* [n_envs * 4] 16-byte records {pos, step, path, s0}:
                               pos  = call contracts (low int16) | put contracts (high int16)
@@ -101,6 +111,8 @@ typedef struct cantor_env_state {
     void* episode_return;  /* [n_envs] float / double, written when an env finishes: Monitor's info["episode"]["r"] */
     int32_t* episode_length;               /* [n_envs], written when an env finishes: info["episode"]["l"] */
     const struct cantor_stats_out* stats;  /* or NULL: finished episodes are reduced (warp -> block -> atomics) into it */
+    const cantor_vecnorm_fuse* vecnorm;    /* or NULL: cantor_env_step / cantor_env_step_sim (without info) also write VecNormalize's
+                                              batch moments for cantor_vecnorm_step_fused */
 } cantor_env_state;
 
 /* cantor_reset_rule.flags */
@@ -318,6 +330,13 @@ int cantor_vecnorm_init(double* rms, double* returns, int64_t n_envs, void* stre
 int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs, float* obs, void* reward, int32_t reward_precision,
                         const uint8_t* done, float* terminal_obs, double gamma, double clip_obs, double clip_reward,
                         double epsilon, int32_t training, int32_t norm_obs, int32_t norm_reward, void* stream);
+/* The same step_wait() when the step kernel that just ran had state.vecnorm = fuse attached (training mode): the batch moments
+ * are already in fuse->partial and the returns already updated, so this only folds the per-CTA partials in a fixed order (one
+ * small kernel, 28 CTAs), does the running-statistics update, and normalises obs / reward in place (returns[done] <- 0,
+ * terminal_obs where done).  Same results as cantor_vecnorm_step up to the summation order of the batch moments. */
+int cantor_vecnorm_step_fused(double* rms, const cantor_vecnorm_fuse* fuse, int64_t n_envs, float* obs, void* reward,
+                              int32_t reward_precision, const uint8_t* done, float* terminal_obs, double clip_obs,
+                              double clip_reward, double epsilon, void* stream);
 
 /* ---- episode-fused rollout + statistics ------------------------------------------------------------------
  * Replaces the evaluation loops around the env: evaluate_baseline_policy (src/agents/baselines.py:32-72),

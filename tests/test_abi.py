@@ -35,7 +35,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     from cantorrl_b200 import _lib
     pairs = {"cantor_env_params": _lib.EnvParams, "cantor_replay_book": _lib.ReplayBook, "cantor_env_state": _lib.EnvState,
              "cantor_reset_rule": _lib.ResetRule, "cantor_info_out": _lib.InfoOut, "cantor_env_sim": _lib.EnvSim, "cantor_sim_params": _lib.SimParams,
-             "cantor_policy": _lib.Policy, "cantor_stats_out": _lib.StatsOut, "cantor_rollout_out": _lib.RolloutOut, "cantor_rbergomi_params": _lib.RbergomiParams}
+             "cantor_policy": _lib.Policy, "cantor_stats_out": _lib.StatsOut, "cantor_vecnorm_fuse": _lib.VecNormFuse, "cantor_rollout_out": _lib.RolloutOut, "cantor_rbergomi_params": _lib.RbergomiParams}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "cantor_hedge.h"', 'int main(void) {']
     for cname, ct in pairs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

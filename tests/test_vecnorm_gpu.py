@@ -192,3 +192,37 @@ def test_vecnormalize_load_accepts_an_sb3_pickle():
     raw = vn.get_original_obs().double().cpu().numpy()
     want = np.clip((raw - o.mean) / np.sqrt(o.var + 1e-8), -10, 10)
     np.testing.assert_allclose(obs.cpu().numpy(), want, rtol=1e-5, atol=5e-6)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp64"])
+@pytest.mark.parametrize("n", [1003, 70000])
+def test_vecnormalize_fused_with_the_step_kernel_equals_the_two_kernel_form(prec, n):
+    """The batch moments produced inside the step kernel (per-CTA partials while the observation tile is in shared memory, then a
+    28-CTA fold) against the stand-alone moments kernel: same running statistics up to float64 summation order, same normalised
+    outputs; replay and on-the-fly envs; record_info / evaluation mode fall back to the unfused path."""
+    from cantorrl_b200 import HedgingVecEnv, sim
+    from cantorrl_b200.vecnorm import VecNormalize
+    T = 7
+    book = sim.generate_paths_and_options(n, n_steps=T, model="heston", seed=4)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    acts = [torch.rand((n, 2), device="cuda", generator=g) * 2 - 1 for _ in range(2 * T + 3)]
+    for make in (lambda **kw: HedgingVecEnv(data=book, num_envs=n, precision=prec, episode_sampler="same_path", **KW, **kw),
+                 lambda **kw: HedgingVecEnv(simulate=dict(model="heston", seed=4, n_steps=T), num_envs=n, precision=prec, **KW, **kw)):
+        fused, plain = VecNormalize(make(), gamma=0.97), VecNormalize(make(), gamma=0.97, fuse=False)
+        assert fused._fuse is not None and plain._fuse is None
+        assert VecNormalize(make(record_info=True))._fuse is None            # info output keeps the two-kernel form
+        of, op = fused.reset(), plain.reset()
+        assert torch.equal(of, op)
+        for i, a in enumerate(acts):
+            if i == 2 * T:                                                    # evaluation mode: statistics frozen, no partials written
+                fused.training = plain.training = False
+            of, rf, df, inf_f = fused.step(a)
+            op, rp, dp, inf_p = plain.step(a)
+            assert torch.equal(df, dp)
+            torch.testing.assert_close(of, op, rtol=2e-6, atol=2e-6)
+            torch.testing.assert_close(rf, rp, rtol=1e-6 if prec == "fp32" else 1e-12, atol=1e-9)
+            torch.testing.assert_close(fused.returns, plain.returns, rtol=1e-12, atol=1e-15)
+            if bool(df.any()):
+                torch.testing.assert_close(inf_f["terminal_observation"][df], inf_p["terminal_observation"][dp], rtol=2e-6, atol=2e-6)
+        torch.testing.assert_close(fused._rms[:30], plain._rms[:30], rtol=1e-11, atol=1e-13)
+        assert abs(fused.obs_rms.count - (1e-4 + (2 * T + 1) * n)) < 1e-3
