@@ -6,6 +6,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#ifndef CANTOR_F64_GREEKS_IN_FP64      // 1: norm.cdf / norm.pdf of the F64 ledger's observation greeks in float64 (round-1 form)
+#define CANTOR_F64_GREEKS_IN_FP64 0
+#endif
+
 namespace cantor {
 
 constexpr double kInvSqrt2Pi = 0.3989422804014326779;   // 1/sqrt(2*pi)
@@ -72,6 +76,7 @@ __device__ __forceinline__ Greeks atm_greeks_f64(float S, float K, float v_spot,
     const float drift = __fmul_rn(__fadd_rn(g.r_f, __fmul_rn(0.5f, __fmul_rn(sigma, sigma))), g.T_f);
     const float num = __fadd_rn(logf(__fdiv_rn(S, Kc)), drift);
     const double sst = __dmul_rn((double)sigma, g.sqrtT_d);                    // :95 float32 * float64
+#if CANTOR_F64_GREEKS_IN_FP64
     double d1;
     if (sst < 1e-9) d1 = (num > 0.f ? 10.0 : (num < 0.f ? -10.0 : 0.0));        // :96-97
     else d1 = (double)num / sst;                                               // :99
@@ -80,6 +85,36 @@ __device__ __forceinline__ Greeks atm_greeks_f64(float S, float K, float v_spot,
     out.put_delta = (float)(cdf - 1.0);                                        // :101
     const double den = __dmul_rn((double)S, sst);                              // :102
     out.gamma = (fabs(den) < 1e-9) ? 0.f : (float)(exp(-0.5 * d1 * d1) * kInvSqrt2Pi / den);   // :103-106
+#else
+    // The three results are float32 observations (tolerance 1e-6 relative / 2e-7 absolute): only d1 and the exponent's argument
+    // need float64; Phi and the exponential run in float32 (CUDA erfcf <= 4 ulp, expf <= 2 ulp), with the argument's low half
+    // applied as a first-order correction.  The all-float64 form (erfc + exp + two divisions: ~45 % of the kernel's instructions,
+    // FP64 pipe 32 % busy, profiles/r02_hedge_step_f64_2p20_ncu_summary.txt) held the F64 step at 0.72 of the HBM roofline.
+    double d1;
+    if (sst < 1e-9) {
+        d1 = (num > 0.f ? 10.0 : (num < 0.f ? -10.0 : 0.0));                    // :96-97
+    } else {                                                                   // :99  num / sst to ~1e-14: float quotient + one float64 residual step
+        const float sst_f = (float)sst;
+        const float q0 = __fdiv_rn(num, sst_f);
+        const double r = fma(-(double)q0, sst, (double)num);
+        d1 = (double)q0 + r * (double)mufu_rcp(sst_f);
+    }
+    const float z = (float)(d1 * kSqrtHalf);
+    const float q = 0.5f * erfcf(fabsf(z));                                    // upper tail of |d1|, relative accuracy
+    const bool pos = z >= 0.f;
+    out.call_delta = pos ? 1.0f - q : q;                                       // norm.cdf(d1)
+    out.put_delta = pos ? -q : q - 1.0f;                                       // :101, without cancellation for d1 >= 0
+    const double den = __dmul_rn((double)S, sst);                              // :102
+    if (fabs(den) < 1e-9) {
+        out.gamma = 0.f;                                                       // :103-106
+    } else {
+        const double xa = -0.5 * d1 * d1;
+        const float hi = (float)xa;
+        const float lo = (float)(xa - (double)hi);
+        const float e = expf(hi);
+        out.gamma = __fdiv_rn(fmaf(e, lo, e) * (float)kInvSqrt2Pi, (float)den);
+    }
+#endif
     return out;
 }
 

@@ -22,6 +22,13 @@
 
 #include "common.cuh"
 
+// 1: all four warps poll the MMA mbarrier; 0: warp 0 polls, the others park at the CTA barrier.  Measured (2^20 envs x 252
+// steps, GBM on the fly): 6.88 ms against 7.01 ms -- the polls are 23 % of the executed instructions but fill issue slots nobody
+// else wants: the kernel is bound by the latency of its three serial MMA round trips per step, not by issue bandwidth.
+#ifndef CANTOR_MLP_ALL_WARPS_POLL
+#define CANTOR_MLP_ALL_WARPS_POLL 1
+#endif
+
 namespace cantor {
 namespace mlptc {
 
@@ -192,14 +199,27 @@ struct Actor {
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
     }
 
+    // Only warp 0 polls the mbarrier; the other three warps sleep in the hardware CTA barrier until it joins them.  With all
+    // four warps polling, the try_wait loop was 23 % of the kernel's executed instructions (~23 iterations per wait per warp:
+    // profiles/r01_rollout_mlp_bf16_tcgen05_ncu_summary.txt) on an issue-bound kernel; a warp parked at bar.sync issues nothing.
     __device__ __forceinline__ void wait_mma() {
-        uint32_t done = 0;
-        unsigned spins = 0;
-        while (!done && !timed_out) {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
-            if (!done && ++spins > kSpinLimit) timed_out = true;      // never hang the GPU: bail out, the caller reports it
+#if CANTOR_MLP_ALL_WARPS_POLL
+        const bool poller = true;
+#else
+        const bool poller = threadIdx.x < 32;
+#endif
+        if (poller) {
+            uint32_t done = 0;
+            unsigned spins = 0;
+            while (!done && !timed_out) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+                if (!done && ++spins > kSpinLimit) timed_out = true;  // never hang the GPU: bail out, the caller reports it
+            }
         }
+#if !CANTOR_MLP_ALL_WARPS_POLL
+        __syncthreads();                  // (a timed-out warp 0 still arrives; its flag reaches the statistics through thread 0)
+#endif
         phase ^= 1;
         fence_after_sync();
     }
