@@ -83,10 +83,10 @@ struct Monitor {
 
 // Optional VecNormalize fusion (cantor_env_state.vecnorm): the step kernel also produces what cantor_vecnorm_step's moments
 // kernel would have to re-read the batch for -- per-CTA partial sums of the observation columns (sum, sum of squares: 26 values)
-// and of the updated discounted returns (2 values), written with plain stores to partial[statistic][CTA] and folded later
+// and of the updated discounted returns (2 values), written with plain stores to partial[CTA][statistic] and folded later
 // in a fixed order (cantor_vecnorm_step_fused), so the running statistics stay bitwise reproducible.
 struct VecNormFuse {
-    double* partial;           // [28, n_cta] (NULL = off)
+    double* partial;           // [n_cta, 28] (NULL = off)
     double* returns;           // [n] discounted returns, updated in place: ret <- ret * gamma + reward
     double gamma;
     int norm_obs, norm_reward;
@@ -95,23 +95,28 @@ constexpr int kVnFuseSums = 2 * CANTOR_OBS_DIM + 2;
 
 // Called by every thread of the CTA after the observation tile is complete and a CTA barrier has been passed.
 // `reward` = this thread's raw reward of the step (ignored for threads without an env).
+// partial layout: [CTA][28] -- one contiguous, fully written 224-byte record per CTA (no partial-sector writes).
 template <int THREADS>
 __device__ __forceinline__ void vecnorm_partials(const VecNormFuse& vn, const float* tile, int rows, bool live, long long i,
                                                  double reward, double* scratch /* [2 * 8 * 13 + 2 * THREADS / 32] */) {
     constexpr int C = CANTOR_OBS_DIM, PARTS = 8;
     double* part = scratch;                            // [2][PARTS][C]
     double* wsum = scratch + 2 * PARTS * C;            // [2][THREADS / 32]
-    const int n_cta = (int)gridDim.x;
-    if (vn.norm_obs && threadIdx.x < PARTS * C) {      // (part v, column c): rows v, v + 8, ... in a fixed order
+    if (vn.norm_obs && threadIdx.x < PARTS * C) {      // (part v, column c): rows v, v + 8, ... in a fixed order, two chains each
         const int v = threadIdx.x / C, c = threadIdx.x % C;
-        double a = 0.0, q = 0.0;
-        for (int r = v; r < rows; r += PARTS) {
-            const double x = (double)tile[r * C + c];
-            a += x;
-            q = fma(x, x, q);
+        double a0 = 0.0, q0 = 0.0, a1 = 0.0, q1 = 0.0;
+        int r = v;
+        for (; r + PARTS < rows; r += 2 * PARTS) {
+            const double x0 = (double)tile[r * C + c], x1 = (double)tile[(r + PARTS) * C + c];
+            a0 += x0; q0 = fma(x0, x0, q0);
+            a1 += x1; q1 = fma(x1, x1, q1);
         }
-        part[v * C + c] = a;
-        part[(PARTS + v) * C + c] = q;
+        if (r < rows) {
+            const double x0 = (double)tile[r * C + c];
+            a0 += x0; q0 = fma(x0, x0, q0);
+        }
+        part[v * C + c] = a0 + a1;
+        part[(PARTS + v) * C + c] = q0 + q1;
     }
     double rs = 0.0, rq = 0.0;
     if (vn.norm_reward && live) {
@@ -130,6 +135,7 @@ __device__ __forceinline__ void vecnorm_partials(const VecNormFuse& vn, const fl
         wsum[THREADS / 32 + (threadIdx.x >> 5)] = rq;
     }
     __syncthreads();
+    double* out = vn.partial + (long long)blockIdx.x * kVnFuseSums;
     if (threadIdx.x < 2 * C) {                         // column sums: the 8 parts in order
         const int kind = threadIdx.x / C, c = threadIdx.x % C;
         double a = 0.0;
@@ -137,13 +143,13 @@ __device__ __forceinline__ void vecnorm_partials(const VecNormFuse& vn, const fl
 #pragma unroll
             for (int v = 0; v < PARTS; ++v) a += part[(kind * PARTS + v) * C + c];
         }
-        vn.partial[(long long)threadIdx.x * n_cta + blockIdx.x] = a;
+        out[threadIdx.x] = a;
     } else if (threadIdx.x < 2 * C + 2) {              // returns: the warps in order
         const int kind = threadIdx.x - 2 * C;
         double a = 0.0;
 #pragma unroll
         for (int w = 0; w < THREADS / 32; ++w) a += wsum[kind * (THREADS / 32) + w];
-        vn.partial[(long long)threadIdx.x * n_cta + blockIdx.x] = a;
+        out[threadIdx.x] = a;
     }
 }
 
@@ -412,7 +418,7 @@ __device__ __forceinline__ void monitor_epilogue(const Monitor& mon, double (&st
 // ---------------------------------------------------------------------------------------------------
 // Gym-style step, replay mode: one launch = one env-step.
 template <bool F64, bool INFO, bool MON, bool VN>
-__global__ void __launch_bounds__(kStepThreads, (MON || INFO || F64 || VN) ? 8 : CANTOR_STEP_MIN_BLOCKS)
+__global__ void __launch_bounds__(kStepThreads, (MON || INFO || F64) ? 8 : (VN ? 12 : CANTOR_STEP_MIN_BLOCKS))   // VN alone: 40 registers
 hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                   double* __restrict__ pv_arr, long long n_envs, const float2* __restrict__ actions,
                   float* __restrict__ obs, void* __restrict__ reward_arr, unsigned char* __restrict__ done_arr,

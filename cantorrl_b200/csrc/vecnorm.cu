@@ -230,48 +230,68 @@ vecnorm_moments_kernel(double* __restrict__ rms, double* __restrict__ returns, l
     running_update(rms, cols, n, norm_obs, norm_reward, epsilon, ticket);
 }
 
-// Fused form (cantor_vecnorm_step_fused): the step kernel already wrote the per-CTA partial sums partial[statistic][CTA]
-// (hedge_step.cu: vecnorm_partials).  One CTA per statistic sums its row in a fixed order (thread-strided, then a fixed tree);
-// the last of the 28 CTAs (atomic ticket) runs the running-statistics update.  ~64 KB per CTA at 2^20 envs.
+// Fused form (cantor_vecnorm_step_fused): the step kernel already wrote the per-CTA partial sums partial[CTA][28]
+// (hedge_step.cu: vecnorm_partials).  Two levels, both with coalesced reads and a fixed summation order: fold CTA f sums the
+// records of source CTAs [128 f, 128 f + 128) -- 252 threads = 9 parts x 28 statistics, each thread's <= 15 loads in flight at
+// once, then the 9 parts in order -- into level1[f][28]; the last fold CTA (atomic ticket) sums level1 the same way and runs the
+// running-statistics update.  (A one-CTA-per-statistic fold over a statistic-major layout took 8 us: the step kernel's 8-byte
+// scattered writes left partially valid sectors that every read had to fill from DRAM.)
 constexpr int kFoldThreads = 256;
+constexpr int kFoldParts = 9, kFoldRows = 128, kFoldDepth = (kFoldRows + kFoldParts - 1) / kFoldParts;   // 15
+
+// sums rows [0, n_rows) of a [n_rows][28] array (n_rows <= 128 per call) into out28 (shared), deterministic
+__device__ __forceinline__ void fold_rows(const double* __restrict__ rows, int n_rows, double* sh /* [9 * 28] */, double* out28) {
+    const int t = threadIdx.x;
+    if (t < kFoldParts * kVnSums) {
+        const int part = t / kVnSums;
+        double v[kFoldDepth];
+#pragma unroll
+        for (int k = 0; k < kFoldDepth; ++k) {
+            const int r = k * kFoldParts + part;
+            v[k] = r < n_rows ? __ldcg(rows + (long long)r * kVnSums + (t - part * kVnSums)) : 0.0;
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < kFoldDepth; ++k) a += v[k];
+        sh[t] = a;
+    }
+    __syncthreads();
+    if (t < kVnSums) {
+        double a = 0.0;
+#pragma unroll
+        for (int p = 0; p < kFoldParts; ++p) a += sh[p * kVnSums + t];
+        out28[t] = a;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kFoldThreads)
-vecnorm_fold_kernel(double* __restrict__ rms, const double* __restrict__ partial, int n_cta, long long n, int norm_obs,
-                    int norm_reward, double epsilon) {
-    __shared__ double sh[kFoldThreads];
+vecnorm_fold_kernel(double* __restrict__ rms, const double* __restrict__ partial, double* __restrict__ level1, int n_cta,
+                    long long n, int norm_obs, int norm_reward, double epsilon) {
+    __shared__ double sh[kFoldParts * kVnSums];
     __shared__ double cols[kVnSums];
+    __shared__ double acc28[kVnSums];
     __shared__ int is_last;
     pdl_wait_prior_grid();
-    const double* row = partial + (long long)blockIdx.x * n_cta;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;                                  // four independent chains, fixed assignment
-    int j = threadIdx.x;
-    for (; j + 3 * kFoldThreads < n_cta; j += 4 * kFoldThreads) {
-        a0 += __ldcg(row + j);
-        a1 += __ldcg(row + j + kFoldThreads);
-        a2 += __ldcg(row + j + 2 * kFoldThreads);
-        a3 += __ldcg(row + j + 3 * kFoldThreads);
-    }
-    for (; j < n_cta; j += kFoldThreads) a0 += __ldcg(row + j);
-    sh[threadIdx.x] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-#pragma unroll
-    for (int off = kFoldThreads / 2; off > 0; off >>= 1) {
-        if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
-        __syncthreads();
-    }
+    const int first = (int)blockIdx.x * kFoldRows;
+    fold_rows(partial + (long long)first * kVnSums, min(kFoldRows, n_cta - first), sh, cols);
+    if (threadIdx.x < kVnSums) level1[(long long)blockIdx.x * kVnSums + threadIdx.x] = cols[threadIdx.x];
     pdl_launch_dependents();
-    double* folded = rms + kPartial;                                                 // [28]: reuse the head of the moments kernel's scratch
     unsigned* ticket = reinterpret_cast<unsigned*>(rms + kTicket);
-    if (threadIdx.x == 0) {
-        folded[blockIdx.x] = sh[0];
-        __threadfence();
-        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
-    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1 : 0;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (threadIdx.x < kVnSums) cols[threadIdx.x] = __ldcg(folded + threadIdx.x);
+    if (threadIdx.x < kVnSums) acc28[threadIdx.x] = 0.0;
     __syncthreads();
-    running_update(rms, cols, n, norm_obs, norm_reward, epsilon, ticket);
+    for (int base = 0; base < (int)gridDim.x; base += kFoldRows) {                   // level 2, chunks of 128 level-1 records in order
+        fold_rows(level1 + (long long)base * kVnSums, min(kFoldRows, (int)gridDim.x - base), sh, cols);
+        if (threadIdx.x < kVnSums) acc28[threadIdx.x] += cols[threadIdx.x];
+        __syncthreads();
+    }
+    running_update(rms, acc28, n, norm_obs, norm_reward, epsilon, ticket);
 }
 
 __global__ void __launch_bounds__(kVnThreads, 2)
@@ -417,8 +437,11 @@ extern "C" int cantor_vecnorm_step_fused(double* rms, const cantor_vecnorm_fuse*
     int n_cta = (int)n_cta_ll;
     const double* partial = fuse->partial;
     int norm_obs = fuse->norm_obs, norm_reward = fuse->norm_reward;
-    void* a1[] = {&rms, &partial, &n_cta, &n, &norm_obs, &norm_reward, &epsilon};
-    int rc = launch_pdl((const void*)vecnorm_fold_kernel, dim3(kVnSums), dim3(kFoldThreads), s, a1);
+    const int n_fold = (n_cta + kFoldRows - 1) / kFoldRows;
+    // level-1 records live behind the step kernel's partials: fuse->partial holds 28 * (n_partial_ctas + ceil(n_partial_ctas / 128)) doubles
+    double* level1 = fuse->partial + (long long)fuse->n_partial_ctas * kVnSums;
+    void* a1[] = {&rms, &partial, &level1, &n_cta, &n, &norm_obs, &norm_reward, &epsilon};
+    int rc = launch_pdl((const void*)vecnorm_fold_kernel, dim3(n_fold), dim3(kFoldThreads), s, a1);
     if (rc) return rc;
     return launch_apply(rms, fuse->returns, n, obs, reward, reward_precision == CANTOR_F64, done, terminal_obs, clip_obs, clip_reward,
                         epsilon, norm_obs, norm_reward, s);

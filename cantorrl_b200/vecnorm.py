@@ -94,11 +94,11 @@ class VecNormalize:
         self._dummy_reward = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
         # Fusion with the step kernel (cantor_vecnorm_step_fused): a HedgingVecEnv without record_info computes the batch moments
         # while its observation tile is still in shared memory, so the wrapper's own pass over the batch (the moments kernel)
-        # disappears: step -> 28-CTA fold -> in-place apply.  fuse=False (or any other venv) keeps the two-kernel form.
+        # disappears: step -> two-level fold of the per-CTA records -> in-place apply.  fuse=False (or any other venv) keeps the two-kernel form.
         self._fuse = self._fuse_ptr = None
         if fuse and hasattr(venv, "_state") and getattr(venv, "_info", None) is None and hasattr(_lib.EnvState, "vecnorm"):
             n_cta = (self.num_envs + 127) // 128
-            self._partial = torch.zeros(28 * n_cta, dtype=torch.float64, device=self.device)
+            self._partial = torch.zeros(28 * (n_cta + (n_cta + 127) // 128), dtype=torch.float64, device=self.device)
             self._fuse = _lib.VecNormFuse(self._partial.data_ptr(), self.returns.data_ptr(), self.gamma, n_cta,
                                           int(self.norm_obs), int(self.norm_reward))
             self._fuse_ptr = C.cast(C.pointer(self._fuse), C.c_void_p)

@@ -91,7 +91,8 @@ struct cantor_stats_out;
  * observation tile is still in shared memory the step kernel writes per-CTA partial sums of the observation columns and of
  * the updated discounted returns, so the wrapper does not re-read the batch to get them. */
 typedef struct cantor_vecnorm_fuse {
-    double* partial;          /* [28 * n_partial_ctas] scratch: statistic-major {obs sum [13], obs sum of squares [13], return sum, sumsq} */
+    double* partial;          /* scratch of 28 * (n_partial_ctas + ceil(n_partial_ctas / 128)) doubles: one 28-double record per step-kernel
+                                 CTA {obs sum [13], obs sum of squares [13], return sum, sumsq}, then the fold's level-1 records */
     double* returns;          /* [n_envs] discounted returns (VecNormalize.returns): ret <- ret * gamma + reward, in place */
     double gamma;
     int64_t n_partial_ctas;   /* capacity of `partial` in CTAs: >= ceil(n_envs / 128) */
@@ -332,7 +333,7 @@ int cantor_vecnorm_step(double* rms, double* returns, int64_t n_envs, float* obs
                         double epsilon, int32_t training, int32_t norm_obs, int32_t norm_reward, void* stream);
 /* The same step_wait() when the step kernel that just ran had state.vecnorm = fuse attached (training mode): the batch moments
  * are already in fuse->partial and the returns already updated, so this only folds the per-CTA partials in a fixed order (one
- * small kernel, 28 CTAs), does the running-statistics update, and normalises obs / reward in place (returns[done] <- 0,
+ * small two-level kernel), does the running-statistics update, and normalises obs / reward in place (returns[done] <- 0,
  * terminal_obs where done).  Same results as cantor_vecnorm_step up to the summation order of the batch moments. */
 int cantor_vecnorm_step_fused(double* rms, const cantor_vecnorm_fuse* fuse, int64_t n_envs, float* obs, void* reward,
                               int32_t reward_precision, const uint8_t* done, float* terminal_obs, double clip_obs,

@@ -198,7 +198,7 @@ def test_vecnormalize_load_accepts_an_sb3_pickle():
 @pytest.mark.parametrize("n", [1003, 70000])
 def test_vecnormalize_fused_with_the_step_kernel_equals_the_two_kernel_form(prec, n):
     """The batch moments produced inside the step kernel (per-CTA partials while the observation tile is in shared memory, then a
-    28-CTA fold) against the stand-alone moments kernel: same running statistics up to float64 summation order, same normalised
+    two-level fold) against the stand-alone moments kernel: same running statistics up to float64 summation order, same normalised
     outputs; replay and on-the-fly envs; record_info / evaluation mode fall back to the unfused path."""
     from cantorrl_b200 import HedgingVecEnv, sim
     from cantorrl_b200.vecnorm import VecNormalize

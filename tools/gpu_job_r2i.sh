@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, call I (2 GPUs): the multi-GPU tests that skip on one GPU, then the bench line through torchrun, the copy probe on both GPUs
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_multigpu_gpu.py -m gpu -q > gpurun_out/r2i_pytest.log 2>&1; tail -12 gpurun_out/r2i_pytest.log
+timeout 200 python tools/host_copy_probe.py --gpus 1,2 > gpurun_out/r2i_probe.log 2>&1; cat gpurun_out/r2i_probe.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2i_bench2.log 2> gpurun_out/r2i_bench2.err; echo "bench2 rc=$?"; tail -5 gpurun_out/r2i_bench2.err
+tail -1 gpurun_out/r2i_bench2.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('n_gpus', d['n_gpus'], 'value %.4e' % d['value'], 'frac %.3f' % d['roofline']['frac'], 'e2e %.4e' % d['e2e']['value'])
+print(json.dumps(d['e2e'].get('copy_ceiling'), indent=1))
+print(json.dumps(d['extra'].get('stats_check'), indent=1))
+print({k: (v.get('env_steps_per_s') or v.get('ms')) for k, v in d['extra'].items() if isinstance(v, dict)})"

@@ -48,6 +48,36 @@ def main():
         fused_note = f"fused all-reduce unavailable ({type(e).__name__}: {str(e)[:200]})"
     ok = fused_ok
     print(f"[rank {rank}] {fused_note}", flush=True)
+    # the gym-style step kernel's fused Monitor with the all-reduce in ITS epilogue (replay and on-the-fly), against NCCL
+    from cantorrl_b200 import HedgingVecEnv
+    from cantorrl_b200.stats import EpisodeStats
+    n_env_total, Te = 40_003, 9
+    eo, ec = shard(n_env_total, rank, world)
+    g = torch.Generator(device=dev).manual_seed(17)
+    tape = torch.rand((2 * Te + 3, n_env_total, 2), device=dev, generator=g) * 2 - 1
+    env_ok = True
+    for enable_late in (False, True):
+        est_f, est_n = EpisodeStats(dev, hist_bins=512), EpisodeStats(dev, hist_bins=512)
+        if not enable_late:
+            est_f.enable_fused_all_reduce()
+        envs = [HedgingVecEnv(simulate=dict(model="gbm", seed=3, n_steps=Te), num_envs=ec, total_envs=n_env_total, env_offset=eo,
+                              device=dev, monitor=True, stats=st, **KW) for st in (est_f, est_n)]
+        if enable_late:                 # enabling the fused transport AFTER the env was constructed must take effect too
+            est_f.enable_fused_all_reduce()
+        est_f.zero_()
+        for e in envs:
+            e.reset()
+        for t in range(tape.shape[0]):
+            a = tape[t, eo:eo + ec].contiguous()
+            for e in envs:
+                e.step(a)
+        est_f.all_reduce()
+        est_n.all_reduce()
+        torch.cuda.synchronize()
+        env_ok &= torch.equal(est_f.hist, est_n.hist) and int(est_n.sums[0]) == 2 * n_env_total
+        env_ok &= bool(np.allclose(est_f.sums.cpu().numpy()[:12], est_n.sums.cpu().numpy()[:12], rtol=1e-10, atol=0))
+    print(f"[rank {rank}] step-kernel Monitor statistics, fused all-reduce vs NCCL: {'OK' if env_ok else 'MISMATCH'}", flush=True)
+    ok &= env_ok
     if rank == 0:
         whole = HedgingRollout(simulate=sim, num_envs=total, device=dev, **KW).run(steps, "delta_benchmark").stats
         ok &= torch.equal(whole.hist, st.hist)
