@@ -94,11 +94,12 @@ struct VecNormFuse {
 constexpr int kVnFuseSums = 2 * CANTOR_OBS_DIM + 2;
 
 // Called by every thread of the CTA after the observation tile is complete and a CTA barrier has been passed.
-// `reward` = this thread's raw reward of the step (ignored for threads without an env).
+// `reward` = this thread's raw reward of the step, `ret_prev` = its discounted return before the step (both ignored for
+// threads without an env).
 // partial layout: [CTA][28] -- one contiguous, fully written 224-byte record per CTA (no partial-sector writes).
 template <int THREADS>
 __device__ __forceinline__ void vecnorm_partials(const VecNormFuse& vn, const float* tile, int rows, bool live, long long i,
-                                                 double reward, double* scratch /* [2 * 8 * 13 + 2 * THREADS / 32] */) {
+                                                 double reward, double ret_prev, double* scratch /* [2 * 8 * 13 + 2 * THREADS / 32] */) {
     constexpr int C = CANTOR_OBS_DIM, PARTS = 8;
     double* part = scratch;                            // [2][PARTS][C]
     double* wsum = scratch + 2 * PARTS * C;            // [2][THREADS / 32]
@@ -120,8 +121,8 @@ __device__ __forceinline__ void vecnorm_partials(const VecNormFuse& vn, const fl
     }
     double rs = 0.0, rq = 0.0;
     if (vn.norm_reward && live) {
-        const double ret = fma(vn.returns[i], vn.gamma, reward);
-        vn.returns[i] = ret;
+        const double ret = fma(ret_prev, vn.gamma, reward);   // ret_prev was requested with the kernel's first loads: a load here,
+        vn.returns[i] = ret;                                  // at the end of the CTA's life, would add a DRAM round trip to every CTA
         rs = ret;
         rq = ret * ret;
     }
@@ -427,7 +428,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
     __shared__ __align__(128) float tile[kStepThreads * CANTOR_OBS_DIM];
     __shared__ double red[MON ? 11 * (kStepThreads / 32) : 1];
     __shared__ double vn_scratch[VN ? 2 * 8 * CANTOR_OBS_DIM + 2 * (kStepThreads / 32) : 1];
-    double my_reward = 0.0;
+    double my_reward = 0.0, ret_prev = 0.0;
     double stat[11];
     bool finished_episode = false;                                            // MON: this thread's env just ended an episode
     if (MON) {
@@ -445,6 +446,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         // ---- independent loads first -----------------------------------------------------------------
         EnvRegs e = load_env<F64>(core_arr, cash_arr, pv_arr, i);
         const float2 a = __ldcs(actions + i);
+        if (VN && vn.norm_reward) ret_prev = vn.returns[i];
         // ---- the two time records of this env's path ----------------------------------------------------
         const int t_prev = (e.step >= k.T) ? k.T - 1 : e.step;
         const float4* rp = b.rec + ((long long)t_prev * b.ld + e.path);
@@ -475,7 +477,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
-    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, vn_scratch);
+    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch);
     if (MON) monitor_epilogue<kStepThreads>(mon, stat, finished_episode, red, (double)n_envs);
 }
 
@@ -639,7 +641,7 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
     __shared__ __align__(128) float tile[kStepThreads * CANTOR_OBS_DIM];
     __shared__ double red[MON ? 11 * (kStepThreads / 32) : 1];
     __shared__ double vn_scratch[VN ? 2 * 8 * CANTOR_OBS_DIM + 2 * (kStepThreads / 32) : 1];
-    double my_reward = 0.0;
+    double my_reward = 0.0, ret_prev = 0.0;
     double stat[11];
     bool finished_episode = false;
     if (MON) {
@@ -657,6 +659,7 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
         EnvRegs e = load_env<F64>(core_arr, cash_arr, pv_arr, i);
         const float2 a = __ldcs(actions + i);
         float2 sv = src.sv[i];
+        if (VN && vn.norm_reward) ret_prev = vn.returns[i];
         pdl_launch_dependents();
         const int t_prev = (e.step >= k.T) ? k.T - 1 : e.step;
         const unsigned long long gp = (unsigned long long)e.path * (unsigned long long)src.total_envs +
@@ -716,7 +719,7 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
-    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, vn_scratch);
+    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch);
     if (MON) monitor_epilogue<kStepThreads>(mon, stat, finished_episode, red, (double)n_envs);
 }
 
