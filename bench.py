@@ -842,9 +842,11 @@ def main():
     tt = torch.tensor([ms, e2e_s, roll[0] if roll else 0.0, mlp_roll[0] if mlp_roll else 0.0, lstm_roll[0] if lstm_roll else 0.0,
                        per_launch_ms], dtype=torch.float64, device=dev)
     ps = torch.tensor([pr["d2h_gbs"], pr["h2d_gbs"], pr["rounds_per_s"], pr["d2h_only_gbs"]], dtype=torch.float64, device=dev)
+    pmin = torch.tensor([pr["rounds_per_s"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ps, op=dist.ReduceOp.SUM)
+        dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
     ms, e2e_s, roll_ms, mlp_ms, lstm_ms, per_launch_ms = (float(x) for x in tt)
     if rank == 0:
         env_steps = float(n) * world * T * K
@@ -897,11 +899,13 @@ def main():
                                              hbm_write_gbs=float(n) * (T + 1) * 16 / (sim_ms * 1e-3) / 1e9)))
         if probe is not None:
             ceil = float(ps[2]) * n                      # env-steps/s the raw copies alone would sustain, summed over ranks
+            ceil_slowest = float(pmin[0]) * n * world    # ... when every rank has to wait for the slowest one, as the e2e timing (max over ranks) does
             e2e_v = line["e2e"]["value"]
             line["e2e"]["copy_ceiling"] = dict(
                 what="cantor_host_copy_probe on every rank at once: the same bytes per step (57 out + 8 in per env, 8 chunks, 3 streams, "
                      "stream sync after every round) as plain cudaMemcpyAsync between page-locked host memory and HBM, no kernel",
                 d2h_gbs_total=float(ps[0]), h2d_gbs_total=float(ps[1]), env_steps_per_s=ceil, e2e_over_ceiling=e2e_v / ceil if ceil else None,
+                env_steps_per_s_at_slowest_rank=ceil_slowest, e2e_over_ceiling_at_slowest_rank=e2e_v / ceil_slowest if ceil_slowest else None,
                 d2h_only_unsynchronised_gbs_total=float(ps[3]), e2e_d2h_gbs=e2e_v * (52 + (8 if fp64 else 4) + 1) / 1e9)
         if l2free:
             line["extra"]["step_kernels_beyond_l2"] = l2free
