@@ -50,6 +50,9 @@
 #ifndef CANTOR_MANY_EVICT_FIRST       // L2 policy of the persistent kernel's observation stores.  Nothing it touches is ever re-read, so there
 #define CANTOR_MANY_EVICT_FIRST 0     // is nothing to protect in L2: the plain policy measured 3.689 ms against 3.771 ms with evict-first
 #endif                                // (2^20 envs x 252 steps) -- evict-first lines leave L2 in smaller, less DRAM-friendly batches.
+#ifndef CANTOR_MANY_PREFETCH          // how many steps ahead the persistent kernel requests a step's action and path record (1 or 2).
+#define CANTOR_MANY_PREFETCH 1        // Measured (2^20 envs x 252 steps): 1 -> 3.695 ms, 2 -> 3.742 ms (same 48 registers): the first-use stalls
+#endif                                // are back-pressure of the memory system, not latency that deeper prefetch could hide.
 #ifndef CANTOR_MANY_THREADS
 #define CANTOR_MANY_THREADS 128       // envs per CTA of the persistent kernel
 #endif
@@ -510,8 +513,8 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
     const Greeks none{0.f, 0.f, 0.f};
 
     EnvRegs e{};
-    float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, cur_n = prev;
-    float2 a = make_float2(0.f, 0.f), a_n = a;
+    float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, cur_n = prev, cur_n2 = prev;
+    float2 a = make_float2(0.f, 0.f), a_n = a, a_n2 = a;
     const float4* rp = b.rec;                                                  // record (t + 1, path) of the step being computed
     if (live) {
         e = load_env<F64>(core_arr, cash_arr, pv_arr, i);
@@ -520,6 +523,12 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
         prev = __ldcs(rp - b.ld);
         cur = __ldcs(rp);
         a = __ldcs(actions + i);
+#if CANTOR_MANY_PREFETCH >= 2
+        if (n_steps > 1) {                                                     // step 1's inputs (its record only if step 0 does not end the episode)
+            a_n = __ldcs(actions + n_envs + i);
+            if (t_prev + 2 <= k.T) cur_n = __ldcs(rp + b.ld);
+        }
+#endif
     }
     for (int s = 0; s < n_steps; ++s) {
         float* tile = tiles[s & 1];
@@ -527,12 +536,20 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
         const long long at = (long long)s * n_envs + i;
         bool terminated = false;
         if (live) {
-            // request the next step's inputs before this step's arithmetic (unless this step ends the episode: new path)
+            // request later steps' inputs before this step's arithmetic: CANTOR_MANY_PREFETCH steps ahead (a record only while the
+            // episode it belongs to is the current one: after an episode end the new path is known only at the reset)
+#if CANTOR_MANY_PREFETCH >= 2
+            if (s + 2 < n_steps) {
+                a_n2 = __ldcs(actions + at + 2 * n_envs);
+                if (e.step + 3 <= k.T) cur_n2 = __ldcs(rp + 2 * b.ld);
+            }
+#else
             const bool ends = e.step + 1 >= k.T;
             if (s + 1 < n_steps) {
                 a_n = __ldcs(actions + at + n_envs);
                 if (!ends) cur_n = __ldcs(rp + b.ld);
             }
+#endif
             const int path = e.path;
             terminated = step_body<F64, false, MON, false>(k, e, a, prev, cur, none, o, i, n_envs, (char*)reward_arr + at * rb,
                                                            no_info, mon, stat, finished_episode);
@@ -544,12 +561,19 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
                 rp = b.rec + (b.ld + next);
                 prev = r0;
                 if (s + 1 < n_steps) cur_n = __ldcs(rp);
+#if CANTOR_MANY_PREFETCH >= 2
+                if (s + 2 < n_steps && k.T >= 2) cur_n2 = __ldcs(rp + b.ld);
+#endif
             } else {
                 prev = cur;
                 rp += b.ld;
             }
             cur = cur_n;
             a = a_n;
+#if CANTOR_MANY_PREFETCH >= 2
+            cur_n = cur_n2;
+            a_n = a_n2;
+#endif
             done_arr[at] = terminated ? 1 : 0;
         }
         // ---- the CTA's observation tile of step s ---------------------------------------------------------------
