@@ -899,13 +899,13 @@ def main():
                                              hbm_write_gbs=float(n) * (T + 1) * 16 / (sim_ms * 1e-3) / 1e9)))
         if probe is not None:
             ceil = float(ps[2]) * n                      # env-steps/s the raw copies alone would sustain, summed over ranks
-            ceil_slowest = float(pmin[0]) * n * world    # ... when every rank has to wait for the slowest one, as the e2e timing (max over ranks) does
+            slowest = float(pmin[0]) * n                 # the slowest rank's share (the box's GPUs do not get equal shares of its host side)
             e2e_v = line["e2e"]["value"]
             line["e2e"]["copy_ceiling"] = dict(
                 what="cantor_host_copy_probe on every rank at once: the same bytes per step (57 out + 8 in per env, 8 chunks, 3 streams, "
                      "stream sync after every round) as plain cudaMemcpyAsync between page-locked host memory and HBM, no kernel",
                 d2h_gbs_total=float(ps[0]), h2d_gbs_total=float(ps[1]), env_steps_per_s=ceil, e2e_over_ceiling=e2e_v / ceil if ceil else None,
-                env_steps_per_s_at_slowest_rank=ceil_slowest, e2e_over_ceiling_at_slowest_rank=e2e_v / ceil_slowest if ceil_slowest else None,
+                slowest_rank_env_steps_per_s=slowest, fastest_to_slowest_note="ranks are not in lock-step: a rank that finishes early leaves its share to the others",
                 d2h_only_unsynchronised_gbs_total=float(ps[3]), e2e_d2h_gbs=e2e_v * (52 + (8 if fp64 else 4) + 1) / 1e9)
         if l2free:
             line["extra"]["step_kernels_beyond_l2"] = l2free
