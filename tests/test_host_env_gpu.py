@@ -124,3 +124,18 @@ def test_sb3_vecenv_subclass_against_a_stub_base_class():
         np.testing.assert_array_equal(o, po)
     venv.close()
     plain.close()
+
+
+def test_host_copy_probe_reports_plausible_bandwidths():
+    """cantor_host_copy_probe: the raw copies of one host-buffer step, no kernel; argument validation on the host."""
+    from cantorrl_b200 import _lib
+    from cantorrl_b200.host_env import host_copy_probe
+    r = host_copy_probe(device=0, d2h_bytes=57 << 18, h2d_bytes=8 << 18, n_chunks=4, sync_each_round=True, seconds=0.1)
+    assert 1.0 < r["d2h_gbs"] < 200.0 and 0.1 < r["h2d_gbs"] < 200.0 and r["rounds_per_s"] > 10
+    assert abs(r["d2h_gbs"] / r["h2d_gbs"] - 57 / 8) < 1e-6
+    one_way = host_copy_probe(device=0, d2h_bytes=1 << 24, h2d_bytes=0, n_chunks=1, sync_each_round=False, seconds=0.05)
+    assert one_way["h2d_gbs"] == 0.0 and one_way["d2h_gbs"] > 1.0
+    with pytest.raises(_lib.CantorError):
+        host_copy_probe(device=0, d2h_bytes=0, h2d_bytes=0)
+    with pytest.raises(_lib.CantorError):
+        host_copy_probe(device=99, d2h_bytes=1 << 20, h2d_bytes=0)
