@@ -14,9 +14,10 @@ Episode ``e`` of global env ``g`` runs on path ``(e * total_envs + g) % n_paths`
 ``cantorrl_b200/csrc/rollout.cu`` -- so a population sharded over ranks visits the same paths.
 
 Parity status: the env step and the two delta policies are PINNED (see hedge_oracle.py / policy_oracle.py); the
-uniform-action stream is pinned by the Random123 known-answer vectors of ``sim_oracle.philox4x32_10``; the MLP
-has no reference golden vector (the reference's actor runs inside SB3/torch) -- "parity unpinned" for it, it is
-checked against this plain float32 restatement only.
+uniform-action stream is pinned by the Random123 known-answer vectors of ``sim_oracle.philox4x32_10``; the recurrent
+actor is PINNED on ``tests/golden/lstm_golden.npz`` and the plain MLP on ``tests/golden/mlp_golden.npz`` -- both produced by
+the reference's own network modules (quantconnect/model_wrapper.py:167-204) with the shipped ``policy_weights.pth``
+(``tests/golden/make_golden.py --lstm-only / --mlp-only``; the MLP is the shipped head behind a fixed 13 -> 128 projection).
 """
 from __future__ import annotations
 
