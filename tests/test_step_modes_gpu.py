@@ -177,3 +177,56 @@ def test_float32_info_arrays_in_fp32_mode():
     assert torch.equal(i32["actual_calls_traded"], i64["actual_calls_traded"])
     d = i32[3]
     assert isinstance(d["cash"], np.float64) and d["loss_type_used"] == "abs"
+
+
+def test_step_many_edge_cases_single_step_ragged_tail_and_unaligned_slabs():
+    """n_steps = 1 (falls back to the per-step kernel), a 5-env population (no TMA: rows % 4 != 0), slabs whose per-step offset is
+    not 16-byte aligned (n_envs % 4 != 0), and an episode length of 1 (every step ends an episode)."""
+    from cantorrl_b200 import HedgingVecEnv, sim
+    for n, T in ((5, 3), (1001, 1), (130, 2)):
+        book = sim.generate_paths_and_options(17, n_steps=T, model="gbm", seed=8)
+        a, b = (HedgingVecEnv(data=book, num_envs=n, episode_sampler="philox", seed=2, **KW) for _ in range(2))
+        a.reset()
+        b.reset()
+        tape = _tape(7, n, n)
+        o1, r1, d1 = a.step_many(tape[:1])
+        o2, r2, d2 = a.step_many(tape[1:])
+        for t in range(7):
+            o, r, d, _ = b.step(tape[t])
+            want = (o1[0], r1[0], d1[0]) if t == 0 else (o2[t - 1], r2[t - 1], d2[t - 1])
+            assert torch.equal(o, want[0]) and torch.equal(r, want[1]) and torch.equal(d, want[2]), (n, T, t)
+        assert torch.equal(a._core, b._core)
+
+
+def test_v1_env_positional_call_of_the_reference_and_record_metrics_off_on_the_fly():
+    """src/agents/test_rand_ppo.py:26-27 calls the v1 class positionally: HedgingEnv(DATA_FILE, 0.05, 1.0, 0.0, 10000, 200) binds
+    loss_type=10000 (-> the abs formula, hedging_env.py:240-242) and initial_cash=200.  Same call here, same numbers as keywords."""
+    import os
+    import tempfile
+    from cantorrl_b200 import HedgingVecEnv, sim
+    book = sim.generate_paths_and_options(32, n_steps=6, model="gbm", seed=5)
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "book.npz")
+        book.save_npz(f)
+        pos = HedgingVecEnv(f, 0.05, 1.0, 0.0, 10000, 200, version="v1", num_envs=32, episode_sampler="same_path", precision="fp64")
+        kw = HedgingVecEnv(f, transaction_cost_per_contract=0.05, lambda_cost=1.0, pnl_penalty_weight=0.0, loss_type=10000,
+                           initial_cash=200, version="v1", num_envs=32, episode_sampler="same_path", precision="fp64")
+    assert pos.initial_cash == 200 and pos.loss_type == 10000 and pos.shares_held_fixed == 10000 and pos.slippage_bps == 0.0
+    pos.reset()
+    kw.reset()
+    a = _tape(1, 32, 4)[0]
+    o1, r1, d1, _ = pos.step(a)
+    o2, r2, d2, _ = kw.step(a)
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and float(pos.cash_balance.max()) <= 200.0
+    with pytest.raises(TypeError):
+        HedgingVecEnv(data=book, version="v1", theta_weight=1e-4)
+    # record_metrics=False zeroes obs[7:11] (hedging_env_v2.py:80-81) in the on-the-fly kernel as in the replay kernel
+    simkw = dict(model="gbm", seed=5, n_steps=6)
+    fly = HedgingVecEnv(simulate=simkw, num_envs=32, record_metrics=False, **KW)
+    rep = HedgingVecEnv(data=sim.generate_paths_and_options(32, n_steps=6, model="gbm", seed=5), num_envs=32, record_metrics=False,
+                        episode_sampler="same_path", **KW)
+    of, orp = fly.reset(), rep.reset()
+    assert torch.equal(of, orp) and float(of[:, 7:11].abs().max()) == 0.0
+    of, rf, _, _ = fly.step(a)
+    orp, rr, _, _ = rep.step(a)
+    assert torch.equal(of, orp) and torch.equal(rf, rr) and float(of[:, 7:11].abs().max()) == 0.0
