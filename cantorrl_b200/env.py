@@ -154,10 +154,16 @@ class VecInfo:
 class HedgingVecEnv:
     """``num_envs`` copies of the reference ``HedgingEnv`` stepped by one CUDA kernel per ``step``.
 
-    Reference keywords keep their names, order and defaults.  Additions (keyword-only):
+    Reference keywords keep their names, order and defaults -- positionally too, in the order of the chosen ``version``
+    (``bind_reference_arguments``).  Additions (keyword-only):
 
     num_envs         number of environments (SB3 ``VecEnv.num_envs``)
     data             a ``ReplayData`` or a dict with the npz keys, instead of ``data_file_path``
+    simulate         no data at all: ``dict(model="gbm" | "heston", seed=, n_steps=, s0=, v0=, kappa=, theta=, sigma_v=, rho=, r=, dt=,
+                     tenor=)`` -- the ON-THE-FLY mode (``cantor_env_step_sim``): every env carries {S, v} and the step kernel generates
+                     the day's move and the ATM marks itself, bit-identical to replaying the book ``sim.generate_paths_and_options``
+                     writes for the same parameters.  Episode e of global env g runs global path ``e * total_envs + g``.
+    total_envs       global env population of a sharded on-the-fly run (default ``env_offset + num_envs``)
     precision        "fp32" (float cash/reward, 137 B per env-step) or "fp64" (the reference's exact
                      float32/float64 ledger: integers bit-exact, floats <= 1e-6 relative; 157 B)
     version          "v2" (default) or "v1" (commission default 0.05; slippage/theta must stay 0)
