@@ -132,6 +132,8 @@ class VecNormalize:
             self._fuse.gamma, self._fuse.norm_obs, self._fuse.norm_reward = self.gamma, int(self.norm_obs), int(self.norm_reward)
             self.venv._state.vecnorm = self._fuse_ptr if fused else None
         obs, reward, done, infos = self.venv.step(actions)
+        if self._fuse is not None:
+            self.venv._state.vecnorm = None     # a direct venv.step / step_many by the caller must not pay for (or trip over) the moments
         if self.keep_original:
             self.old_obs, self.old_reward = obs.clone(), reward.clone()
         term = infos["terminal_observation"] if hasattr(infos, "__getitem__") else None
