@@ -39,6 +39,9 @@
 #ifndef CANTOR_OBS_EVICT_FIRST        // observation tiles leave through L2 with an evict-first policy: they are never re-read by
 #define CANTOR_OBS_EVICT_FIRST 1      // the env, and must not displace the state / path rows that the next launch re-reads
 #endif                                // (2^20 envs: 21.25 -> 18.05 us per launch; no effect once nothing fits L2: 174 vs 171 us at 2^23).
+#ifndef CANTOR_STEP_MON_BLOCKS        // resident CTAs per SM of the fp32 Monitor variants (statistics formed lazily: no float64 accumulators live
+#define CANTOR_STEP_MON_BLOCKS 12     // across the step body); 2^20 envs, step + Monitor + statistics: 8 / 10 / 12 CTAs -> 24.0 / 23.4 / 22.5 us
+#endif
 #ifndef CANTOR_MANY_MIN_BLOCKS
 #define CANTOR_MANY_MIN_BLOCKS 10     // persistent multi-step kernel: 48 registers, two 6.5 KB observation tiles per CTA
 #endif                                // (2^20 envs x 252 steps: 8 CTAs / SM 3.94 ms, 10: 3.78 ms, 12: 3.76 ms with spills, 16: 4.85 ms)
@@ -238,7 +241,7 @@ template <bool F64, bool INFO, bool MON, bool SHARE>
 __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const float2 a, const float4& prev, const float4& cur,
                                           const Greeks& g_cur, float* __restrict__ o, long long i, long long n_envs,
                                           void* __restrict__ reward_slot, const InfoOut& info, const Monitor& mon,
-                                          double (&stat)[11], bool& finished_episode, double* reward_out = nullptr) {
+                                          float4& fin_acc, bool& finished_episode, double* reward_out = nullptr) {
     const int pos_c = e.pos_c, pos_p = e.pos_p;
     const bool already_done = e.step >= k.T;                                  // only reachable with auto_reset = 0
     const int t_prev = already_done ? k.T - 1 : e.step;
@@ -303,8 +306,8 @@ __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const
             if (terminated) {
                 if (mon.episode_return != nullptr) reinterpret_cast<double*>(mon.episode_return)[i] = a0.x;
                 if (mon.episode_length != nullptr) mon.episode_length[i] = t_new;
-                if (mon.stats.sums != nullptr) {
-                    episode_statistics(stat, (float)a0.x, (float)a0.y, (float)a1.x, (float)a1.y, k.inv_T_f, mon.stats);
+                if (mon.stats.sums != nullptr) {                               // the caller turns these four sums into the statistics
+                    fin_acc = make_float4((float)a0.x, (float)a0.y, (float)a1.x, (float)a1.y);
                     finished_episode = true;
                 }
                 a0 = make_double2(0.0, 0.0);
@@ -348,7 +351,7 @@ __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const
                 if (mon.episode_return != nullptr) reinterpret_cast<float*>(mon.episode_return)[i] = m.x;
                 if (mon.episode_length != nullptr) mon.episode_length[i] = t_new;
                 if (mon.stats.sums != nullptr) {
-                    episode_statistics(stat, m.x, m.y, m.z, m.w, k.inv_T_f, mon.stats);
+                    fin_acc = m;
                     finished_episode = true;
                 }
                 m = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -418,11 +421,28 @@ __device__ __forceinline__ void monitor_epilogue(const Monitor& mon, double (&st
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(mon.stats.sums + 11, env_steps);
     push_statistics_to_all_ranks<THREADS>(mon.stats);
 }
+// One-step kernels: an env finishes at most one episode per launch, so the eleven float64 statistics are formed HERE, inside the
+// (block-uniform, rare) branch, from the four sums the step body handed back -- they are not live across the step body, which keeps
+// the Monitor variants' registers down.
+template <int THREADS>
+__device__ __forceinline__ void monitor_epilogue_one_step(const Monitor& mon, const StepConsts& k, const float4& fin_acc,
+                                                          bool finished_episode, double* red, double env_steps) {
+    if (mon.stats.sums == nullptr) return;
+    if (__syncthreads_or(finished_episode)) {
+        double stat[11];
+#pragma unroll
+        for (int s = 0; s < 11; ++s) stat[s] = 0.0;
+        if (finished_episode) episode_statistics(stat, fin_acc.x, fin_acc.y, fin_acc.z, fin_acc.w, k.inv_T_f, mon.stats);
+        block_accumulate<11, THREADS>(stat, mon.stats.sums, red);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(mon.stats.sums + 11, env_steps);
+    push_statistics_to_all_ranks<THREADS>(mon.stats);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Gym-style step, replay mode: one launch = one env-step.
 template <bool F64, bool INFO, bool MON, bool VN>
-__global__ void __launch_bounds__(kStepThreads, (MON || INFO || F64) ? 8 : (VN ? 12 : CANTOR_STEP_MIN_BLOCKS))   // VN alone: 40 registers
+__global__ void __launch_bounds__(kStepThreads, (INFO || F64) ? 8 : (MON ? CANTOR_STEP_MON_BLOCKS : (VN ? 12 : CANTOR_STEP_MIN_BLOCKS)))   // VN alone: 40 registers
 hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                   double* __restrict__ pv_arr, long long n_envs, const float2* __restrict__ actions,
                   float* __restrict__ obs, void* __restrict__ reward_arr, unsigned char* __restrict__ done_arr,
@@ -432,12 +452,8 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
     __shared__ double red[MON ? 11 * (kStepThreads / 32) : 1];
     __shared__ double vn_scratch[VN ? 2 * 8 * CANTOR_OBS_DIM + 2 * (kStepThreads / 32) : 1];
     double my_reward = 0.0, ret_prev = 0.0;
-    double stat[11];
+    float4 fin_acc = make_float4(0.f, 0.f, 0.f, 0.f);
     bool finished_episode = false;                                            // MON: this thread's env just ended an episode
-    if (MON) {
-#pragma unroll
-        for (int s = 0; s < 11; ++s) stat[s] = 0.0;
-    }
     const long long first_env = (long long)blockIdx.x * kStepThreads;
     const long long i = first_env + threadIdx.x;
     const int rows = (int)min((long long)kStepThreads, n_envs - first_env);
@@ -460,7 +476,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         const Greeks none{0.f, 0.f, 0.f};
         const size_t rb = F64 ? sizeof(double) : sizeof(float);
         const bool terminated = step_body<F64, INFO, MON, false>(k, e, a, prev, cur, none, o, i, n_envs,
-                                                                 (char*)reward_arr + i * rb, info, mon, stat, finished_episode,
+                                                                 (char*)reward_arr + i * rb, info, mon, fin_acc, finished_episode,
                                                                  VN ? &my_reward : nullptr);
 #if CANTOR_STEP_PREFETCH
         // the next step of this env reads rows `step` (just read: L2-resident) and `step + 1` (new): start that DRAM read now
@@ -481,7 +497,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
     if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch);
-    if (MON) monitor_epilogue<kStepThreads>(mon, stat, finished_episode, red, (double)n_envs);
+    if (MON) monitor_epilogue_one_step<kStepThreads>(mon, k, fin_acc, finished_episode, red, (double)n_envs);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -551,8 +567,14 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
             }
 #endif
             const int path = e.path;
+            float4 fin_acc;
+            bool fin_now = false;
             terminated = step_body<F64, false, MON, false>(k, e, a, prev, cur, none, o, i, n_envs, (char*)reward_arr + at * rb,
-                                                           no_info, mon, stat, finished_episode);
+                                                           no_info, mon, fin_acc, fin_now);
+            if (MON && fin_now) {                                             // several episodes can end inside one launch: accumulate
+                episode_statistics(stat, fin_acc.x, fin_acc.y, fin_acc.z, fin_acc.w, k.inv_T_f, mon.stats);
+                finished_episode = true;
+            }
             if (terminated) {
                 if (terminal_obs != nullptr) write_terminal_obs(terminal_obs, i, o);
                 const int next = next_episode_path(rr, b, i, path, rr.episode_counter + s);
@@ -666,12 +688,8 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
     __shared__ double red[MON ? 11 * (kStepThreads / 32) : 1];
     __shared__ double vn_scratch[VN ? 2 * 8 * CANTOR_OBS_DIM + 2 * (kStepThreads / 32) : 1];
     double my_reward = 0.0, ret_prev = 0.0;
-    double stat[11];
+    float4 fin_acc = make_float4(0.f, 0.f, 0.f, 0.f);
     bool finished_episode = false;
-    if (MON) {
-#pragma unroll
-        for (int s = 0; s < 11; ++s) stat[s] = 0.0;
-    }
     const long long first_env = (long long)blockIdx.x * kStepThreads;
     const long long i = first_env + threadIdx.x;
     const int rows = (int)min((long long)kStepThreads, n_envs - first_env);
@@ -720,10 +738,10 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
         bool terminated;
         if (!F64 && share_quote)
             terminated = step_body<F64, INFO, MON, true>(k, e, a, prev, cur, g_cur, o, i, n_envs, (char*)reward_arr + i * rb, info,
-                                                         mon, stat, finished_episode, VN ? &my_reward : nullptr);
+                                                         mon, fin_acc, finished_episode, VN ? &my_reward : nullptr);
         else
             terminated = step_body<F64, INFO, MON, false>(k, e, a, prev, cur, g_cur, o, i, n_envs, (char*)reward_arr + i * rb, info,
-                                                          mon, stat, finished_episode, VN ? &my_reward : nullptr);
+                                                          mon, fin_acc, finished_episode, VN ? &my_reward : nullptr);
         if (!terminated || auto_reset) sv = make_float2(S, v);                // a finished env without auto-reset stays at day T - 1
         if (terminated) {
             if (terminal_obs != nullptr) write_terminal_obs(terminal_obs, i, o);
@@ -744,7 +762,7 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
     if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch);
-    if (MON) monitor_epilogue<kStepThreads>(mon, stat, finished_episode, red, (double)n_envs);
+    if (MON) monitor_epilogue_one_step<kStepThreads>(mon, k, fin_acc, finished_episode, red, (double)n_envs);
 }
 
 // ---------------------------------------------------------------------------------------------------
