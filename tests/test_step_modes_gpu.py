@@ -230,3 +230,41 @@ def test_v1_env_positional_call_of_the_reference_and_record_metrics_off_on_the_f
     of, rf, _, _ = fly.step(a)
     orp, rr, _, _ = rep.step(a)
     assert torch.equal(of, orp) and torch.equal(rf, rr) and float(of[:, 7:11].abs().max()) == 0.0
+
+
+def test_full_shard_size_the_three_step_forms_agree():
+    """BASELINE configs[3] per-GPU shard (2^23 envs, 34 GB simulated book): a whole 252-step episode stepped by the on-the-fly kernel
+    (no book) and by the replay kernel gives identical rewards / dones / final observations, and a 6-step action tape through the
+    persistent kernel equals the same six steps launched one by one."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80 * 2 ** 30:
+        pytest.skip("needs ~60 GB of free HBM")
+    from cantorrl_b200 import HedgingVecEnv, sim
+    n, T = 1 << 23, 252
+    kw = dict(slippage_bps=1.0, theta_weight=2e-4, pnl_penalty_weight=1e-3, lambda_cost=1e-4)
+    book = sim.generate_paths_and_options(n, n_steps=T, model="gbm", seed=42)
+    replay = HedgingVecEnv(data=book, num_envs=n, episode_sampler="same_path", **kw)
+    fly = HedgingVecEnv(simulate=dict(model="gbm", seed=42, n_steps=T), num_envs=n, total_envs=n, **kw)
+    assert torch.equal(replay.reset(), fly.reset())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = [torch.rand((n, 2), device="cuda", generator=g) * 2 - 1 for _ in range(4)]
+    for t in range(T):
+        o_r, r_r, d_r, _ = replay.step(acts[t & 3])
+        o_f, r_f, d_f, _ = fly.step(acts[t & 3])
+        if t in (0, 1, 100, T - 2, T - 1):
+            assert torch.equal(r_r, r_f) and torch.equal(d_r, d_f), t
+            if t < T - 1:                       # after the last step the two envs start different second episodes
+                assert torch.equal(o_r, o_f), t
+        assert bool(d_f.any()) == (t == T - 1)
+    assert int(fly.current_episode_idx.min()) == 1 and int(replay.current_step.max()) == 0
+    del fly
+    torch.cuda.empty_cache()
+    other = HedgingVecEnv(data=book, num_envs=n, episode_sampler="same_path", **kw)
+    other.reset()
+    replay.reset()
+    tape = torch.stack([acts[j & 3] for j in range(6)]).contiguous()
+    o_m, r_m, d_m = other.step_many(tape)
+    for t in range(6):
+        o, r, d, _ = replay.step(tape[t])
+        assert torch.equal(r, r_m[t]) and torch.equal(d, d_m[t]) and torch.equal(o, o_m[t]), t
+    assert torch.equal(other._core, replay._core) and torch.equal(other._cash, replay._cash)
