@@ -39,6 +39,9 @@
 #ifndef CANTOR_OBS_EVICT_FIRST        // observation tiles leave through L2 with an evict-first policy: they are never re-read by
 #define CANTOR_OBS_EVICT_FIRST 1      // the env, and must not displace the state / path rows that the next launch re-reads
 #endif                                // (2^20 envs: 21.25 -> 18.05 us per launch; no effect once nothing fits L2: 174 vs 171 us at 2^23).
+#ifndef CANTOR_STEP_VN_BLOCKS         // resident CTAs per SM of the fp32 step kernel that also produces VecNormalize's moments (40 registers)
+#define CANTOR_STEP_VN_BLOCKS 12
+#endif
 #ifndef CANTOR_STEP_MON_BLOCKS        // resident CTAs per SM of the fp32 Monitor variants (statistics formed lazily: no float64 accumulators live
 #define CANTOR_STEP_MON_BLOCKS 12     // across the step body); 2^20 envs, step + Monitor + statistics: 8 / 10 / 12 CTAs -> 24.0 / 23.4 / 22.5 us
 #endif
@@ -442,7 +445,7 @@ __device__ __forceinline__ void monitor_epilogue_one_step(const Monitor& mon, co
 // ---------------------------------------------------------------------------------------------------
 // Gym-style step, replay mode: one launch = one env-step.
 template <bool F64, bool INFO, bool MON, bool VN>
-__global__ void __launch_bounds__(kStepThreads, (INFO || F64) ? 8 : (MON ? CANTOR_STEP_MON_BLOCKS : (VN ? 12 : CANTOR_STEP_MIN_BLOCKS)))   // VN alone: 40 registers
+__global__ void __launch_bounds__(kStepThreads, (INFO || F64) ? 8 : (MON ? CANTOR_STEP_MON_BLOCKS : (VN ? CANTOR_STEP_VN_BLOCKS : CANTOR_STEP_MIN_BLOCKS)))
 hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                   double* __restrict__ pv_arr, long long n_envs, const float2* __restrict__ actions,
                   float* __restrict__ obs, void* __restrict__ reward_arr, unsigned char* __restrict__ done_arr,
