@@ -521,6 +521,7 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
 #pragma unroll
         for (int s = 0; s < 11; ++s) stat[s] = 0.0;
     }
+    pdl_wait_prior_grid();          // the state may come from a per-step launch, which releases its dependents before it finishes
     const long long first_env = (long long)blockIdx.x * kManyThreads;
     const long long i = first_env + threadIdx.x;
     const bool live = i < n_envs;

@@ -227,9 +227,31 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
             // on the fly, the greeks of this state came with its price one step ago (same r, tenor: share_quote)
             if (SRC != 0 && share_quote) make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y, gk);
             else make_observation_f32(o, k, cur.x, cur.y, cur.z, cur.w, inv_s0, pos_c, pos_p, t, prev.x, prev.y);
+            // ---- next path record: does not depend on the action.  The recurrent actor computes it between its gate phase and its head
+            // (under the head's first product, where the thread would only wait); the other policies after the action, as before.
+            float4 nxt;
+            auto next_record = [&]() {
+                if (SRC == 0) {
+                    nxt = live ? __ldcs(b.rec + ((long long)(t + 1) * b.ld + (long long)(gp % (unsigned long long)b.n_paths))) : cur;
+                } else {
+                    sim_advance<MODEL>(sk, S, v, z[NPS * j], z[NPS * j + NPS - 1]);
+                    nxt.x = S;
+                    nxt.y = fmaxf(v, 0.f);
+                    nxt.z = cur.z;
+                    nxt.w = cur.w;                                                 // stale marks at the terminal step (:226-231)
+                    if (t + 1 < k.T) {
+                        const AtmQuote q = atm_quote_f32(nxt.x, nxt.y, sk);
+                        nxt.z = q.call;
+                        nxt.w = q.put;
+                        gk = q.g;
+                    }
+                }
+            };
             float2 a;
             if (MLP == 3) {
-                a = lstm.forward(o);                                           // CTA-collective; carries h, c across steps
+                lstm.forward_gates(o);                                         // CTA-collective; carries h, c across steps
+                next_record();
+                a = lstm.forward_head();
             } else if (MLP == 2) {
                 a = actor.forward(o);                                          // CTA-collective: all 128 threads, every step
             } else if (MLP == 1) {
@@ -248,23 +270,7 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                 else a = make_float2(fminf(fmaxf(a.x, -1.f), 1.f), fminf(fmaxf(a.y, -1.f), 1.f));   // SB3: clip to the Box
             }
             if (pc.put_disabled) a.y = 0.f;
-            // ---- next path record -------------------------------------------------------------------------
-            float4 nxt;
-            if (SRC == 0) {
-                nxt = live ? __ldcs(b.rec + ((long long)(t + 1) * b.ld + (long long)(gp % (unsigned long long)b.n_paths))) : cur;
-            } else {
-                sim_advance<MODEL>(sk, S, v, z[NPS * j], z[NPS * j + NPS - 1]);
-                nxt.x = S;
-                nxt.y = fmaxf(v, 0.f);
-                nxt.z = cur.z;
-                nxt.w = cur.w;                                                 // stale marks at the terminal step (:226-231)
-                if (t + 1 < k.T) {
-                    const AtmQuote q = atm_quote_f32(nxt.x, nxt.y, sk);
-                    nxt.z = q.call;
-                    nxt.w = q.put;
-                    gk = q.g;
-                }
-            }
+            if (MLP != 3) next_record();
             // ---- fused hedge step ---------------------------------------------------------------------------
             const LedgerF32 L = ledger_f32(k, a.x, a.y, pos_c, pos_p, t, inv_s0, cur, nxt, false);
             const bool terminated = t + 1 >= k.T;
@@ -272,23 +278,43 @@ rollout_kernel(const StepConsts k, const Book b, const SimConsts sk, const Polic
                 float* orow = tile_row(threadIdx.x);
 #pragma unroll
                 for (int q = 0; q < CANTOR_OBS_DIM; ++q) orow[q] = o[q];
+                if (MLP == 3) {
+                    // the recurrent actor's groups are half a step apart: each group of 128 stores its own [128 x 13] piece behind its
+                    // own named barrier (ids 2 / 3, 128 threads), never waiting for the other group
+                    const int grp = threadIdx.x >> 7, m = threadIdx.x & 127;
+                    const int grows = max(0, min(rows - 128 * grp, 128));
+                    float* dst = out.obs + ((long long)g * n_envs + first_env + 128 * grp) * CANTOR_OBS_DIM;
+                    const bool tma = obs_tma_ok && (grows % 4 == 0) && ((((long long)g * n_envs) & 3) == 0);
+                    if (tma) fence_proxy_async_smem();
+                    lstmtc::group_sync(grp);
+                    if (tma) {
+                        if (m == 0 && grows > 0) {
+                            tma_store_1d_evict_first(dst, lstm.obs_staging(grp), (uint32_t)(grows * CANTOR_OBS_DIM * sizeof(float)));
+                            tma_store_commit();
+                            tma_store_wait_read();
+                        }
+                    } else {
+                        const float* src = lstm.obs_staging(grp);
+                        for (int q = m; q < grows * CANTOR_OBS_DIM; q += 128) dst[q] = src[q];
+                    }
+                    lstmtc::group_sync(grp);
+                } else {
                 float* dst = out.obs + ((long long)g * n_envs + first_env) * CANTOR_OBS_DIM;
                 const bool tma = obs_tma_ok && (rows % 4 == 0) && ((((long long)g * n_envs) & 3) == 0);
                 if (tma) {
                     fence_proxy_async_smem();
                     env_sync();
                     if (threadIdx.x == 0) {
-                        for (int r0 = 0; r0 < rows; r0 += kRollThreads)                        // one piece (MLP == 3: one per group)
-                            tma_store_1d_evict_first(dst + r0 * CANTOR_OBS_DIM, tile_row(r0),
-                                                     (uint32_t)((MLP == 3 ? min(rows - r0, kRollThreads) : rows) * CANTOR_OBS_DIM * sizeof(float)));
+                        tma_store_1d_evict_first(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
                         tma_store_commit();
                         tma_store_wait_read();
                     }
                     env_sync();
                 } else {
                     env_sync();
-                    for (int q = threadIdx.x; q < rows * CANTOR_OBS_DIM; q += kEnv) dst[q] = tile_row(q / CANTOR_OBS_DIM)[q % CANTOR_OBS_DIM];
+                    for (int q = threadIdx.x; q < rows * CANTOR_OBS_DIM; q += kEnv) dst[q] = tile[q];
                     env_sync();
+                }
                 }
                 if (live) {
                     const long long at = (long long)g * n_envs + i;

@@ -84,13 +84,15 @@ def pack_lstm(w_ih, w_hh, b_ih, b_hh, W1, b1, W2, b2, W3, b3, obs_mean=None, obs
     bias = f(b_ih, (512,)) + f(b_hh, (512,))
     W1, b1, W2, b2, W3, b3 = f(W1, (64, 128)), f(b1, (64,)), f(W2, (64, 64)), f(b2, (64,)), f(W3, (2, 64)), f(b3, (2,))
     parts = []
-    for p in range(4):                                                # pass p = hidden units 32 p .. 32 p + 31, rows {i, f, g, o} x 32
-        tile = np.zeros((128, 144), np.float32)
+    for q in range(8):                                                # half-pass q = hidden units 16 q .. 16 q + 15, rows {i, f, g, o} x 16
+        tile = np.zeros((64, 144), np.float32)
         for g in range(4):
-            rows = slice(g * 128 + 32 * p, g * 128 + 32 * p + 32)
-            tile[g * 32:(g + 1) * 32, 0:13] = w_ih[rows]
-            tile[g * 32:(g + 1) * 32, 13] = bias[rows]
-            tile[g * 32:(g + 1) * 32, 16:144] = w_hh[rows]
+            rows = slice(g * 128 + 16 * q, g * 128 + 16 * q + 16)
+            tile[g * 16:(g + 1) * 16, 0:13] = w_ih[rows]
+            tile[g * 16:(g + 1) * 16, 13] = bias[rows]
+            tile[g * 16:(g + 1) * 16, 16:144] = w_hh[rows]
+            if g != 2:                                                # sigmoid gates: the kernel evaluates 0.5 + 0.5 tanh(x / 2), and the
+                tile[g * 16:(g + 1) * 16] *= 0.5                      # halving is done here (a power of two: exact in bf16)
         parts.append(_umma_tile(tile))
     t1 = np.zeros((64, 144), np.float32)
     t1[:, 13], t1[:, 16:144] = b1, W1

@@ -358,7 +358,9 @@ enum {
                                             reference trained (quantconnect/model_wrapper.py:167-204); cantor_policy.mlp = the
                                             CANTOR_LSTM_IMAGE_BYTES weight image (cantorrl_b200/rollout.py: pack_lstm) */
 };
-#define CANTOR_LSTM_IMAGE_BYTES 178816   /* 4 gate tiles [128 x 144] + W1 [64 x 144] + W2 [64 x 80] + W3 [16 x 80] bf16 + mean / inv_std */
+#define CANTOR_LSTM_IMAGE_BYTES 178816   /* 4 gate tiles [128 x 144] + W1 [64 x 144] + W2 [64 x 80] + W3 [16 x 80] bf16 + mean / inv_std;
+                                            the i / f / o rows of the gate tiles hold HALF the torch.nn.LSTM weights and biases
+                                            (sigmoid(x) is evaluated as 0.5 + 0.5 tanh(x / 2); pack_lstm does the halving) */
 #define CANTOR_MLP_FLOATS 5212           /* W1[13][64] b1[64] W2[64][64] b2[64] W3[64][2] b3[2] obs_mean[13] obs_inv_std[13] */
 typedef struct cantor_policy {
     int32_t kind;                        /* CANTOR_POLICY_* */

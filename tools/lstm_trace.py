@@ -34,15 +34,11 @@ t0 = ev[0][0]
 names = {1: "forward in", 2: "x published", 30: "h published", 31: "L1 done", 32: "a2 published", 33: "L2 done", 34: "a2 published", 35: "L3 done"}
 for t, a, tag in ev:
     if a < 2:
-        n = names.get(tag) or (f"pass {tag - 10} MMA seen" if 10 <= tag < 20 else f"epilogue {tag - 20} done")
+        n = names.get(tag) or (f"product {tag - 10} seen" if 10 <= tag < 20 else f"epilogue {tag - 20} done")
     else:
-        if 100 <= tag < 140:
-            p, r = divmod(tag - 100, 10)
-            n = f"issue pass {p} grp {r % 5}" + (" ready" if r < 5 else " issued")
-        elif 140 <= tag < 150:
-            n = f"pass {tag - 140} grp 0 complete"
-        elif 150 <= tag < 160:
-            n = f"pass {tag - 150} grp 1 complete"
+        if 100 <= tag < 120:
+            q, r = divmod(tag - 100, 2)
+            n = f"gate product {q}" + (" issued" if r else " ready")
         else:
-            n = f"L1 grp {tag - 160} ready"
+            n = f"head layer {tag - 119} ready"
     print(f"{t - t0:8d}  {'  ' * 20 * a}{['G0', 'G1', 'IS'][a]} {n}")
