@@ -34,6 +34,12 @@
 #pragma once
 #include "mlp_tc.cuh"
 
+#ifndef CANTOR_LSTM_HEAD_FIRST
+#define CANTOR_LSTM_HEAD_FIRST 0         // issuer: a head layer that is ready when its slot starts goes before the slot's gate product
+#endif                                   // (measured: 64.1 -> 67.5 ms -- it delays the gate product the other group's epilogue chain waits for)
+#ifndef CANTOR_LSTM_SLOT0_REFILL_LATE
+#define CANTOR_LSTM_SLOT0_REFILL_LATE 0  // issuer: slot 0 requests the next weight tile after its gate product, not before
+#endif                                   // (measured: 64.1 -> 67.6 ms, both: 68.7 -- the tile then lands late for slot 1)
 #ifndef CANTOR_LSTM_FULL_LOAD_PASSES
 #define CANTOR_LSTM_FULL_LOAD_PASSES 0   // the first n passes of a step read all 128 gate columns before any arithmetic (the h_t backlog is
 #endif                                   // still small enough for 128 + 16 input registers); the others release after the second half's load.
@@ -260,7 +266,7 @@ struct Actor {
     // something issued earlier in this fixed order, so the order cannot deadlock.
     //   slot p:  refill                 the buffer of product p - 1 (complete by now) with the tile of product p + 1
     //            gate product p of GA   <- weight tile p landed; x rows published (p = 0) / gate columns of p - 1 read (p >= 1)
-    //            head layer p + 1 of GB <- h rows published (L1) / A2 rows published (L2, L3)            (p < 3)
+    //            head layer p + 1 of GB <- h rows published (L1) / A2 rows published (L2, L3)            (p < 3; first if ready first)
     template <int GA>
     __device__ __forceinline__ void half_cycle(Issuer& I, bool gates_on, bool head_on, bool x_only, bool first) {
         constexpr int GB = GA ^ 1;
@@ -270,16 +276,45 @@ struct Actor {
         const bool trace_on = I.trace_on;
         int& tr_n = I.tr_n;
 #endif
+        auto ready = [](uint32_t bar, uint32_t phase) {                                              // non-blocking look at a barrier
+            uint32_t done;
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+            return done != 0;
+        };
 #pragma unroll
         for (int p = 0; p < kPasses; ++p) {
             const int buf = p % kWgBufs;
-            // first of all the refill: the tile of product p + 1 into the buffer of product p - 1 (issued a whole slot ago: complete), so
-            // that the copy has this whole slot to land
-            if (gates_on && !(first && p == 0)) {
-                const int r = buf ^ 1;                                                               // buffer of the previous product
-                wait_on(B + 8 * (kBarWfree + r), I.ph_wfree[r], I.to);
-                if (elect_one()) tma_load_1d(I.wg_s[r], I.image + kImgGate + ((p + 1) % kPasses) * kWgBytes, kWgBytes, B + 8 * (kBarW + r));
+            auto refill = [&]() {                       // the tile of product p + 1 into the buffer of product p - 1, once that product is complete
+                if (gates_on && !(first && p == 0)) {
+                    const int r = buf ^ 1;
+                    wait_on(B + 8 * (kBarWfree + r), I.ph_wfree[r], I.to);
+                    if (elect_one()) tma_load_1d(I.wg_s[r], I.image + kImgGate + ((p + 1) % kPasses) * kWgBytes, kWgBytes, B + 8 * (kBarW + r));
+                    __syncwarp();
+                }
+            };
+            auto head_layer = [&]() {
+                mlptc::fence_after_sync();
+                LSTM_TR(2, 120 + p);
+                if (elect_one()) {
+                    const uint32_t d = I.tm + kColGates + kGroupCols * GB;
+                    if (p == 0) mlptc::umma_batch<kKA / 16>(I.d_a[GB], I.d_w1, idesc_h, d);
+                    else if (p == 1) mlptc::umma_batch<kK2 / 16>(I.d_a2[GB], I.d_w2, idesc_h, d);
+                    else mlptc::umma_batch<kK2 / 16>(I.d_a2[GB], I.d_w3, idesc_o, d + kColHeadOut);
+                    mlptc::umma_commit(B + 8 * (kBarH + GB));
+                }
                 __syncwarp();
+            };
+            const bool head_slot = head_on && p < 3;
+            const uint32_t head_bar = B + 8 * ((p == 0 ? kBarHready : kBarA2) + GB);
+            uint32_t& head_phase = p == 0 ? I.ph_hready[GB] : I.ph_a2[GB];
+            // the refill first, so that the copy has this whole slot to land
+            if (p != 0 || !CANTOR_LSTM_SLOT0_REFILL_LATE) refill();
+            bool head_done = !head_slot;
+            if (CANTOR_LSTM_HEAD_FIRST && head_slot && ready(head_bar, head_phase)) {                   // the short head layer goes first when it is ready first
+                head_phase ^= 1;
+                head_layer();
+                head_done = true;
             }
             if (gates_on) {
                 wait_on(B + 8 * (kBarW + buf), I.ph_w[buf], I.to);
@@ -297,20 +332,11 @@ struct Actor {
                 __syncwarp();
                 LSTM_TR(2, 101 + 2 * p);
             }
-            if (head_on && p < 3) {
-                if (p == 0) wait_on(B + 8 * (kBarHready + GB), I.ph_hready[GB], I.to);               // h_t rows in the A tile, gate columns read
-                else wait_on(B + 8 * (kBarA2 + GB), I.ph_a2[GB], I.to);
-                mlptc::fence_after_sync();
-                LSTM_TR(2, 120 + p);
-                if (elect_one()) {
-                    const uint32_t d = I.tm + kColGates + kGroupCols * GB;
-                    if (p == 0) mlptc::umma_batch<kKA / 16>(I.d_a[GB], I.d_w1, idesc_h, d);
-                    else if (p == 1) mlptc::umma_batch<kK2 / 16>(I.d_a2[GB], I.d_w2, idesc_h, d);
-                    else mlptc::umma_batch<kK2 / 16>(I.d_a2[GB], I.d_w3, idesc_o, d + kColHeadOut);
-                    mlptc::umma_commit(B + 8 * (kBarH + GB));
-                }
-                __syncwarp();
+            if (!head_done) {
+                wait_on(head_bar, head_phase, I.to);                           // L1: h_t rows in the A tile, gate columns read; L2 / L3: A2 rows
+                head_layer();
             }
+            if (p == 0 && CANTOR_LSTM_SLOT0_REFILL_LATE) refill();
         }
     }
 
