@@ -261,37 +261,79 @@ def _config(args, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled WHILE the timed region runs (B200_PROFILING.md's clocks line).  Polls NVML in-process
+    every few milliseconds (the timed region of the default run is ~75 ms: a freshly spawned `nvidia-smi -lms` often delivers its
+    first row after that); falls back to the nvidia-smi subprocess when pynvml is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.nvml, self.thread, self.stop_flag = [], None, gpu_index, None, None, False
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip() != ""]
+        if ids and all(x.strip().isdigit() for x in ids) and self.idx < len(ids):
+            return int(ids[self.idx])
+        return self.idx
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                    pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        self.rows.append([sm, mx, pw] + [bool(r & b) for b in bits])
+                    except pynvml.NVMLError:
+                        pass
+                    time.sleep(0.004)
+            self.nvml, self.source = pynvml, "nvml"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:                       # noqa: BLE001 -- any NVML problem: use the command-line tool instead
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            if len(r) == 7 and r[0].replace(".", "").isdigit() and r[1].replace(".", "").isdigit():
+                pw = float(r[2]) if r[2].replace(".", "").isdigit() else float("nan")
+                self.rows.append([float(r[0]), float(r[1]), pw] + [r[3 + j].lower() == "active" for j in range(4)])
 
     def stop(self):
-        if self.proc is None:
+        if self.nvml is None and self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.06)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) == 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) == 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[j] for r in self.rows if len(r) == 7 for j in range(4) if r[3 + j].lower() == "active"})
-        pw = [float(r[2]) for r in self.rows if len(r) == 7 and r[2].replace(".", "").isdigit()]
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.06)
+            self.proc.terminate()
+        rows = list(self.rows)
+        sm, mx = [r[0] for r in rows], [r[1] for r in rows]
+        pw = [r[2] for r in rows if r[2] == r[2]]
+        reasons = sorted({self.NAMES[j] for r in rows for j in range(4) if r[3 + j]})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=reasons)
+                    power_w_max=max(pw) if pw else None, samples=len(sm), reasons=reasons, source=self.source)
 
 
 def synth_replay_data(n, T, rank, device):
