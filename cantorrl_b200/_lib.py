@@ -171,6 +171,7 @@ SIGNATURES = {
     "cantor_host_unregister": (C.c_int, [C.c_void_p]),
     "cantor_host_copy_probe": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double,
                                          C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cantor_umma_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cantor_env_reset": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cantor_env_step": (C.c_int, [C.POINTER(EnvParams), C.POINTER(ReplayBook), C.POINTER(EnvState), C.c_int64,

@@ -440,6 +440,112 @@ extern "C" int cantor_rollout(const cantor_env_params* params, const cantor_repl
     return check_launch("rollout_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// cantor_umma_probe: what ONE tcgen05.mma (cta_group::1, kind::f16, bf16 operands, M = 128, K = 16) costs on this part as a function
+// of N and of where the A operand lives -- the number the two tensor-core actors are designed around.  One CTA per SM,
+// one thread issues `reps` back-to-back K-loops of `k_steps` MMAs into one accumulator and waits for the commit.
+namespace cantor {
+__global__ void __launch_bounds__(128) umma_probe_kernel(int n, int k_steps, int reps, int a_in_tmem, long long* out) {
+    extern __shared__ __align__(1024) unsigned char probe_smem[];
+    __shared__ __align__(8) unsigned long long bar_mem;
+    __shared__ unsigned tmem_slot;
+    const int a_bytes = 128 * 16 * k_steps * 2, b_bytes = n * 16 * k_steps * 2;
+    for (int j = threadIdx.x; j < (a_bytes + b_bytes) / 16; j += 128) reinterpret_cast<uint4*>(probe_smem)[j] = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t bar = mlptc::smem_u32(&bar_mem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(mlptc::smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    mlptc::fence_before_sync();
+    __syncthreads();
+    mlptc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    {   // tensor-memory columns [256, 256 + 8 k_steps): the A operand of the TS form (bf16 pairs; zeros)
+        uint32_t z = 0u;
+        for (int c = 0; c < 8 * k_steps; ++c)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(tmem + ((uint32_t)(threadIdx.x & 96) << 16) + 256 + c), "r"(z) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    mlptc::fence_before_sync();
+    __syncthreads();
+    mlptc::fence_after_sync();
+    if (threadIdx.x == 0) {
+        const int sbo = 2 * k_steps * 128;                                    // bytes between 8-row groups: K / 8 core matrices of 128 B
+        const uint64_t da0 = mlptc::smem_desc(mlptc::smem_u32(probe_smem), mlptc::kLbo, sbo);
+        const uint64_t db0 = mlptc::smem_desc(mlptc::smem_u32(probe_smem + a_bytes), mlptc::kLbo, sbo);
+        const uint32_t idesc = mlptc::instr_desc(128, n);
+        const long long t0 = clock64();
+        // straight-line batches (mlptc::umma_batch: descriptors stepped on the uniform datapath), as the actors issue them -- a rolled
+        // loop that rebuilds the descriptors per instruction costs ~120 clk per MMA in the ISSUING thread and hides the pipe's own rate
+#define PROBE_TS_STEP(ACC) "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], db, %3, " ACC ";\n\tadd.u32 ta, ta, 8;\n\tadd.s64 db, db, 16;\n\t"
+#define PROBE_TS_HEAD "{\n\t.reg .pred pt, pf;\n\t.reg .b32 ta;\n\t.reg .b64 db;\n\tsetp.eq.u32 pt, 0, 0;\n\tsetp.ne.u32 pf, 0, 0;\n\tmov.b32 ta, %1;\n\tmov.b64 db, %2;\n\t"
+        for (int r = 0; r < reps; ++r) {
+            if (a_in_tmem) {
+                if (k_steps == 1)
+                    asm volatile(PROBE_TS_HEAD PROBE_TS_STEP("pf") "}" :: "r"(tmem), "r"(tmem + 256), "l"(db0), "r"(idesc) : "memory");
+                else if (k_steps == 5)
+                    asm volatile(PROBE_TS_HEAD PROBE_TS_STEP("pf") PROBE_TS_STEP("pt") PROBE_TS_STEP("pt") PROBE_TS_STEP("pt") PROBE_TS_STEP("pt") "}"
+                                 :: "r"(tmem), "r"(tmem + 256), "l"(db0), "r"(idesc) : "memory");
+                else
+                    asm volatile(PROBE_TS_HEAD PROBE_TS_STEP("pf") PROBE_TS_STEP("pt") PROBE_TS_STEP("pt") PROBE_TS_STEP("pt") PROBE_TS_STEP("pt")
+                                 PROBE_TS_STEP("pt") PROBE_TS_STEP("pt") PROBE_TS_STEP("pt") PROBE_TS_STEP("pt") "}"
+                                 :: "r"(tmem), "r"(tmem + 256), "l"(db0), "r"(idesc) : "memory");
+            } else {
+                if (k_steps == 1) mlptc::umma_batch<1>(da0, db0, idesc, tmem);
+                else if (k_steps == 5) mlptc::umma_batch<5>(da0, db0, idesc, tmem);
+                else mlptc::umma_batch<9>(da0, db0, idesc, tmem);
+            }
+        }
+#undef PROBE_TS_STEP
+#undef PROBE_TS_HEAD
+        const long long t1 = clock64();
+        mlptc::umma_commit(bar);
+        uint32_t done = 0;
+        unsigned spins = 0;
+        while (!done && ++spins < (1u << 26))
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+        const long long t2 = clock64();
+        out[2 * blockIdx.x] = t1 - t0;                                        // issue
+        out[2 * blockIdx.x + 1] = done ? t2 - t0 : -1;                        // issue + completion
+    }
+    mlptc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+}  // namespace cantor
+
+extern "C" int cantor_umma_probe(int32_t n, int32_t k_steps, int32_t reps, int32_t a_in_tmem, int32_t n_ctas,
+                                 double* issue_clk_per_mma, double* total_clk_per_mma) {
+    CANTOR_REQUIRE(n >= 8 && n <= 256 && n % 16 == 0, "n must be a multiple of 16 in [16, 256]");
+    CANTOR_REQUIRE(k_steps == 1 || k_steps == 5 || k_steps == 9, "k_steps must be 1, 5 or 9 (the batch shapes the actors use)");
+    CANTOR_REQUIRE(reps >= 1 && n_ctas >= 1 && n_ctas <= 1024, "reps / n_ctas");
+    CANTOR_REQUIRE(issue_clk_per_mma && total_clk_per_mma, "output pointer is NULL");
+    const size_t smem = (size_t)(128 + n) * 16 * k_steps * 2;
+    cudaError_t e_ = cudaFuncSetAttribute(cantor::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e_ != cudaSuccess) return cantor::cuda_fail(e_, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    long long* out = nullptr;
+    CANTOR_CUDA(cudaMalloc(&out, sizeof(long long) * 2 * n_ctas));
+    // 120 KB of dynamic shared memory per CTA whatever the tile: one CTA per SM, like the actors that use all 512 TMEM columns
+    cantor::umma_probe_kernel<<<n_ctas, 128, smem > 120 * 1024 ? smem : 120 * 1024>>>(n, k_steps, reps, a_in_tmem, out);
+    long long* host = (long long*)malloc(sizeof(long long) * 2 * n_ctas);
+    cudaError_t e2 = cudaMemcpy(host, out, sizeof(long long) * 2 * n_ctas, cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    if (e2 != cudaSuccess) { free(host); return cantor::cuda_fail(e2, "umma_probe_kernel"); }
+    double issue = 0.0, total = 0.0;
+    bool ok = true;
+    for (int c = 0; c < n_ctas; ++c) { issue += (double)host[2 * c]; total += (double)host[2 * c + 1]; ok = ok && host[2 * c + 1] >= 0; }
+    free(host);
+    if (!ok) return cantor::fail(CANTOR_ERR_CUDA, "cantor_umma_probe: an MMA batch never completed");
+    *issue_clk_per_mma = issue / n_ctas / ((double)reps * k_steps);
+    *total_clk_per_mma = total / n_ctas / ((double)reps * k_steps);
+    return CANTOR_OK;
+}
+
 #ifdef LSTM_TRACE
 // debugging aid of variant builds: copies the recurrent actor's timestamp trace to the host (3 actors x 256 x {tag, clock})
 extern "C" int cantor_debug_lstm_trace(long long* out, int* counts) {

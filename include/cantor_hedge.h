@@ -457,6 +457,11 @@ int cantor_host_unregister(void* ptr);
  * the streams after every round like a gym step has to.  Runs for >= seconds; reports GB/s per direction and rounds/s. */
 int cantor_host_copy_probe(int32_t device, int64_t d2h_bytes, int64_t h2d_bytes, int32_t n_chunks, int32_t sync_each_round,
                            double seconds, double* d2h_gbs, double* h2d_gbs, double* rounds_per_s);
+/* Measurement aid of the tensor-core actors: clocks per tcgen05.mma (cta_group::1, kind::f16, bf16, M = 128, K = 16) at
+ * width n, issued as `reps` back-to-back K-loops of `k_steps` instructions by one thread of one CTA per SM (n_ctas CTAs);
+ * a_in_tmem = 0: both operands in shared memory (what the actors use), 1: A in tensor memory.  Synchronous; allocates a few bytes. */
+int cantor_umma_probe(int32_t n, int32_t k_steps, int32_t reps, int32_t a_in_tmem, int32_t n_ctas,
+                      double* issue_clk_per_mma, double* total_clk_per_mma);
 
 #ifdef __cplusplus
 }

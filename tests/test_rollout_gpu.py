@@ -298,3 +298,21 @@ def test_plain_mlp_policy_with_the_shipped_head_weights(policy, tol_max, tol_mea
     res2 = ro.run(n_steps, policy, mlp=pack_mlp(**w, obs_mean=l["obs_mean"], obs_var=l["obs_var"]), store=True)
     want2 = fn(res2.obs.cpu().numpy().reshape(-1, 13), **w, mean=l["obs_mean"], var=l["obs_var"]).reshape(act.shape)
     assert np.abs(res2.actions.cpu().numpy() - want2).max() < max(tol_max, 5e-5) * 3
+
+
+@pytest.mark.gpu
+def test_umma_probe_reports_the_math_floor_at_n_256():
+    """cantor_umma_probe (the measurement behind DESIGN section 4's tensor-core bounds): a 128 x 256 x 16 bf16 MMA cannot beat the pipe's
+    math floor of 128 clk, and narrow MMAs cost about the same per instruction whatever N."""
+    import ctypes as C
+    from cantorrl_b200 import _lib
+    L = _lib.lib()
+    out = {}
+    for n in (16, 64, 256):
+        i, t = C.c_double(), C.c_double()
+        _lib.check(L.cantor_umma_probe(n, 9, 16, 0, 4, C.byref(i), C.byref(t)), "cantor_umma_probe")
+        out[n] = t.value
+    assert 120.0 <= out[256] <= 200.0, out
+    assert 20.0 <= out[16] <= 110.0 and abs(out[16] - out[64]) <= 15.0, out
+    with pytest.raises(_lib.CantorError):
+        _lib.check(L.cantor_umma_probe(24, 9, 16, 0, 4, C.byref(i), C.byref(t)), "cantor_umma_probe")
