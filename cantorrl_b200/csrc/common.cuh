@@ -68,17 +68,29 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-inline int launch_pdl(const void* kernel, dim3 grid, dim3 block, cudaStream_t stream, void** args, size_t smem = 0) {
+// split cluster barrier: every thread of every CTA of the cluster arrives, later waits (all threads, converged warps)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// `cluster` > 1: thread-block clusters of that many CTAs along x (the grid must be a multiple of it)
+inline int launch_pdl(const void* kernel, dim3 grid, dim3 block, cudaStream_t stream, void** args, size_t smem = 0, unsigned cluster = 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (cluster > 1) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = cluster;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, args);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelExC");
     return CANTOR_OK;

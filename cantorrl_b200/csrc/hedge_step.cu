@@ -59,6 +59,15 @@
 #ifndef CANTOR_MANY_PREFETCH          // how many steps ahead the persistent kernel requests a step's action and path record (1 or 2).
 #define CANTOR_MANY_PREFETCH 1        // Measured (2^20 envs x 252 steps): 1 -> 3.695 ms, 2 -> 3.742 ms (same 48 registers): the first-use stalls
 #endif                                // are back-pressure of the memory system, not latency that deeper prefetch could hide.
+#ifndef CANTOR_MANY_WARP_STORES
+#define CANTOR_MANY_WARP_STORES 0     // 1: every warp stores its own 32 rows of the observation tile (one 1 664-byte bulk store behind a
+#endif                                // warp barrier): no CTA barrier in a step.  Measured: 3.743 ms against 3.658 (2^20 x 252) -- the four
+                                      // times smaller bulk stores cost more than the barrier; 12 CTAs/SM on top 3.87, prefetch 2 on top 3.81
+#ifndef CANTOR_MANY_CLUSTER
+#define CANTOR_MANY_CLUSTER 1         // > 1: the persistent kernel's CTAs run in clusters of this size that stay within one step of each other
+#endif                                // (split cluster barrier around the observation store), so a cluster's pieces of a slab leave together.
+                                      // Measured (2^20 x 252): 2 / 4 / 8 -> 4.60 / 4.91 / 4.92 ms against 3.66: lockstep is what this kernel
+                                      // does NOT want -- drifting CTAs are what keeps five streams flowing at once
 #ifndef CANTOR_MANY_THREADS
 #define CANTOR_MANY_THREADS 128       // envs per CTA of the persistent kernel
 #endif
@@ -525,8 +534,8 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
     const long long first_env = (long long)blockIdx.x * kManyThreads;
     const long long i = first_env + threadIdx.x;
     const bool live = i < n_envs;
-    const int rows = (int)min((long long)kManyThreads, n_envs - first_env);
-    const bool use_tma = (obs_tma_ok & 1) && (rows % 4 == 0) && ((n_envs & 3) == 0);   // every step's tile 16-byte aligned
+    const int rows = (int)max(0ll, min((long long)kManyThreads, n_envs - first_env));   // 0: a CTA that only fills up the last cluster
+    const bool use_tma = rows > 0 && (obs_tma_ok & 1) && (rows % 4 == 0) && ((n_envs & 3) == 0);   // every step's tile 16-byte aligned
     const bool keep_in_l2 = (obs_tma_ok & 2) != 0;
     const size_t rb = F64 ? sizeof(double) : sizeof(float);
     const InfoOut no_info{nullptr, nullptr, nullptr};
@@ -550,6 +559,9 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
         }
 #endif
     }
+#if CANTOR_MANY_CLUSTER > 1
+    cluster_arrive();
+#endif
     for (int s = 0; s < n_steps; ++s) {
         float* tile = tiles[s & 1];
         float* o = tile + threadIdx.x * CANTOR_OBS_DIM;
@@ -604,12 +616,35 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
         }
         // ---- the CTA's observation tile of step s ---------------------------------------------------------------
         float* dst = obs + ((long long)s * n_envs + first_env) * CANTOR_OBS_DIM;
-#if CANTOR_MANY_TMA
+#if CANTOR_MANY_TMA && CANTOR_MANY_WARP_STORES && CANTOR_MANY_CLUSTER <= 1
+        if (use_tma) {
+            // per warp: lane 0 makes sure its earlier bulk stores have read their buffers (the one of step s - 1 is the buffer step s + 1
+            // writes), every lane publishes its row to the async proxy, lane 0 stores the warp's 32 rows (32 x 52 B = 13 full lines)
+            const int w = threadIdx.x >> 5;
+            const int wrows = min(32, rows - 32 * w);
+            if ((threadIdx.x & 31) == 0) tma_store_wait_read();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0 && wrows > 0) {
+                const uint32_t bytes = (uint32_t)(wrows * CANTOR_OBS_DIM * sizeof(float));
+#if CANTOR_MANY_EVICT_FIRST
+                if (!keep_in_l2) tma_store_1d_evict_first(dst + w * 32 * CANTOR_OBS_DIM, tile + w * 32 * CANTOR_OBS_DIM, bytes);
+                else
+#endif
+                tma_store_1d(dst + w * 32 * CANTOR_OBS_DIM, tile + w * 32 * CANTOR_OBS_DIM, bytes);
+                tma_store_commit();
+            }
+            continue;
+        }
+#elif CANTOR_MANY_TMA
         if (use_tma) {
             // the store issued two steps ago read this step's buffer: thread 0 makes sure it has, before the barrier everybody passes
             if (threadIdx.x == 0) tma_store_wait_read();
             fence_proxy_async_smem();
             __syncthreads();
+#if CANTOR_MANY_CLUSTER > 1
+            cluster_wait();                       // every CTA of the cluster has issued its stores of step s - 1
+#endif
             if (threadIdx.x == 0) {
 #if CANTOR_MANY_EVICT_FIRST
                 if (!keep_in_l2) tma_store_1d_evict_first(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
@@ -618,10 +653,17 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
                 tma_store_1d(dst, tile, (uint32_t)(rows * CANTOR_OBS_DIM * sizeof(float)));
                 tma_store_commit();
             }
+#if CANTOR_MANY_CLUSTER > 1
+            cluster_arrive();
+#endif
             continue;
         }
 #endif
         __syncthreads();                          // tile s complete; everybody finished copying tile s - 1 (the other buffer) out
+#if CANTOR_MANY_CLUSTER > 1
+        cluster_wait();
+        cluster_arrive();
+#endif
         if (use_tma) {                            // 16-byte aligned tile of whole float4s: coalesced 16-byte streaming stores
             const float4* src4 = reinterpret_cast<const float4*>(tile);
             float4* dst4 = reinterpret_cast<float4*>(dst);
@@ -637,8 +679,11 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
             for (int j = threadIdx.x; j < rows * CANTOR_OBS_DIM; j += kManyThreads) dst[j] = tile[j];
         }
     }
+#if CANTOR_MANY_CLUSTER > 1
+    cluster_wait();
+#endif
 #if CANTOR_MANY_TMA
-    if (use_tma && threadIdx.x == 0) tma_store_wait_read();                     // shared memory must outlive the last bulk reads
+    if (use_tma && (threadIdx.x & 31) == 0) tma_store_wait_read();              // shared memory must outlive the last bulk reads
 #endif
     if (live) store_env<F64>(e, core_arr, cash_arr, pv_arr, i);
     if (MON) monitor_epilogue<kManyThreads>(mon, stat, finished_episode, red, (double)n_envs * (double)n_steps);
@@ -984,8 +1029,9 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
         const void* fn = precision == CANTOR_F64
             ? (mon_on ? (const void*)hedge_step_many_kernel<true, true> : (const void*)hedge_step_many_kernel<true, false>)
             : (mon_on ? (const void*)hedge_step_many_kernel<false, true> : (const void*)hedge_step_many_kernel<false, false>);
-        const unsigned grid_many = (unsigned)((n_envs + kManyThreads - 1) / kManyThreads);
-        return launch_pdl(fn, dim3(grid_many), dim3(kManyThreads), s, args);
+        unsigned grid_many = (unsigned)((n_envs + kManyThreads - 1) / kManyThreads);
+        grid_many = (grid_many + CANTOR_MANY_CLUSTER - 1) / CANTOR_MANY_CLUSTER * CANTOR_MANY_CLUSTER;   // CTAs beyond the envs only keep the barriers company
+        return launch_pdl(fn, dim3(grid_many), dim3(kManyThreads), s, args, 0, CANTOR_MANY_CLUSTER);
     }
     for (int32_t t = 0; t < n_steps; ++t) {
         // step t of a rollout writes slab t of the caller's [n_steps, n_envs, ...] buffers
