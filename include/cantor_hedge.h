@@ -358,9 +358,12 @@ enum {
                                             reference trained (quantconnect/model_wrapper.py:167-204); cantor_policy.mlp = the
                                             CANTOR_LSTM_IMAGE_BYTES weight image (cantorrl_b200/rollout.py: pack_lstm) */
 };
-#define CANTOR_LSTM_IMAGE_BYTES 178816   /* 4 gate tiles [128 x 144] + W1 [64 x 144] + W2 [64 x 80] + W3 [16 x 80] bf16 + mean / inv_std;
-                                            the i / f / o rows of the gate tiles hold HALF the torch.nn.LSTM weights and biases
-                                            (sigmoid(x) is evaluated as 0.5 + 0.5 tanh(x / 2); pack_lstm does the halving) */
+#define CANTOR_LSTM_IMAGE_BYTES 178816   /* 4 gate tiles [128 x 144] + W1 [64 x 144] + W2 [64 x 80] + W3 [16 x 80] bf16 + mean / inv_std.
+                                            Gate tile p = hidden units 32 p .. 32 p + 31 as two 64-row halves, rows ordered
+                                            [half][gate i, f, g, o][16 units] (one tcgen05.ld.x64 per half in the epilogue); columns =
+                                            {w_ih (13), b_ih + b_hh, 0, 0 | w_hh (128)}; the i / f / o rows hold HALF the torch.nn.LSTM
+                                            weights and biases (sigmoid(x) is evaluated as 0.5 + 0.5 tanh(x / 2)).  All tiles in the
+                                            canonical K-major no-swizzle UMMA layout; pack_lstm builds the image. */
 #define CANTOR_MLP_FLOATS 5212           /* W1[13][64] b1[64] W2[64][64] b2[64] W3[64][2] b3[2] obs_mean[13] obs_inv_std[13] */
 typedef struct cantor_policy {
     int32_t kind;                        /* CANTOR_POLICY_* */
