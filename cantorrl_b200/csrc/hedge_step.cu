@@ -68,6 +68,9 @@
 #endif                                // (split cluster barrier around the observation store), so a cluster's pieces of a slab leave together.
                                       // Measured (2^20 x 252): 2 / 4 / 8 -> 4.60 / 4.91 / 4.92 ms against 3.66: lockstep is what this kernel
                                       // does NOT want -- drifting CTAs are what keeps five streams flowing at once
+#ifndef CANTOR_MANY_MON_BLOCKS
+#define CANTOR_MANY_MON_BLOCKS 8      // resident CTAs per SM of the persistent kernel's fp32 Monitor variant
+#endif
 #ifndef CANTOR_MANY_THREADS
 #define CANTOR_MANY_THREADS 128       // envs per CTA of the persistent kernel
 #endif
@@ -253,7 +256,8 @@ template <bool F64, bool INFO, bool MON, bool SHARE>
 __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const float2 a, const float4& prev, const float4& cur,
                                           const Greeks& g_cur, float* __restrict__ o, long long i, long long n_envs,
                                           void* __restrict__ reward_slot, const InfoOut& info, const Monitor& mon,
-                                          float4& fin_acc, bool& finished_episode, double* reward_out = nullptr) {
+                                          float4& fin_acc, bool& finished_episode, double* reward_out = nullptr,
+                                          float4* acc_f32 = nullptr, double2* acc_f64 = nullptr) {
     const int pos_c = e.pos_c, pos_p = e.pos_p;
     const bool already_done = e.step >= k.T;                                  // only reachable with auto_reset = 0
     const int t_prev = already_done ? k.T - 1 : e.step;
@@ -312,7 +316,8 @@ __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const
         __stcs(reinterpret_cast<double*>(reward_slot), reward);
         if (reward_out != nullptr) *reward_out = reward;
         if (MON && !already_done) {
-            double2* ap = reinterpret_cast<double2*>(mon.acc) + 2 * i;
+            // the running sums of the episode: in the caller's registers (persistent kernel) or in the state arrays (one-step kernels)
+            double2* ap = acc_f64 != nullptr ? acc_f64 : reinterpret_cast<double2*>(mon.acc) + 2 * i;
             double2 a0 = ap[0], a1 = ap[1];                                   // {reward, pps}, {|pps|, cost}
             a0.x += reward; a0.y += pps; a1.x += fabs(pps); a1.y += costs;
             if (terminated) {
@@ -356,7 +361,7 @@ __device__ __forceinline__ bool step_body(const StepConsts& k, EnvRegs& e, const
         __stcs(reinterpret_cast<float*>(reward_slot), reward);
         if (reward_out != nullptr) *reward_out = (double)reward;
         if (MON && !already_done) {
-            float4* ap = reinterpret_cast<float4*>(mon.acc) + i;
+            float4* ap = acc_f32 != nullptr ? acc_f32 : reinterpret_cast<float4*>(mon.acc) + i;
             float4 m = *ap;                                                   // {reward, pps, |pps|, cost}
             m.x += reward; m.y += pps; m.z += fabsf(pps); m.w += costs;
             if (terminated) {
@@ -517,19 +522,18 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
 // the thread reads its action and ONE new path record (both requested a step ahead) and the CTA writes one observation tile
 // (double-buffered in shared memory: the TMA store of step s drains while step s + 1 computes), 128 rewards and 128 dones.
 template <bool F64, bool MON>
-__global__ void __launch_bounds__(kManyThreads, (MON || F64) ? (6 * 128 / kManyThreads) : (CANTOR_MANY_MIN_BLOCKS * 128 / kManyThreads))
+__global__ void __launch_bounds__(kManyThreads, F64 ? (6 * 128 / kManyThreads) : ((MON ? CANTOR_MANY_MON_BLOCKS : CANTOR_MANY_MIN_BLOCKS) * 128 / kManyThreads))
 hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr, void* __restrict__ cash_arr,
                        double* __restrict__ pv_arr, long long n_envs, int n_steps, const float2* __restrict__ actions,
                        float* __restrict__ obs, void* __restrict__ reward_arr, unsigned char* __restrict__ done_arr,
                        float* __restrict__ terminal_obs, const ResetRule rr, int obs_tma_ok, const Monitor mon) {
     __shared__ __align__(128) float tiles[2][kManyThreads * CANTOR_OBS_DIM];
     __shared__ double red[MON ? 11 * (kManyThreads / 32) : 1];
-    double stat[11];
-    bool finished_episode = false;
-    if (MON) {
-#pragma unroll
-        for (int s = 0; s < 11; ++s) stat[s] = 0.0;
-    }
+    // Monitor: the episode's running sums stay in registers for the whole launch (one 16 / 32-byte record each way per LAUNCH, not per step),
+    // and the eleven statistics of finished episodes are formed inside the rare, block-uniform branch below -- nothing float64 is
+    // live across the step body (the first form kept an 11-double accumulator per thread: 6 CTAs per SM, 5.02 ms per 2^20 x 252 sweep)
+    float4 macc_f = make_float4(0.f, 0.f, 0.f, 0.f);
+    double2 macc_d[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
     pdl_wait_prior_grid();          // the state may come from a per-step launch, which releases its dependents before it finishes
     const long long first_env = (long long)blockIdx.x * kManyThreads;
     const long long i = first_env + threadIdx.x;
@@ -547,6 +551,10 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
     const float4* rp = b.rec;                                                  // record (t + 1, path) of the step being computed
     if (live) {
         e = load_env<F64>(core_arr, cash_arr, pv_arr, i);
+        if (MON) {
+            if (F64) { macc_d[0] = reinterpret_cast<const double2*>(mon.acc)[2 * i]; macc_d[1] = reinterpret_cast<const double2*>(mon.acc)[2 * i + 1]; }
+            else macc_f = reinterpret_cast<const float4*>(mon.acc)[i];
+        }
         const int t_prev = (e.step >= k.T) ? k.T - 1 : e.step;                // cannot be >= T here (auto-reset), kept for safety
         rp = b.rec + ((long long)(t_prev + 1) * b.ld + e.path);
         prev = __ldcs(rp - b.ld);
@@ -567,6 +575,8 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
         float* o = tile + threadIdx.x * CANTOR_OBS_DIM;
         const long long at = (long long)s * n_envs + i;
         bool terminated = false;
+        float4 fin_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool fin_now = false;
         if (live) {
             // request later steps' inputs before this step's arithmetic: CANTOR_MANY_PREFETCH steps ahead (a record only while the
             // episode it belongs to is the current one: after an episode end the new path is known only at the reset)
@@ -583,14 +593,8 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
             }
 #endif
             const int path = e.path;
-            float4 fin_acc;
-            bool fin_now = false;
             terminated = step_body<F64, false, MON, false>(k, e, a, prev, cur, none, o, i, n_envs, (char*)reward_arr + at * rb,
-                                                           no_info, mon, fin_acc, fin_now);
-            if (MON && fin_now) {                                             // several episodes can end inside one launch: accumulate
-                episode_statistics(stat, fin_acc.x, fin_acc.y, fin_acc.z, fin_acc.w, k.inv_T_f, mon.stats);
-                finished_episode = true;
-            }
+                                                           no_info, mon, fin_acc, fin_now, nullptr, &macc_f, macc_d);
             if (terminated) {
                 if (terminal_obs != nullptr) write_terminal_obs(terminal_obs, i, o);
                 const int next = next_episode_path(rr, b, i, path, rr.episode_counter + s);
@@ -613,6 +617,15 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
             a_n = a_n2;
 #endif
             done_arr[at] = terminated ? 1 : 0;
+        }
+        if (MON && mon.stats.sums != nullptr) {                               // episodes that ended in this step -> the statistics vector
+            if (__syncthreads_or(fin_now)) {
+                double stat[11];
+#pragma unroll
+                for (int q = 0; q < 11; ++q) stat[q] = 0.0;
+                if (fin_now) episode_statistics(stat, fin_acc.x, fin_acc.y, fin_acc.z, fin_acc.w, k.inv_T_f, mon.stats);
+                block_accumulate<11, kManyThreads>(stat, mon.stats.sums, red);
+            }
         }
         // ---- the CTA's observation tile of step s ---------------------------------------------------------------
         float* dst = obs + ((long long)s * n_envs + first_env) * CANTOR_OBS_DIM;
@@ -685,8 +698,14 @@ hedge_step_many_kernel(const StepConsts k, const Book b, int4* __restrict__ core
 #if CANTOR_MANY_TMA
     if (use_tma && (threadIdx.x & 31) == 0) tma_store_wait_read();              // shared memory must outlive the last bulk reads
 #endif
-    if (live) store_env<F64>(e, core_arr, cash_arr, pv_arr, i);
-    if (MON) monitor_epilogue<kManyThreads>(mon, stat, finished_episode, red, (double)n_envs * (double)n_steps);
+    if (live) {
+        store_env<F64>(e, core_arr, cash_arr, pv_arr, i);
+        if (MON) {
+            if (F64) { reinterpret_cast<double2*>(mon.acc)[2 * i] = macc_d[0]; reinterpret_cast<double2*>(mon.acc)[2 * i + 1] = macc_d[1]; }
+            else reinterpret_cast<float4*>(mon.acc)[i] = macc_f;
+        }
+    }
+    if (MON) monitor_epilogue_one_step<kManyThreads>(mon, k, make_float4(0.f, 0.f, 0.f, 0.f), false, red, (double)n_envs * (double)n_steps);
 }
 
 // ---------------------------------------------------------------------------------------------------
