@@ -524,6 +524,27 @@ def graph_us(fn, dev, steps_per_graph=21, reps=8):
     return e0.elapsed_time(e1) / (reps * steps_per_graph) * 1e3
 
 
+def hbm_mix_context(dev, stream):
+    """HBM bandwidth of this GPU for pure reads, a copy, `add` and pure writes (plain torch streaming kernels over 1 GiB float32 buffers,
+    best of 5): context for fractions quoted against the 50 % / 50 % copy peak -- pure writes are NOT the slower stream on this part."""
+    import torch
+    n = (1 << 30) // 4
+    a = torch.empty(n, dtype=torch.float32, device=dev).fill_(1.0)
+    b = torch.empty_like(a).fill_(2.0)
+    c = torch.empty_like(a)
+
+    def best(fn, nbytes):
+        t = min(gpu_ms(fn, 1, stream, dev, warm=1) for _ in range(5))
+        return nbytes / t / 1e6
+
+    out = dict(what="torch kernels over 1 GiB float32 buffers, best of 5, GB/s",
+               read_only_sum=best(lambda: a.sum(), 4 * n), copy=best(lambda: c.copy_(a), 8 * n),
+               add_two_reads_one_write=best(lambda: torch.add(a, b, out=c), 12 * n), write_only_fill=best(lambda: c.fill_(1.0), 4 * n))
+    del a, b, c
+    torch.cuda.empty_cache()
+    return out
+
+
 def side_kernel_bench(dev, stream, peak):
     """Time + algorithmic GB/s + fraction of the HBM peak of the float64 parity forms and the format / wrapper kernels, called
     through the C ABI on preallocated buffers: bs_price (A6), schema_b_book (A7 + A8), bs_delta_hedge (A12), pack / unpack
@@ -886,6 +907,7 @@ def main():
     if args.forms and rank == 0:
         torch.cuda.empty_cache()
         forms = side_kernel_bench(dev, stream, peak)
+        forms["hbm_bandwidth_vs_mix"] = hbm_mix_context(dev, stream)
 
     # ---- reduce over ranks ------------------------------------------------------------------------------------
     pr = probe or dict(d2h_gbs=0.0, h2d_gbs=0.0, rounds_per_s=0.0, d2h_only_gbs=0.0)
