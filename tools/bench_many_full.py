@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=252)
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--monitor", type=int, default=0)
+    ap.add_argument("--record-metrics", type=int, default=1, help="0: the observation's greeks are zeros (fewer instructions, same bytes)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -32,7 +33,7 @@ def main():
     for n in [int(x) for x in a.envs.split(",")]:
         data, _ = bench.synth_replay_data(n, T, 0, dev)
         env = HedgingVecEnv(data=data, num_envs=n, device=dev, precision=a.precision, episode_sampler="same_path",
-                            monitor=bool(a.monitor), **bench.ENV_KW)
+                            monitor=bool(a.monitor), record_metrics=bool(a.record_metrics), **bench.ENV_KW)
         g = torch.Generator(device=dev).manual_seed(1234)
         actions = torch.rand((T, n, 2), device=dev, generator=g) * 2 - 1
         actions[:, :, 1] = 0.0
