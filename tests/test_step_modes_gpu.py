@@ -52,7 +52,11 @@ def test_step_many_persistent_equals_per_step_launches(prec, n_envs, sampler):
         assert torch.equal(envs[0]._pv_prev, envs[1]._pv_prev)
 
 
-def test_step_many_with_monitor_and_statistics():
+@pytest.mark.parametrize("prec", ["fp32", "fp64"])
+def test_step_many_with_monitor_and_statistics(prec):
+    """The persistent kernel keeps the Monitor's running sums in registers for the whole launch and forms the statistics of finished
+    episodes on the spot: after 3 1/3 episodes the statistics, the per-env episode returns and the running sums of the unfinished
+    episode must equal those of 20 per-step launches."""
     from cantorrl_b200 import HedgingVecEnv, sim
     from cantorrl_b200.stats import EpisodeStats
     T, n, k = 6, 700, 20
@@ -61,7 +65,7 @@ def test_step_many_with_monitor_and_statistics():
     res = []
     for many in (True, False):
         st = EpisodeStats("cuda", hist_bins=128, hist_max=4.0)
-        env = HedgingVecEnv(data=book, num_envs=n, episode_sampler="same_path", monitor=True, stats=st, **KW)
+        env = HedgingVecEnv(data=book, num_envs=n, episode_sampler="same_path", monitor=True, stats=st, precision=prec, **KW)
         env.reset()
         if many:
             env.step_many(tape)
