@@ -5,7 +5,9 @@
 // Packed book: float4 {S, v, C, P} at [t * ld + path], t = 0..T, row T repeating the marks of row T-1.
 //
 // 32 x 32 tiles through shared memory: reads are contiguous along time (source rows), writes are contiguous
-// along paths (512 B of float4 records per warp).
+// along paths (512 B of float4 records per warp).  Tiles are numbered TIME-FASTEST (1-D grid): the CTAs that run next to each
+// other touch neighbouring 128 / 256-byte pieces of the same path-major rows, whose 253-element rows start at every alignment --
+// the pieces meet in L2 and leave as whole lines instead of as partially written sectors.
 #include "common.cuh"
 
 namespace cantor {
@@ -15,7 +17,8 @@ __global__ void __launch_bounds__(256)
 pack_book_kernel(const T* __restrict__ paths, const T* __restrict__ vols, const T* __restrict__ calls,
                  const T* __restrict__ puts, int n_paths, int Tlen, float4* __restrict__ rec, long long ld) {
     __shared__ float tile[4][32][33];
-    const int p0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    const unsigned n_t = (unsigned)(Tlen + 1 + 31) / 32;
+    const int p0 = (int)(blockIdx.x / n_t) * 32, t0 = (int)(blockIdx.x % n_t) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                    // 32 x 8
     for (int r = ty; r < 32; r += 8) {
         const int p = p0 + r, t = t0 + tx;
@@ -40,7 +43,8 @@ __global__ void __launch_bounds__(256)
 unpack_book_kernel(const float4* __restrict__ rec, long long ld, int n_paths, int Tlen, T* __restrict__ paths,
                    T* __restrict__ vols, T* __restrict__ calls, T* __restrict__ puts) {
     __shared__ float tile[4][32][33];
-    const int p0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    const unsigned n_t = (unsigned)(Tlen + 1 + 31) / 32;
+    const int p0 = (int)(blockIdx.x / n_t) * 32, t0 = (int)(blockIdx.x % n_t) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int r = ty; r < 32; r += 8) {
         const int t = t0 + r, p = p0 + tx;
@@ -74,7 +78,9 @@ extern "C" int cantor_pack_book(const void* paths, const void* vols, const void*
     CANTOR_REQUIRE(src_dtype == CANTOR_F32 || src_dtype == CANTOR_F64, "src_dtype must be 32 or 64");
     CANTOR_REQUIRE(n_paths > 0 && episode_length > 0 && ld >= n_paths, "bad shape");
     CANTOR_REQUIRE(aligned16(svcp), "svcp must be 16-byte aligned");
-    const dim3 grid((n_paths + 31) / 32, (episode_length + 1 + 31) / 32);
+    const long long n_tiles = (long long)((n_paths + 31) / 32) * ((episode_length + 1 + 31) / 32);
+    CANTOR_REQUIRE(n_tiles <= 0x7fffffffLL, "book too large for one launch");
+    const dim3 grid((unsigned)n_tiles);
     cudaStream_t s = (cudaStream_t)stream;
     if (src_dtype == CANTOR_F64)
         pack_book_kernel<double><<<grid, 256, 0, s>>>((const double*)paths, (const double*)vols, (const double*)calls,
@@ -90,7 +96,9 @@ extern "C" int cantor_unpack_book(const float* svcp, int64_t ld, int32_t n_paths
     CANTOR_REQUIRE(paths && vols && calls && puts && svcp, "array is NULL");
     CANTOR_REQUIRE(dst_dtype == CANTOR_F32 || dst_dtype == CANTOR_F64, "dst_dtype must be 32 or 64");
     CANTOR_REQUIRE(n_paths > 0 && episode_length > 0 && ld >= n_paths, "bad shape");
-    const dim3 grid((n_paths + 31) / 32, (episode_length + 1 + 31) / 32);
+    const long long n_tiles = (long long)((n_paths + 31) / 32) * ((episode_length + 1 + 31) / 32);
+    CANTOR_REQUIRE(n_tiles <= 0x7fffffffLL, "book too large for one launch");
+    const dim3 grid((unsigned)n_tiles);
     cudaStream_t s = (cudaStream_t)stream;
     if (dst_dtype == CANTOR_F64)
         unpack_book_kernel<double><<<grid, 256, 0, s>>>((const float4*)svcp, ld, n_paths, episode_length, (double*)paths,
