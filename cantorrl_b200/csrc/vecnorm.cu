@@ -17,6 +17,10 @@
 // Memory-bound: 52 B read for the moments, 104 + ~18 B for the apply, per env-step (L2 hits right behind the step kernel).
 #include "common.cuh"
 
+#ifndef CANTOR_VN_APPLY_REVERSE
+#define CANTOR_VN_APPLY_REVERSE 1
+#endif
+
 namespace cantor {
 
 constexpr int kVnCols = CANTOR_OBS_DIM;            // 13
@@ -316,6 +320,13 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
     const long long n_chunks = (n + kVnRows - 1) / kVnRows;
     const long long n_full = vec_ok ? n / kVnRows : 0;
     constexpr int U = 8;
+    // full chunks are walked LAST-WRITTEN FIRST: the step kernel that produced the batch wrote chunk 0 first and chunk n - 1 last, so what
+    // is still in L2 is the tail of the batch; walking forward would start with the lines most likely to have left
+#if CANTOR_VN_APPLY_REVERSE
+    auto rev = [n_full](long long c) { return n_full - 1 - c; };
+#else
+    auto rev = [](long long c) { return c; };
+#endif
     long long c = blockIdx.x;
     if (norm_obs) {
         for (; c + (U - 1) * (long long)gridDim.x < n_full; c += U * (long long)gridDim.x) {   // full batches of U chunks
@@ -323,7 +334,7 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
             float4 v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                p[u] = reinterpret_cast<float4*>(obs) + (c + u * (long long)gridDim.x) * kVnThreads + threadIdx.x;
+                p[u] = reinterpret_cast<float4*>(obs) + rev(c + u * (long long)gridDim.x) * kVnThreads + threadIdx.x;
                 v[u] = *p[u];
             }
 #pragma unroll
@@ -338,14 +349,14 @@ vecnorm_apply_kernel(const double* __restrict__ rms, double* __restrict__ return
 #pragma unroll
             for (int u = 0; u < UL; ++u) {
                 const long long cu = c + u * (long long)gridDim.x;
-                if (cu < n_full) v[u] = *(reinterpret_cast<float4*>(obs) + cu * kVnThreads + threadIdx.x);
+                if (cu < n_full) v[u] = *(reinterpret_cast<float4*>(obs) + rev(cu) * kVnThreads + threadIdx.x);
             }
 #pragma unroll
             for (int u = 0; u < UL; ++u) {
                 const long long cu = c + u * (long long)gridDim.x;
                 if (cu < n_full) {
                     v[u].x = norm1(v[u].x, 0); v[u].y = norm1(v[u].y, 1); v[u].z = norm1(v[u].z, 2); v[u].w = norm1(v[u].w, 3);
-                    *(reinterpret_cast<float4*>(obs) + cu * kVnThreads + threadIdx.x) = v[u];
+                    *(reinterpret_cast<float4*>(obs) + rev(cu) * kVnThreads + threadIdx.x) = v[u];
                 }
             }
         }
