@@ -68,6 +68,9 @@
 #endif                                // (split cluster barrier around the observation store), so a cluster's pieces of a slab leave together.
                                       // Measured (2^20 x 252): 2 / 4 / 8 -> 4.60 / 4.91 / 4.92 ms against 3.66: lockstep is what this kernel
                                       // does NOT want -- drifting CTAs are what keeps five streams flowing at once
+#ifndef CANTOR_STEP_ALTERNATE
+#define CANTOR_STEP_ALTERNATE 1       // the per-step replay kernel walks the env tiles forward on even global steps, backward on odd ones
+#endif
 #ifndef CANTOR_MANY_MON_BLOCKS
 #define CANTOR_MANY_MON_BLOCKS 8      // resident CTAs per SM of the persistent kernel's fp32 Monitor variant
 #endif
@@ -120,7 +123,8 @@ constexpr int kVnFuseSums = 2 * CANTOR_OBS_DIM + 2;
 // partial layout: [CTA][28] -- one contiguous, fully written 224-byte record per CTA (no partial-sector writes).
 template <int THREADS>
 __device__ __forceinline__ void vecnorm_partials(const VecNormFuse& vn, const float* tile, int rows, bool live, long long i,
-                                                 double reward, double ret_prev, double* scratch /* [2 * 8 * 13 + 2 * THREADS / 32] */) {
+                                                 double reward, double ret_prev, double* scratch /* [2 * 8 * 13 + 2 * THREADS / 32] */,
+                                                 unsigned tile_idx) {
     constexpr int C = CANTOR_OBS_DIM, PARTS = 8;
     double* part = scratch;                            // [2][PARTS][C]
     double* wsum = scratch + 2 * PARTS * C;            // [2][THREADS / 32]
@@ -157,7 +161,7 @@ __device__ __forceinline__ void vecnorm_partials(const VecNormFuse& vn, const fl
         wsum[THREADS / 32 + (threadIdx.x >> 5)] = rq;
     }
     __syncthreads();
-    double* out = vn.partial + (long long)blockIdx.x * kVnFuseSums;
+    double* out = vn.partial + (long long)tile_idx * kVnFuseSums;      // by TILE, not by CTA: the fold's summation order does not depend on the walk
     if (threadIdx.x < 2 * C) {                         // column sums: the 8 parts in order
         const int kind = threadIdx.x / C, c = threadIdx.x % C;
         double a = 0.0;
@@ -471,7 +475,11 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
     double my_reward = 0.0, ret_prev = 0.0;
     float4 fin_acc = make_float4(0.f, 0.f, 0.f, 0.f);
     bool finished_episode = false;                                            // MON: this thread's env just ended an episode
-    const long long first_env = (long long)blockIdx.x * kStepThreads;
+    // Bit 2 of obs_tma_ok: walk the env tiles LAST FIRST.  The host alternates the direction from launch to launch, so a launch starts
+    // with the state and path records the previous launch touched last -- the part of them that is still in L2 when the population
+    // is larger than the cache (at 2^20 envs everything fits either way; at 2^23 the first ~1.5 M envs of every launch hit).
+    const unsigned tile_idx = (obs_tma_ok & 4) ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+    const long long first_env = (long long)tile_idx * kStepThreads;
     const long long i = first_env + threadIdx.x;
     const int rows = (int)min((long long)kStepThreads, n_envs - first_env);
     float* o = tile + threadIdx.x * CANTOR_OBS_DIM;                            // stride 13 words: conflict-free
@@ -513,7 +521,7 @@ hedge_step_kernel(const StepConsts k, const Book b, int4* __restrict__ core_arr,
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
-    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch);
+    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch, tile_idx);
     if (MON) monitor_epilogue_one_step<kStepThreads>(mon, k, fin_acc, finished_episode, red, (double)n_envs);
 }
 
@@ -829,7 +837,7 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
-    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch);
+    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch, blockIdx.x);
     if (MON) monitor_epilogue_one_step<kStepThreads>(mon, k, fin_acc, finished_episode, red, (double)n_envs);
 }
 
@@ -1058,7 +1066,7 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
         float* obs_t = obs + (size_t)t * n_envs * CANTOR_OBS_DIM;
         void* rew_t = (char*)reward + (size_t)t * n_envs * reward_bytes;
         unsigned char* done_t = done + (size_t)t * n_envs;
-        int tma_ok = (aligned16(obs_t) ? 1 : 0) | keep;
+        int tma_ok = (aligned16(obs_t) ? 1 : 0) | keep | ((CANTOR_STEP_ALTERNATE && (rr.episode_counter & 1)) ? 4 : 0);
         void* args[] = {&k, &b, &core, &cash, &pv, &n, &a_t, &obs_t, &rew_t, &done_t, &terminal_obs, &auto_reset,
                         &rr, &io, &tma_ok, &mon, &vn};
         const void* fn;
