@@ -19,6 +19,7 @@ F32, F64 = 32, 64
 LOSS_ABS, LOSS_MSE = 0, 1
 RESET_SAME_PATH, RESET_FROM_ARRAY, RESET_PHILOX = 0, 1, 2
 STEP_KEEP_OBS_IN_L2 = 1
+STEP_WALK_BACKWARD = 2
 INFO_F64_KEYS = (
     "step_pnl_total", "per_share_step_pnl", "raw_pnl_deviation_abs", "transaction_costs_total",
     "commission_cost", "slippage_cost", "reward_pnl_component", "transaction_cost_penalty", "theta_penalty",

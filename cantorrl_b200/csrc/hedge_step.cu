@@ -766,7 +766,8 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
     double my_reward = 0.0, ret_prev = 0.0;
     float4 fin_acc = make_float4(0.f, 0.f, 0.f, 0.f);
     bool finished_episode = false;
-    const long long first_env = (long long)blockIdx.x * kStepThreads;
+    const unsigned tile_idx = (obs_tma_ok & 4) ? gridDim.x - 1 - blockIdx.x : blockIdx.x;     // CANTOR_STEP_WALK_BACKWARD
+    const long long first_env = (long long)tile_idx * kStepThreads;
     const long long i = first_env + threadIdx.x;
     const int rows = (int)min((long long)kStepThreads, n_envs - first_env);
     float* o = tile + threadIdx.x * CANTOR_OBS_DIM;
@@ -837,7 +838,7 @@ hedge_step_sim_kernel(const StepConsts k, const SimConsts sk, const SimSource sr
         pdl_launch_dependents();
     }
     store_obs_tile(obs, tile, first_env, rows, (obs_tma_ok & 1) && (rows % 4 == 0), (obs_tma_ok & 2) != 0);
-    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch, blockIdx.x);
+    if (VN) vecnorm_partials<kStepThreads>(vn, tile, rows, i < n_envs, i, my_reward, ret_prev, vn_scratch, tile_idx);
     if (MON) monitor_epilogue_one_step<kStepThreads>(mon, k, fin_acc, finished_episode, red, (double)n_envs);
 }
 
@@ -1134,7 +1135,7 @@ extern "C" int cantor_env_step_sim(const cantor_env_params* params, const cantor
     double* pv = state->pv_prev;
     long long n = n_envs;
     const float2* a = (const float2*)actions;
-    int tma_ok = (aligned16(obs) ? 1 : 0) | ((flags & CANTOR_STEP_KEEP_OBS_IN_L2) ? 2 : 0);
+    int tma_ok = (aligned16(obs) ? 1 : 0) | ((flags & CANTOR_STEP_KEEP_OBS_IN_L2) ? 2 : 0) | ((flags & CANTOR_STEP_WALK_BACKWARD) ? 4 : 0);
     int share = share_quote_ok(params, k, sk);
     void* args[] = {&k, &sk, &ss, &core, &cash, &pv, &n, &a, &obs, &reward, &done, &terminal_obs, &auto_reset, &io, &tma_ok,
                     &share, &mon, &vn};

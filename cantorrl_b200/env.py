@@ -443,7 +443,8 @@ class HedgingVecEnv:
                     done.data_ptr(), c["term"], int(self.auto_reset), c["rule"], c["info"])
         else:       # on-the-fly mode: the day's path step is generated inside the kernel
             args = (c["params"], c["source"], c["state"], self.num_envs, self._prec, a.data_ptr(), obs.data_ptr(), reward.data_ptr(),
-                    done.data_ptr(), c["term"], int(self.auto_reset), c["info"], int(self._rule.flags))
+                    done.data_ptr(), c["term"], int(self.auto_reset), c["info"],
+                    int(self._rule.flags) | (_lib.STEP_WALK_BACKWARD if (self._global_step & 1) else 0))     # alternate the walk: L2 reuse
         if torch.cuda.current_device() == c["dev"]:
             status = c["fn"](*args, torch.cuda.current_stream().cuda_stream)
         else:

@@ -120,6 +120,10 @@ typedef struct cantor_env_state {
 #define CANTOR_STEP_KEEP_OBS_IN_L2 1   /* store the observations with the normal L2 policy because a device-side consumer (policy
                                           network, cantor_vecnorm_step) reads them next; default: evict-first, which is faster for
                                           the step itself when the observations leave for the host or for a later kernel */
+#define CANTOR_STEP_WALK_BACKWARD 2    /* cantor_env_step_sim: walk the env tiles last-first in this launch.  A caller that alternates the flag from
+                                          step to step lets every launch start with the state the previous one touched last -- the part that is
+                                          still in L2 when the population is larger than the cache (results do not depend on it).
+                                          cantor_env_step alternates by itself on the parity of reset_rule.episode_counter. */
 typedef struct cantor_reset_rule {
     int32_t mode;              /* CANTOR_RESET_* */
     int32_t flags;             /* CANTOR_STEP_* bits */
