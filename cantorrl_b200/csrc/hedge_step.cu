@@ -1061,13 +1061,17 @@ static int env_step_impl(const cantor_env_params* params, const cantor_replay_bo
         grid_many = (grid_many + CANTOR_MANY_CLUSTER - 1) / CANTOR_MANY_CLUSTER * CANTOR_MANY_CLUSTER;   // CTAs beyond the envs only keep the barriers company
         return launch_pdl(fn, dim3(grid_many), dim3(kManyThreads), s, args, 0, CANTOR_MANY_CLUSTER);
     }
+    // The alternating walk pays wherever a launch's footprint presses on L2: beyond ~1.5 M envs, or when the observations are kept in L2 /
+    // info, Monitor or VecNormalize records ride along.  The plain fast path at 2^20 envs (everything it re-reads fits) is 2-3 % faster
+    // walking forward every time (17.3 against 17.9 us per launch), so it keeps doing that.
+    const bool alternate = CANTOR_STEP_ALTERNATE && (n_envs > 1500000 || keep != 0 || info != nullptr || mon_on || vn.partial != nullptr);
     for (int32_t t = 0; t < n_steps; ++t) {
         // step t of a rollout writes slab t of the caller's [n_steps, n_envs, ...] buffers
         const float2* a_t = (const float2*)actions + (size_t)t * n_envs;
         float* obs_t = obs + (size_t)t * n_envs * CANTOR_OBS_DIM;
         void* rew_t = (char*)reward + (size_t)t * n_envs * reward_bytes;
         unsigned char* done_t = done + (size_t)t * n_envs;
-        int tma_ok = (aligned16(obs_t) ? 1 : 0) | keep | ((CANTOR_STEP_ALTERNATE && (rr.episode_counter & 1)) ? 4 : 0);
+        int tma_ok = (aligned16(obs_t) ? 1 : 0) | keep | ((alternate && (rr.episode_counter & 1)) ? 4 : 0);
         void* args[] = {&k, &b, &core, &cash, &pv, &n, &a_t, &obs_t, &rew_t, &done_t, &terminal_obs, &auto_reset,
                         &rr, &io, &tma_ok, &mon, &vn};
         const void* fn;
