@@ -178,11 +178,12 @@ def _lstm_weights(seed=3):
                 W3=g.normal(0, 0.3, (2, 64)).astype(np.float32), b3=g.normal(0, 0.1, 2).astype(np.float32))
 
 
-@pytest.mark.parametrize("n_envs", [203, 900])
+@pytest.mark.parametrize("n_envs", [100, 203, 900])
 def test_recurrent_lstm_actor_matches_oracle_over_episodes(n_envs):
     """The tensor-core LSTM + MLP actor inside the rollout: env parity teacher-forced on its own actions, and the actions
     themselves against the oracle network run over the kernel's observation sequence (state reset at episode ends).
-    203 envs = one ragged CTA (its second group of 128 partly empty); 900 = three full CTAs of 256 + one of 132."""
+    100 envs = one CTA whose second group is EMPTY (the groups store their observation pieces independently: nothing to store for
+    it); 203 = one ragged CTA (second group partly empty); 900 = three full CTAs of 256 + one of 132."""
     from cantorrl_b200.rollout import HedgingRollout, pack_lstm
     n_paths, T, n_steps = 61, 12, 41
     S, V, C, P = _book(n_paths, T, heston=True)
