@@ -25,6 +25,10 @@
 // 1: all four warps poll the MMA mbarrier; 0: warp 0 polls, the others park at the CTA barrier.  Measured (2^20 envs x 252
 // steps, GBM on the fly): 6.88 ms against 7.01 ms -- the polls are 23 % of the executed instructions but fill issue slots nobody
 // else wants: the kernel is bound by the latency of its three serial MMA round trips per step, not by issue bandwidth.
+#ifndef CANTOR_MLP_BIAS_IN_EPILOGUE    // 1: layers 2 / 3 of the MLP actor as K = 64 products (4 instead of 5 MMAs each), their biases added by
+#define CANTOR_MLP_BIAS_IN_EPILOGUE 0  // the threads in the epilogue instead of riding on a ones column that costs a fifth K-step.
+#endif                                 // Measured (2^20 x 252, GBM): 7.57 ms against 6.86 (7 CTAs/SM at 72 registers: 7.35): the 64 FADD +
+                                       // 16 LDS per thread-step cost more issue slots than the two MMAs give back
 #ifndef CANTOR_MLP_ALL_WARPS_POLL
 #define CANTOR_MLP_ALL_WARPS_POLL 1
 #endif
@@ -45,7 +49,12 @@ constexpr int kA1Bytes = kRows * kK1 * 2, kA2Bytes = kRows * kK2 * 2;
 // The layer-1 operand tile A1 (4 KB) ALIASES the head of the A2 tile: A2 is first written by the layer-1 epilogue, after the
 // layer-1 MMA has read A1, and A1 is next written after the layer-3 MMA has read A2.  36 KB per CTA instead of 40: six CTAs
 // per SM fit instead of five.  (The A2 rows' constant tail, which A1 overwrites for some rows, is rewritten by the epilogue.)
-constexpr int kSmemBytes = kW1Bytes + kW2Bytes + kW3Bytes + kA2Bytes + 16 + 128;   // + mbarrier (8) + TMEM address (4) + mean / inv_std (2 x 16 floats)
+// the MLP actor's own layer-2 / 3 geometry (the recurrent actor's head keeps the K = 80 tiles above)
+constexpr int kKa = CANTOR_MLP_BIAS_IN_EPILOGUE ? 64 : kK2;
+constexpr int kSboA2 = (kKa / 8) * 128;
+constexpr int kW2aBytes = kHidden * kKa * 2, kW3aBytes = kN3 * kKa * 2, kA2aBytes = kRows * kKa * 2;
+constexpr int kBiasBytes = CANTOR_MLP_BIAS_IN_EPILOGUE ? (kHidden + 16) * 4 : 0;      // b2[64], b3[2] as floats
+constexpr int kSmemBytes = kW1Bytes + kW2aBytes + kW3aBytes + kA2aBytes + 16 + 128 + kBiasBytes;   // + mbarrier (8) + TMEM address (4) + mean / inv_std (2 x 16 floats)
 constexpr int kTmemCols = 64;
 constexpr unsigned kSpinLimit = 1u << 24;
 
@@ -76,9 +85,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 #define CANTOR_UMMA_HEAD "{\n\t.reg .pred pt, pf;\n\t.reg .b64 da, db;\n\tsetp.eq.u32 pt, 0, 0;\n\tsetp.ne.u32 pf, 0, 0;\n\tmov.b64 da, %1;\n\tmov.b64 db, %2;\n\t"
 template <int NK>
 __device__ __forceinline__ void umma_batch(uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t d) {
-    static_assert(NK == 1 || NK == 5 || NK == 9, "K-step counts in use: K = 16 (x-part, MLP layer 1), 80 (layers 2 / 3), 144 (LSTM A tile)");
+    static_assert(NK == 1 || NK == 4 || NK == 5 || NK == 9, "K-step counts in use: K = 16 (x-part, MLP layer 1), 64 / 80 (layers 2 / 3), 144 (LSTM A tile)");
     if (NK == 1)
         asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+    else if (NK == 4)
+        asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
+                     "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
     else if (NK == 5)
         asm volatile(CANTOR_UMMA_HEAD CANTOR_UMMA_STEP("pf") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt") CANTOR_UMMA_STEP("pt")
                      CANTOR_UMMA_STEP("pt") "}" :: "r"(d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
@@ -125,6 +137,7 @@ struct Actor {
     unsigned char* a2;
     uint32_t mbar, tmem, phase;
     const float* norm;      // shared: mean[16], inv_std[16]
+    const float* bias;      // shared: b2[64], b3[2] (CANTOR_MLP_BIAS_IN_EPILOGUE)
     bool timed_out;
 
     // One-time CTA setup: converts the float32 weight block to bf16 tiles, allocates 64 TMEM columns, arms the mbarrier.
@@ -132,10 +145,10 @@ struct Actor {
     __device__ __forceinline__ void setup(unsigned char* smem, const float* __restrict__ w, float obs_clip) {
         w1 = smem;
         w2 = w1 + kW1Bytes;
-        w3 = w2 + kW2Bytes;
-        a2 = w3 + kW3Bytes;
+        w3 = w2 + kW2aBytes;
+        a2 = w3 + kW3aBytes;
         a1 = a2;
-        uint64_t* bar = reinterpret_cast<uint64_t*>(a2 + kA2Bytes);
+        uint64_t* bar = reinterpret_cast<uint64_t*>(a2 + kA2aBytes);
         uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
         mbar = smem_u32(bar);
         phase = 0;
@@ -147,7 +160,10 @@ struct Actor {
         const float* W3 = b2 + kHidden;
         const float* b3 = W3 + kHidden * kOut;
         const int tid = threadIdx.x;
-        float* norm_s = reinterpret_cast<float*>(a2 + kA2Bytes + 16);
+        float* norm_s = reinterpret_cast<float*>(a2 + kA2aBytes + 16);
+        float* bias_s = norm_s + 32;
+        bias = bias_s;
+        if (CANTOR_MLP_BIAS_IN_EPILOGUE && tid < kHidden + kOut) bias_s[tid] = tid < kHidden ? b2[tid] : b3[tid - kHidden];
         if (tid < 32) norm_s[tid] = (tid & 15) < kIn ? (b3 + kOut)[(tid >> 4) * kIn + (tid & 15)] : (tid == 15 ? obs_clip : 0.f);   // [15] = clip
         norm = norm_s;
         __nv_bfloat16* w1h = reinterpret_cast<__nv_bfloat16*>(w1);
@@ -157,22 +173,21 @@ struct Actor {
             w1h[((n >> 3) * kSbo1 + (k >> 3) * kLbo + (n & 7) * 16 + (k & 7) * 2) >> 1] = __float2bfloat16_rn(v);
         }
         __nv_bfloat16* w2h = reinterpret_cast<__nv_bfloat16*>(w2);
-        for (int e = tid; e < kHidden * kK2; e += kRows) {           // B2(n, k) = W2[k][n], k = 64 -> b2[n]
-            const int n = e / kK2, k = e % kK2;
+        for (int e = tid; e < kHidden * kKa; e += kRows) {           // B2(n, k) = W2[k][n], k = 64 -> b2[n]
+            const int n = e / kKa, k = e % kKa;
             const float v = k < kHidden ? W2[k * kHidden + n] : (k == kHidden ? b2[n] : 0.f);
-            w2h[((n >> 3) * kSbo2 + (k >> 3) * kLbo + (n & 7) * 16 + (k & 7) * 2) >> 1] = __float2bfloat16_rn(v);
+            w2h[((n >> 3) * kSboA2 + (k >> 3) * kLbo + (n & 7) * 16 + (k & 7) * 2) >> 1] = __float2bfloat16_rn(v);
         }
         __nv_bfloat16* w3h = reinterpret_cast<__nv_bfloat16*>(w3);
-        for (int e = tid; e < kN3 * kK2; e += kRows) {               // B3(n, k) = W3[k][n] for n < 2, k = 64 -> b3[n]
-            const int n = e / kK2, k = e % kK2;
+        for (int e = tid; e < kN3 * kKa; e += kRows) {               // B3(n, k) = W3[k][n] for n < 2, k = 64 -> b3[n]
+            const int n = e / kKa, k = e % kKa;
             float v = 0.f;
             if (n < kOut) v = k < kHidden ? W3[k * kOut + n] : (k == kHidden ? b3[n] : 0.f);
-            w3h[((n >> 3) * kSbo2 + (k >> 3) * kLbo + (n & 7) * 16 + (k & 7) * 2) >> 1] = __float2bfloat16_rn(v);
+            w3h[((n >> 3) * kSboA2 + (k >> 3) * kLbo + (n & 7) * 16 + (k & 7) * 2) >> 1] = __float2bfloat16_rn(v);
         }
-        // constant tail of this thread's A2 row: column 64 = 1.0 (bias), 65..79 = 0
-        {
+        if (!CANTOR_MLP_BIAS_IN_EPILOGUE) {                           // constant tail of this thread's A2 row: column 64 = 1.0 (bias), 65..79 = 0
             const int m = tid;
-            unsigned char* row = a2 + (m >> 3) * kSbo2 + (m & 7) * 16;
+            unsigned char* row = a2 + (m >> 3) * kSboA2 + (m & 7) * 16;
             *reinterpret_cast<uint4*>(row + 8 * kLbo) = make_uint4(0x00003F80u, 0u, 0u, 0u);     // bf16(1.0) = 0x3F80
             *reinterpret_cast<uint4*>(row + 9 * kLbo) = make_uint4(0u, 0u, 0u, 0u);
         }
@@ -240,10 +255,12 @@ struct Actor {
 
     // accumulator row of this thread (64 columns) -> ReLU -> bf16 -> this thread's A2 row; two TMEM loads in flight per wait
     // (all four at once cost 30 more registers and a resident CTA per SM: 7.99 ms instead of 6.9 for the 2^20 x 252 sweep)
+    // ADD_BIAS (layer 2 with CANTOR_MLP_BIAS_IN_EPILOGUE): b2 is added here, in float32, before the ReLU
+    template <bool ADD_BIAS>
     __device__ __forceinline__ void hidden_epilogue() {
         const int m = threadIdx.x;
         const uint32_t lane_addr = tmem + ((uint32_t)(m & ~31) << 16);
-        unsigned char* row = a2 + (m >> 3) * kSbo2 + (m & 7) * 16;
+        unsigned char* row = a2 + (m >> 3) * kSboA2 + (m & 7) * 16;
 #pragma unroll
         for (int c2 = 0; c2 < kHidden / 32; ++c2) {
             uint32_t r[2][16];
@@ -256,6 +273,16 @@ struct Actor {
                 // ties the registers of the asynchronous loads to this point: nothing below may be scheduled above the wait
                 asm volatile("" : "+r"(r[h][0]), "+r"(r[h][1]), "+r"(r[h][2]), "+r"(r[h][3]), "+r"(r[h][4]), "+r"(r[h][5]), "+r"(r[h][6]), "+r"(r[h][7]),
                                   "+r"(r[h][8]), "+r"(r[h][9]), "+r"(r[h][10]), "+r"(r[h][11]), "+r"(r[h][12]), "+r"(r[h][13]), "+r"(r[h][14]), "+r"(r[h][15]) :: "memory");
+                if (ADD_BIAS) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bq = *reinterpret_cast<const float4*>(bias + 16 * c + 4 * q);
+                        r[h][4 * q + 0] = __float_as_uint(__uint_as_float(r[h][4 * q + 0]) + bq.x);
+                        r[h][4 * q + 1] = __float_as_uint(__uint_as_float(r[h][4 * q + 1]) + bq.y);
+                        r[h][4 * q + 2] = __float_as_uint(__uint_as_float(r[h][4 * q + 2]) + bq.z);
+                        r[h][4 * q + 3] = __float_as_uint(__uint_as_float(r[h][4 * q + 3]) + bq.w);
+                    }
+                }
                 uint4 lo, hi;
                 lo.x = relu_pack_bf16(__uint_as_float(r[h][0]), __uint_as_float(r[h][1]));
                 lo.y = relu_pack_bf16(__uint_as_float(r[h][2]), __uint_as_float(r[h][3]));
@@ -269,8 +296,10 @@ struct Actor {
                 *reinterpret_cast<uint4*>(row + (2 * c + 1) * kLbo) = hi;
             }
         }
-        *reinterpret_cast<uint4*>(row + 8 * kLbo) = make_uint4(0x00003F80u, 0u, 0u, 0u);     // column 64 = bf16(1.0): the bias column
-        *reinterpret_cast<uint4*>(row + 9 * kLbo) = make_uint4(0u, 0u, 0u, 0u);
+        if (!CANTOR_MLP_BIAS_IN_EPILOGUE) {
+            *reinterpret_cast<uint4*>(row + 8 * kLbo) = make_uint4(0x00003F80u, 0u, 0u, 0u);     // column 64 = bf16(1.0): the bias column
+            *reinterpret_cast<uint4*>(row + 9 * kLbo) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
 
     // The actor on this thread's observation; CTA-collective (every thread of the CTA must call it each step).
@@ -287,13 +316,14 @@ struct Actor {
         *reinterpret_cast<uint4*>(row) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
         *reinterpret_cast<uint4*>(row + kLbo) = make_uint4(pack_bf16(x[8], x[9]), pack_bf16(x[10], x[11]), pack_bf16(x[12], x[13]), pack_bf16(x[14], x[15]));
         run_layer<kK1 / 16>(smem_u32(a1), kSbo1, smem_u32(w1), kSbo1, instr_desc(kRows, kHidden));
-        hidden_epilogue();
-        run_layer<kK2 / 16>(smem_u32(a2), kSbo2, smem_u32(w2), kSbo2, instr_desc(kRows, kHidden));
-        hidden_epilogue();
-        run_layer<kK2 / 16>(smem_u32(a2), kSbo2, smem_u32(w3), kSbo2, instr_desc(kRows, kN3));
+        hidden_epilogue<false>();
+        run_layer<kKa / 16>(smem_u32(a2), kSboA2, smem_u32(w2), kSboA2, instr_desc(kRows, kHidden));
+        hidden_epilogue<CANTOR_MLP_BIAS_IN_EPILOGUE != 0>();
+        run_layer<kKa / 16>(smem_u32(a2), kSboA2, smem_u32(w3), kSboA2, instr_desc(kRows, kN3));
         uint32_t r0, r1;
         tmem_ld2(tmem + ((uint32_t)(m & ~31) << 16), r0, r1);
         tmem_ld_wait();
+        if (CANTOR_MLP_BIAS_IN_EPILOGUE) return make_float2(__uint_as_float(r0) + bias[kHidden], __uint_as_float(r1) + bias[kHidden + 1]);
         return make_float2(__uint_as_float(r0), __uint_as_float(r1));         // action means; the caller squashes them
     }
 };
